@@ -1,0 +1,95 @@
+"""Pins the C oracle (oracle/mcq_oracle.c) against the reference's own code compiled
+unmodified (oracle/_ref/libmcq_ref.so).  CPU only; skipped where oracle/_ref is absent."""
+import numpy as np
+import pytest
+
+import cpu_libs
+from problems import make_problem
+
+pytestmark = pytest.mark.skipif(not cpu_libs.have_ref(), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def libs():
+    return cpu_libs.Checker("oracle"), cpu_libs.Checker("ref")
+
+
+@pytest.mark.parametrize("gaps", [False, True])
+def test_full_state_bit_exact(libs, gaps):
+    orc, ref = libs
+    p = make_problem("toy", gaps=gaps)
+    so, sr = cpu_libs.full_state(orc, p), cpu_libs.full_state(ref, p)
+    for k in so:
+        assert np.array_equal(so[k], sr[k]), k
+
+
+@pytest.mark.parametrize("mode,which", [(0, 1), (0, -1), (1, 0), (2, -1), (2, 2)])
+def test_partial_emission_updates(libs, mode, which):
+    """window-restricted ESC / REV / BOTH updates on top of an existing table (mcmc_moves.c:789)."""
+    orc, ref = libs
+    p = make_problem("toy")
+    rng = np.random.default_rng(5)
+    outs = []
+    for chk in (orc, ref):
+        c2c = np.zeros((p.Q, 64, p.S)); A = np.zeros_like(c2c)
+        chk.emission(p, c2c, A, 0, p.S - 1, -1, 2)
+        esc = p.esc.copy(); rev = p.rev.copy()
+        esc[:, 30:55] *= 1.7; rev[0, 30:55] *= 0.6
+        chk.emission(p, c2c, A, 30, 54, which, mode, esc=esc, rev=rev)
+        outs.append((c2c, A))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("start,end", [(1, 1), (40, 40), (99, 99), (17, 63), (0, 99), (60, 99)])
+def test_window_forward_and_backward(libs, start, end):
+    orc, ref = libs
+    p = make_problem("toy", gaps=True)
+    base = cpu_libs.full_state(ref, p)
+    R2 = p.R.copy(); R2[start:end + 1] *= 1.9
+    for q in (0, 7, 49):
+        res = []
+        for chk in (orc, ref):
+            F = base["F"][q].copy(); Fn = base["Fn"][q].copy()
+            tF = np.full_like(F, np.nan); tFn = np.full_like(Fn, -7)
+            chk.forward(p, q, base["c2c"][q], R2, F, Fn, tFn, tF, start, end)
+            B = base["B"][q].copy(); Bn = base["Bn"][q].copy()
+            chk.backward(p, q, base["c2c"][q], R2, B, Bn, end)
+            res.append((tF[:, start:end + 1].copy(), tFn[start:end + 1].copy(), B, Bn, Fn))
+        for a, b in zip(*res):
+            assert np.array_equal(a, b)
+
+
+def test_hamming_and_closest_bit_exact(libs):
+    orc, ref = libs
+    p = make_problem("toy", gaps=True)
+    d = p.data
+    for q in range(0, p.Q, 7):
+        ho, hr = orc.hamming(d["ref_seqs"], d["query_seqs"][q]), ref.hamming(d["ref_seqs"], d["query_seqs"][q])
+        assert np.array_equal(ho, hr)
+        for n in (1, 5, 20, 21, 199):
+            cpu_libs.srandom(11 + q)
+            co = orc.closest(ho, n); ro = cpu_libs.libc_random()
+            cpu_libs.srandom(11 + q)
+            cr = ref.closest(hr, n); rr = cpu_libs.libc_random()
+            assert np.array_equal(co, cr)
+            assert ro == rr          # same number of random() draws consumed
+
+
+def test_closest_survey_quirks(libs):
+    """the element before the cut joins the tie window of the element after it."""
+    orc, ref = libs
+    ham = np.array([0, 2, 4, 6, 6, 6], np.int32)
+    seen = set()
+    for seed in range(40):
+        cpu_libs.srandom(seed); a = orc.closest(ham, 3)
+        cpu_libs.srandom(seed); b = ref.closest(ham, 3)
+        assert np.array_equal(a, b)
+        seen.add(int(a[2]))
+    assert list(a[:2]) == [0, 1] and seen == {2, 3, 4, 5}
+
+
+def test_hamming_survey_example(libs):
+    orc, ref = libs
+    refs = np.frombuffer(b"ACGTACGNNNNNacgt", np.uint8).reshape(4, 4).copy()
+    q = np.frombuffer(b"AC-T", np.uint8).copy()
+    assert list(orc.hamming(refs, q)) == [0, 2, 6, 0] == list(ref.hamming(refs, q))
