@@ -1,0 +1,632 @@
+// mcq_ctx.cu - the batched context API of include/mcq_b200.h: device memory, static-table
+// construction, parameter upload, proposal / accept sequencing, inspection, NCCL all-reduce.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "mcq_internal.cuh"
+#include "../../include/mcq_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+int mcq_fail(const char *file, int line, const char *what) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "[%s:%d] %s", file, line, what);
+  g_err = buf;
+  return 1;
+}
+#define CK(x)                                                                   \
+  do {                                                                          \
+    cudaError_t e_ = (x);                                                       \
+    if (e_ != cudaSuccess) return mcq_fail(__FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+#define REQUIRE(c, msg)                                         \
+  do {                                                          \
+    if (!(c)) return mcq_fail(__FILE__, __LINE__, msg);         \
+  } while (0)
+
+extern "C" const char *mcq_last_error(void) { return g_err.c_str(); }
+extern "C" int mcq_abi_version(void) { return 1; }
+extern "C" int mcq_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    mcq_fail(__FILE__, __LINE__, cudaGetErrorString(e));
+    return -1;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU users need no NCCL at all
+// ------------------------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return mcq_fail(__FILE__, __LINE__, "cannot dlopen libnccl.so.2");
+  g_nccl.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+    return mcq_fail(__FILE__, __LINE__, "libnccl lacks expected symbols");
+  return 0;
+}
+static const int kNcclDouble = 8;  // ncclFloat64
+static const int kNcclSum = 0;     // ncclSum
+
+// ------------------------------------------------------------------------------------------
+// the context
+// ------------------------------------------------------------------------------------------
+struct mcq_ctx {
+  mcq_dims d;
+  int Ls = 0, ES = 0;
+  cudaStream_t stream = nullptr;
+  size_t bytes = 0;
+  bool have_static = false, have_params = false, have_state = false;
+
+  // static (device)
+  uint8_t *G = nullptr, *slot_codon = nullptr, *slot_flags = nullptr, *cons_codon = nullptr;
+  uint8_t *query_codon = nullptr, *hla = nullptr;
+  int *eoff = nullptr;
+  // static (host mirrors)
+  std::vector<int> eoff_h;
+  std::vector<uint8_t> slot_codon_h, slot_flags_h;
+
+  McqModel m{};
+  double *F = nullptr, *B = nullptr, *T = nullptr;
+  int *Fn = nullptr, *Bn = nullptr, *Tn = nullptr;
+  double *E = nullptr, *A = nullptr, *Et = nullptr, *At = nullptr;
+  double *llk_cur = nullptr, *llk_prop = nullptr, *d_sum = nullptr;
+  double *h_sum = nullptr;   // pinned
+
+  McqOverride pending{};
+  bool has_pending = false;
+  int opt_sparse_esc = 0;
+
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int last_launches = 0, launches = 0;
+
+  ncclComm_t comm = nullptr;
+  int nranks = 1;
+  double logBIG = 0.0;
+};
+
+template <typename T>
+static int dev_alloc(mcq_ctx *c, T **p, size_t n) {
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void **)p, n * sizeof(T)));
+  c->bytes += n * sizeof(T);
+  return 0;
+}
+#define ALLOC(ptr, n)                          \
+  do {                                         \
+    if (dev_alloc(c, &(ptr), (n))) return 1;   \
+  } while (0)
+
+static McqStatic make_static(const mcq_ctx *c) {
+  McqStatic st;
+  st.Q = c->d.num_query; st.S = c->d.num_sites; st.L = c->d.closest_n; st.Ls = c->Ls;
+  st.N = c->d.total_num_refs; st.H = c->d.num_hla_types; st.ES = c->ES;
+  st.G = c->G; st.eoff = c->eoff; st.slot_codon = c->slot_codon; st.slot_flags = c->slot_flags;
+  st.cons_codon = c->cons_codon; st.query_codon = c->query_codon; st.hla = c->hla;
+  return st;
+}
+
+struct CallScope {   // brackets one API call for mcq_ctx_last_timing
+  mcq_ctx *c;
+  explicit CallScope(mcq_ctx *ctx) : c(ctx) {
+    c->launches = 0;
+    if (c->timing) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~CallScope() {
+    c->last_launches = c->launches;
+    if (c->timing) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+    }
+  }
+};
+
+extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
+  REQUIRE(out && dims, "null argument");
+  REQUIRE(dims->num_sites > 0 && dims->closest_n > 0 && dims->total_num_refs > 0 && dims->num_query > 0 &&
+              dims->num_hla_types > 0, "dimensions must be positive");
+  REQUIRE(dims->closest_n <= 1024, "closest_n > 1024 is not supported");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  REQUIRE(ndev > 0, "no CUDA device: libmcq_b200 has no CPU fallback");
+  REQUIRE(dims->device >= 0 && dims->device < ndev, "device ordinal out of range");
+  CK(cudaSetDevice(dims->device));
+  static bool tables_ready[64] = {false};
+  if (!tables_ready[dims->device]) {
+    CK(mcq_launch_tables_init());
+    tables_ready[dims->device] = true;
+  }
+  mcq_ctx *c = new mcq_ctx();
+  c->d = *dims;
+  c->Ls = (dims->closest_n + 15) / 16 * 16;
+  c->logBIG = log(MCQ_BIG);   // the host libm value the reference itself uses (mcmc_moves.c:223)
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  const size_t S = dims->num_sites, Q = dims->num_query, H = dims->num_hla_types;
+  ALLOC(c->m.R, S); ALLOC(c->m.omega, S); ALLOC(c->m.rate_out, S * 64);
+  ALLOC(c->m.esc, H * S); ALLOC(c->m.rev, S); ALLOC(c->m.prior, 64);
+  ALLOC(c->llk_cur, Q); ALLOC(c->llk_prop, Q); ALLOC(c->d_sum, 1);
+  CK(cudaMallocHost((void **)&c->h_sum, sizeof(double)));
+  c->pending.kind = -1;
+  *out = c;
+  return 0;
+}
+
+extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->d.device);
+  cudaStreamSynchronize(c->stream);
+  void *ptrs[] = {c->G, c->slot_codon, c->slot_flags, c->cons_codon, c->query_codon, c->hla, c->eoff,
+                  c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
+                  c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->E, c->A, c->Et, c->At,
+                  c->llk_cur, c->llk_prop, c->d_sum};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (c->h_sum) cudaFreeHost(c->h_sum);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" size_t mcq_ctx_device_bytes(const mcq_ctx *c) { return c ? c->bytes : 0; }
+
+extern "C" int mcq_ctx_enable_timing(mcq_ctx *c, int on) {
+  REQUIRE(c, "null context");
+  c->timing = on != 0;
+  return 0;
+}
+extern "C" int mcq_ctx_last_timing(const mcq_ctx *c, float *ms, int *launches) {
+  REQUIRE(c, "null context");
+  if (ms) *ms = c->last_ms;
+  if (launches) *launches = c->last_launches;
+  return 0;
+}
+extern "C" int mcq_ctx_set_option(mcq_ctx *c, int option, int value) {
+  REQUIRE(c, "null context");
+  if (option == MCQ_OPT_SPARSE_ESC) { c->opt_sparse_esc = value; return 0; }
+  return mcq_fail(__FILE__, __LINE__, "unknown option");
+}
+
+// ------------------------------------------------------------------------------------------
+// static data
+// ------------------------------------------------------------------------------------------
+extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const int *closest_refs,
+                                     const char *cons_query_nucls, const char *query_codons,
+                                     const char *hla_types, const char *consensus_codons,
+                                     const int *num_ref_site_codons, const char *ref_site_codons) {
+  REQUIRE(c, "null context");
+  REQUIRE(ref_triplets && closest_refs && cons_query_nucls && query_codons && hla_types &&
+              consensus_codons && num_ref_site_codons && ref_site_codons, "null argument");
+  REQUIRE(!c->have_static, "static data already uploaded");
+  CK(cudaSetDevice(c->d.device));
+  const int S = c->d.num_sites, Q = c->d.num_query, L = c->d.closest_n, N = c->d.total_num_refs,
+            H = c->d.num_hla_types;
+
+  // slot lists: the codons the panel shows at the site (ascending, amino_acids.c:155-176), plus
+  // the consensus codon when no reference shows it (create_codon_to_codon_HLA writes that row too)
+  c->eoff_h.assign(S + 1, 0);
+  std::vector<uint8_t> slot_of((size_t)S * 64, MCQ_NOSLOT);
+  for (int s = 0; s < S; s++) {
+    const int n = num_ref_site_codons[s];
+    REQUIRE(n >= 0 && n <= 64, "num_ref_site_codons out of range");
+    const int cons = (unsigned char)consensus_codons[s];
+    REQUIRE(cons < 64, "consensus codon out of range");
+    bool has_cons = false;
+    int k = 0;
+    for (int i = 0; i < n; i++) {
+      const int cd = (unsigned char)ref_site_codons[(size_t)s * 64 + i];
+      REQUIRE(cd < 64, "reference codon out of range");
+      REQUIRE(slot_of[(size_t)s * 64 + cd] == MCQ_NOSLOT, "duplicate codon in ref_site_codons");
+      slot_of[(size_t)s * 64 + cd] = (uint8_t)k++;
+      c->slot_codon_h.push_back((uint8_t)cd);
+      c->slot_flags_h.push_back((uint8_t)(1 | (cd == cons ? 2 : 0)));
+      has_cons |= (cd == cons);
+    }
+    if (!has_cons) {
+      slot_of[(size_t)s * 64 + cons] = (uint8_t)k++;
+      c->slot_codon_h.push_back((uint8_t)cons);
+      c->slot_flags_h.push_back(2);
+    }
+    c->eoff_h[s + 1] = c->eoff_h[s] + k;
+  }
+  c->ES = (c->eoff_h[S] + 1) / 2 * 2;
+
+  ALLOC(c->eoff, (size_t)S + 1);
+  ALLOC(c->slot_codon, c->slot_codon_h.size());
+  ALLOC(c->slot_flags, c->slot_flags_h.size());
+  ALLOC(c->cons_codon, (size_t)S);
+  ALLOC(c->query_codon, (size_t)Q * S);
+  ALLOC(c->hla, (size_t)Q * H);
+  ALLOC(c->G, (size_t)Q * S * c->Ls);
+  CK(cudaMemcpy(c->eoff, c->eoff_h.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->slot_codon, c->slot_codon_h.data(), c->slot_codon_h.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->slot_flags, c->slot_flags_h.data(), c->slot_flags_h.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->query_codon, query_codons, (size_t)Q * S, cudaMemcpyHostToDevice));
+  {
+    std::vector<uint8_t> bits((size_t)Q * H);
+    for (size_t i = 0; i < bits.size(); i++) bits[i] = (hla_types[i] == '1');
+    CK(cudaMemcpy(c->hla, bits.data(), bits.size(), cudaMemcpyHostToDevice));
+  }
+
+  // temporaries for the gather
+  int8_t *d_trip = nullptr, *d_cons = nullptr;
+  int *d_closest = nullptr;
+  uint8_t *d_slot_of = nullptr;
+  for (size_t i = 0; i < (size_t)Q * L; i++)
+    REQUIRE(closest_refs[i] >= 0 && closest_refs[i] < N, "closest_refs entry out of range");
+  CK(cudaMalloc((void **)&d_trip, (size_t)N * S));
+  CK(cudaMalloc((void **)&d_cons, (size_t)Q * 3 * S));
+  CK(cudaMalloc((void **)&d_closest, (size_t)Q * L * sizeof(int)));
+  CK(cudaMalloc((void **)&d_slot_of, (size_t)S * 64));
+  CK(cudaMemcpyAsync(d_trip, ref_triplets, (size_t)N * S, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_cons, cons_query_nucls, (size_t)Q * 3 * S, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_closest, closest_refs, (size_t)Q * L * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
+  CK(mcq_launch_gather(d_trip, d_closest, d_cons, d_slot_of, c->G, Q, S, L, c->Ls, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_trip); cudaFree(d_cons); cudaFree(d_closest); cudaFree(d_slot_of);
+
+  const size_t cells = (size_t)Q * S * c->Ls;
+  ALLOC(c->F, cells); ALLOC(c->B, cells); ALLOC(c->T, cells);
+  ALLOC(c->Fn, (size_t)Q * S); ALLOC(c->Bn, (size_t)Q * S); ALLOC(c->Tn, (size_t)Q * S);
+  const size_t rows = (size_t)Q * c->ES;
+  ALLOC(c->E, rows); ALLOC(c->A, rows); ALLOC(c->Et, rows); ALLOC(c->At, rows);
+  CK(cudaMemsetAsync(c->E, 0, rows * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->A, 0, rows * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->Et, 0, rows * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->At, 0, rows * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->Fn, 0, (size_t)Q * S * sizeof(int), c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->have_static = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+extern "C" int mcq_ctx_set_params(mcq_ctx *c, const mcq_params *p) {
+  REQUIRE(c && p, "null argument");
+  CK(cudaSetDevice(c->d.device));
+  const size_t S = c->d.num_sites, H = c->d.num_hla_types;
+  c->m.mu = p->mu; c->m.kappa = p->kappa; c->m.phi = p->phi;
+  if (p->prior_C2) CK(cudaMemcpyAsync(c->m.prior, p->prior_C2, 64 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (p->R) CK(cudaMemcpyAsync(c->m.R, p->R, S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (p->omega) CK(cudaMemcpyAsync(c->m.omega, p->omega, S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  std::vector<double> tr;
+  if (p->rate_out_of_codons) {
+    tr.resize(S * 64);
+    for (size_t cd = 0; cd < 64; cd++)
+      for (size_t s = 0; s < S; s++) tr[s * 64 + cd] = p->rate_out_of_codons[cd * S + s];
+    CK(cudaMemcpyAsync(c->m.rate_out, tr.data(), S * 64 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (p->HLA_select_esc) CK(cudaMemcpyAsync(c->m.esc, p->HLA_select_esc, H * S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (p->HLA_select_rev) CK(cudaMemcpyAsync(c->m.rev, p->HLA_select_rev, S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->have_params = true;
+  c->has_pending = false;
+  return 0;
+}
+
+extern "C" int mcq_ctx_get_params(mcq_ctx *c, double *mu, double *R, double *omega, double *rate_out,
+                                  double *esc, double *rev) {
+  REQUIRE(c, "null context");
+  CK(cudaSetDevice(c->d.device));
+  const size_t S = c->d.num_sites, H = c->d.num_hla_types;
+  CK(cudaStreamSynchronize(c->stream));
+  if (mu) *mu = c->m.mu;
+  if (R) CK(cudaMemcpy(R, c->m.R, S * sizeof(double), cudaMemcpyDeviceToHost));
+  if (omega) CK(cudaMemcpy(omega, c->m.omega, S * sizeof(double), cudaMemcpyDeviceToHost));
+  if (rate_out) {
+    std::vector<double> tr(S * 64);
+    CK(cudaMemcpy(tr.data(), c->m.rate_out, S * 64 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t cd = 0; cd < 64; cd++)
+      for (size_t s = 0; s < S; s++) rate_out[cd * S + s] = tr[s * 64 + cd];
+  }
+  if (esc) CK(cudaMemcpy(esc, c->m.esc, H * S * sizeof(double), cudaMemcpyDeviceToHost));
+  if (rev) CK(cudaMemcpy(rev, c->m.rev, S * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels sequencing helpers
+// ------------------------------------------------------------------------------------------
+static int run_emission(mcq_ctx *c, int start, int end, int which_hla, int mode, const McqOverride &ov,
+                        const double *Es, const double *As, double *Ed, double *Ad) {
+  EmisArgs a;
+  a.st = make_static(c); a.m = c->m; a.ov = ov;
+  a.start = start; a.end = end; a.which_hla = which_hla; a.mode = mode;
+  a.Esrc = Es; a.Asrc = As; a.Edst = Ed; a.Adst = Ad;
+  CK(mcq_launch_emission(a, c->stream));
+  c->launches++;
+  return 0;
+}
+
+static int run_forward(mcq_ctx *c, const double *E, int start, int end, const double *Fin, const int *Fn_in,
+                       double *Fout, int *Fn_out, int llk_mode, double *llk_out, int r_site, double r_value,
+                       bool sparse, int hla) {
+  FwdArgs a;
+  a.st = make_static(c);
+  a.E = E; a.R = c->m.R; a.r_site = r_site; a.r_value = r_value;
+  a.Fin = Fin; a.Fn_in = Fn_in; a.Fout = Fout; a.Fn_out = Fn_out;
+  a.start = start; a.end = end; a.llk_mode = llk_mode;
+  a.B = c->B; a.Bn = c->Bn; a.llk_out = llk_out; a.llk_keep = c->llk_cur;
+  a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
+  a.logBIG = c->logBIG;
+  CK(mcq_launch_forward(a, c->stream));
+  c->launches++;
+  return 0;
+}
+
+static int run_backward(mcq_ctx *c, int update, bool sparse, int hla) {
+  BwdArgs a;
+  a.st = make_static(c);
+  a.E = c->E; a.R = c->m.R; a.B = c->B; a.Bn = c->Bn; a.update = update;
+  a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
+  CK(mcq_launch_backward(a, c->stream));
+  c->launches++;
+  return 0;
+}
+
+// total over the shard (+ all ranks), brought to the host
+static int reduce_llk(mcq_ctx *c, const double *per_query, double *out) {
+  CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->stream));
+  c->launches++;
+  if (c->comm) {
+    int r = g_nccl.AllReduce(c->d_sum, c->d_sum, 1, kNcclDouble, kNcclSum, c->comm, c->stream);
+    if (r != 0) return mcq_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce failed");
+  }
+  CK(cudaMemcpyAsync(c->h_sum, c->d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (out) *out = *c->h_sum;
+  return 0;
+}
+
+#define READY(c)                                                                   \
+  do {                                                                             \
+    REQUIRE(c, "null context");                                                    \
+    REQUIRE((c)->have_static, "mcq_ctx_upload_static has not been called");        \
+    REQUIRE((c)->have_params, "mcq_ctx_set_params has not been called");           \
+    CK(cudaSetDevice((c)->d.device));                                              \
+  } while (0)
+
+extern "C" int mcq_ctx_emission(mcq_ctx *c, int start, int end, int which_hla, int mode) {
+  READY(c);
+  REQUIRE(start >= 0 && end < c->d.num_sites && start <= end, "site range");
+  REQUIRE(mode >= 0 && mode <= 2 && which_hla >= -1 && which_hla < c->d.num_hla_types, "mode / HLA");
+  CallScope scope(c);
+  McqOverride none{}; none.kind = -1;
+  if (run_emission(c, start, end, which_hla, mode, none, c->E, c->A, c->E, c->A)) return 1;
+  if (!c->timing) CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
+  READY(c);
+  CallScope scope(c);
+  const int S = c->d.num_sites;
+  McqOverride none{}; none.kind = -1;
+  if (with_emission && run_emission(c, 0, S - 1, -1, 2, none, c->E, c->A, c->E, c->A)) return 1;
+  if (run_forward(c, c->E, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (reduce_llk(c, c->llk_cur, llk)) return 1;
+  c->has_pending = false;
+  return 0;
+}
+
+extern "C" int mcq_ctx_backward_fill(mcq_ctx *c) {
+  READY(c);
+  CallScope scope(c);
+  if (run_backward(c, c->d.num_sites - 1, false, 0)) return 1;
+  if (!c->timing) CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int mcq_ctx_init_state(mcq_ctx *c, double *llk) {
+  READY(c);
+  CallScope scope(c);
+  const int S = c->d.num_sites;
+  McqOverride none{}; none.kind = -1;
+  if (run_emission(c, 0, S - 1, -1, 2, none, c->E, c->A, c->E, c->A)) return 1;
+  if (run_forward(c, c->E, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (run_backward(c, S - 1, false, 0)) return 1;
+  if (reduce_llk(c, c->llk_cur, llk)) return 1;
+  c->have_state = true;
+  c->has_pending = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// proposals
+// ------------------------------------------------------------------------------------------
+extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_llk) {
+  READY(c);
+  REQUIRE(p, "null proposal");
+  REQUIRE(c->have_state, "mcq_ctx_init_state has not been called");
+  const int S = c->d.num_sites;
+  McqOverride ov;
+  ov.kind = p->kind; ov.start = p->start; ov.end = p->end; ov.hla = p->hla; ov.split = p->split;
+  ov.v0 = p->value0; ov.v1 = p->value1;
+  if (p->kind == MCQ_PROP_MU) { ov.start = 0; ov.end = S - 1; }
+  REQUIRE(ov.start >= 0 && ov.end < S && ov.start <= ov.end, "proposal site range");
+  CallScope scope(c);
+  switch (p->kind) {
+    case MCQ_PROP_REC:
+      REQUIRE(ov.start == ov.end, "REC proposal covers one site");
+      if (run_forward(c, c->E, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, ov.start, ov.v0, false, 0)) return 1;
+      break;
+    case MCQ_PROP_SEL:
+      REQUIRE(ov.start == ov.end, "SEL proposal covers one site");
+      if (run_emission(c, ov.start, ov.end, -1, 2, ov, c->E, c->A, c->Et, c->At)) return 1;
+      if (run_forward(c, c->Et, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      break;
+    case MCQ_PROP_ESC: {
+      REQUIRE(ov.hla >= 0 && ov.hla < c->d.num_hla_types, "ESC proposal HLA index");
+      if (run_emission(c, ov.start, ov.end, ov.hla, 0, ov, c->E, c->A, c->Et, c->At)) return 1;
+      const bool sparse = c->opt_sparse_esc != 0;
+      if (run_forward(c, c->Et, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, sparse, ov.hla)) return 1;
+      break;
+    }
+    case MCQ_PROP_REV:
+      if (run_emission(c, ov.start, ov.end, -1, 1, ov, c->E, c->A, c->Et, c->At)) return 1;
+      if (run_forward(c, c->Et, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      break;
+    case MCQ_PROP_MU:
+      CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->E, c->A, c->Et, c->At, c->stream));
+      c->launches++;
+      if (run_forward(c, c->Et, 0, S - 1, c->F, c->Fn, c->T, c->Tn, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      break;
+    default:
+      return mcq_fail(__FILE__, __LINE__, "unknown proposal kind");
+  }
+  if (reduce_llk(c, c->llk_prop, sum_llk)) return 1;
+  c->pending = ov;
+  c->has_pending = true;
+  return 0;
+}
+
+extern "C" int mcq_ctx_reject(mcq_ctx *c) {
+  REQUIRE(c, "null context");
+  c->has_pending = false;
+  return 0;
+}
+
+template <typename T>
+static void swap_ptr(T *&a, T *&b) { T *t = a; a = b; b = t; }
+
+extern "C" int mcq_ctx_accept(mcq_ctx *c) {
+  READY(c);
+  REQUIRE(c->has_pending, "no proposal to accept");
+  const int S = c->d.num_sites;
+  const McqOverride ov = c->pending;
+  CallScope scope(c);
+  const McqStatic st = make_static(c);
+  if (ov.kind == MCQ_PROP_MU) {
+    // the reference swaps the roles of the tmp and current arrays (mcmc_moves.c:1166-1169)
+    swap_ptr(c->F, c->T); swap_ptr(c->Fn, c->Tn); swap_ptr(c->E, c->Et); swap_ptr(c->A, c->At);
+    c->m.mu = ov.v0;
+    if (run_backward(c, S - 1, false, 0)) return 1;
+  } else {
+    const bool sparse = (ov.kind == MCQ_PROP_ESC) && c->opt_sparse_esc != 0;
+    CK(mcq_launch_commit_params(st, c->m, ov, c->stream));
+    c->launches++;
+    if (ov.kind != MCQ_PROP_REC) {
+      CK(mcq_launch_commit_rows(st, c->Et, c->At, c->E, c->A, c->eoff_h[ov.start], c->eoff_h[ov.end + 1], c->stream));
+      c->launches++;
+    }
+    CK(mcq_launch_commit_cols(st, c->T, c->Tn, c->F, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
+    c->launches++;
+    if (ov.end + 1 < S)
+      if (run_forward(c, c->E, ov.end + 1, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
+    if (run_backward(c, ov.end, sparse, ov.hla)) return 1;
+  }
+  swap_ptr(c->llk_cur, c->llk_prop);
+  c->has_pending = false;
+  if (!c->timing) CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// inspection
+// ------------------------------------------------------------------------------------------
+extern "C" int mcq_ctx_get_matrix(mcq_ctx *c, int which, int q, double *out, int *rnorm) {
+  REQUIRE(c && c->have_static, "context not ready");
+  REQUIRE(q >= 0 && q < c->d.num_query, "query index");
+  CK(cudaSetDevice(c->d.device));
+  const int S = c->d.num_sites, L = c->d.closest_n, Ls = c->Ls;
+  const double *src = which == MCQ_BUF_F ? c->F : which == MCQ_BUF_B ? c->B : c->T;
+  const int *nsrc = which == MCQ_BUF_F ? c->Fn : which == MCQ_BUF_B ? c->Bn : c->Tn;
+  CK(cudaStreamSynchronize(c->stream));
+  if (out) {
+    std::vector<double> slab((size_t)S * Ls);
+    CK(cudaMemcpy(slab.data(), src + (size_t)q * S * Ls, slab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < L; r++)
+      for (int s = 0; s < S; s++) out[(size_t)r * S + s] = slab[(size_t)s * Ls + r];
+  }
+  if (rnorm) CK(cudaMemcpy(rnorm, nsrc + (size_t)q * S, S * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int mcq_ctx_get_table(mcq_ctx *c, int which, int q, double *out) {
+  REQUIRE(c && c->have_static && out, "context not ready");
+  REQUIRE(q >= 0 && q < c->d.num_query, "query index");
+  CK(cudaSetDevice(c->d.device));
+  const int S = c->d.num_sites;
+  const double *src = which == MCQ_TAB_C2C ? c->E : which == MCQ_TAB_A ? c->A : which == MCQ_TAB_TMP_C2C ? c->Et : c->At;
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<double> row(c->ES);
+  CK(cudaMemcpy(row.data(), src + (size_t)q * c->ES, row.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof(double) * 64 * S);
+  for (int s = 0; s < S; s++)
+    for (int k = c->eoff_h[s]; k < c->eoff_h[s + 1]; k++) out[(size_t)c->slot_codon_h[k] * S + s] = row[k];
+  return 0;
+}
+
+extern "C" int mcq_ctx_get_query_llk(mcq_ctx *c, int proposed, double *out) {
+  REQUIRE(c && out, "null argument");
+  CK(cudaSetDevice(c->d.device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out, proposed ? c->llk_prop : c->llk_cur, c->d.num_query * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU
+// ------------------------------------------------------------------------------------------
+extern "C" int mcq_comm_unique_id(unsigned char id[128]) {
+  if (nccl_load()) return 1;
+  ncclUniqueId u;
+  int r = g_nccl.GetUniqueId(&u);
+  if (r != 0) return mcq_fail(__FILE__, __LINE__, "ncclGetUniqueId failed");
+  memcpy(id, u.internal, 128);
+  return 0;
+}
+
+extern "C" int mcq_ctx_attach_comm(mcq_ctx *c, int nranks, int rank, const unsigned char id[128]) {
+  REQUIRE(c && id, "null argument");
+  REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "rank / nranks");
+  if (nccl_load()) return 1;
+  CK(cudaSetDevice(c->d.device));
+  ncclUniqueId u;
+  memcpy(u.internal, id, 128);
+  int r = g_nccl.CommInitRank(&c->comm, nranks, u, rank);
+  if (r != 0) return mcq_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclCommInitRank failed");
+  c->nranks = nranks;
+  return 0;
+}

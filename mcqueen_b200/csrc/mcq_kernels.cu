@@ -1,0 +1,662 @@
+// mcq_kernels.cu - the CUDA kernels of the McQueen likelihood path (sm_100a).
+//
+//   K0  k_gather        triplet_to_codon (amino_acids.c:50-66) evaluated once into G[q][s][r]
+//   K3  k_emission      create_codon_to_codon_HLA (mcmc_moves.c:33-170), compact rows
+//   K3b k_mu_rescale    the mu-rescale of mutation_move (mcmc_moves.c:1082-1111)
+//   K4  k_forward<NJ>   initialise_F / update_F (forward_backward.c:11-171) + K6 llk epilogue
+//   K5  k_backward<NJ>  update_B (forward_backward.c:173-244)
+//   K7  k_commit_*      accept-commit copies (mcmc_moves.c:263-265,447-449,959-965)
+//   K6b k_sum           cross-query total (mcmc_moves.c:222 etc.), fixed-shape reduction
+//
+// All arithmetic is fp64 and the library is compiled with -fmad=false: the reference is built
+// without FMA contraction (its Makefile:22 gives -O3 only), and with contraction off the emission
+// rows are bit-identical to the reference's and a cell update differs from it only through the
+// order of the per-site sum over copy states (a warp butterfly here, ascending r there).
+#include "mcq_internal.cuh"
+#include "../../include/mcq_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// substitution classes, derived from the genetic code on the host (mcq_tables.cpp) and copied
+// here once: 0 = none / multi-step, 1 = NS_TS, 2 = NS_TV, 3 = S_TS, 4 = S_TV
+// (constants.c:424-688 stores these as four 64x64 0/1 int matrices).
+// ------------------------------------------------------------------------------------------
+__device__ uint8_t d_cls[64 * 64];
+__device__ uint8_t d_cnt[4][64];     // alpha_S, alpha_V, beta_S, beta_V (constants.c:405-422)
+
+extern "C" void mcq_host_tables(uint8_t cls[64 * 64], uint8_t cnt[4][64]);
+
+cudaError_t mcq_launch_tables_init() {
+  static uint8_t cls[64 * 64];
+  static uint8_t cnt[4][64];
+  mcq_host_tables(cls, cnt);
+  cudaError_t e = cudaMemcpyToSymbol(d_cls, cls, sizeof(cls));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(d_cnt, cnt, sizeof(cnt));
+}
+
+// omega*(kappa*NS_TS + NS_TV) + kappa*S_TS + S_TV for one codon pair.  Exactly one class bit is
+// set per pair, so the reference's expression (mcmc_moves.c:85-88) reduces, bit for bit, to one
+// of {omega*kappa, omega, kappa, 1, 0}.
+__device__ __forceinline__ double step_rate(double omega, double kappa, int c1, int c2) {
+  switch (d_cls[c1 * 64 + c2]) {
+    case 1: return omega * kappa;
+    case 2: return omega;
+    case 3: return kappa;
+    case 4: return 1.0;
+    default: return 0.0;
+  }
+}
+// kappa*NS_TS + NS_TV for one pair
+__device__ __forceinline__ double ns_rate(double kappa, int c1, int c2) {
+  uint8_t c = d_cls[c1 * 64 + c2];
+  return c == 1 ? kappa : (c == 2 ? 1.0 : 0.0);
+}
+__device__ __forceinline__ double s_rate(double kappa, int c1, int c2) {
+  uint8_t c = d_cls[c1 * 64 + c2];
+  return c == 3 ? kappa : (c == 4 ? 1.0 : 0.0);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: gathered codon-slot table.  Tile = 32 sites x 32 states through shared memory: reads of
+// ref_triplets run along a reference's row (sites), writes of G along states.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_triplets,
+                                                const int *__restrict__ closest,
+                                                const int8_t *__restrict__ cons_nucls,
+                                                const uint8_t *__restrict__ slot_of,
+                                                uint8_t *__restrict__ G, int S, int L, int Ls) {
+  __shared__ uint8_t tile[32][33];
+  const int q = blockIdx.z;
+  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows per pass
+  const int s = s0 + tx;
+  int c0 = 0, c1 = 0, c2 = 0;
+  if (s < S) {
+    const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
+    c0 = cn[0]; c1 = cn[1]; c2 = cn[2];
+  }
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int rr = ty + 8 * p, r = r0 + rr;
+    uint8_t slot = MCQ_NOSLOT;
+    if (s < S && r < L) {
+      const int ref = closest[(size_t)q * L + r];
+      const int t = ref_triplets[(size_t)ref * S + s];
+      int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
+      if (d0 == 4) d0 = c0;
+      if (d1 == 4) d1 = c1;
+      if (d2 == 4) d2 = c2;
+      slot = slot_of[s * 64 + (d0 * 16 + d1 * 4 + d2)];
+    }
+    tile[rr][tx] = slot;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const int ss = ty + 8 * p, so = s0 + ss, r = r0 + tx;
+    if (so < S && r < Ls) G[((size_t)q * S + so) * Ls + r] = tile[tx][ss];
+  }
+}
+
+cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, const int8_t *cons_nucls,
+                              const uint8_t *slot_of, uint8_t *G, int Q, int S, int L, int Ls,
+                              cudaStream_t stream) {
+  // gridDim.z is limited to 65535: walk the queries in slabs
+  for (int q0 = 0; q0 < Q; q0 += 65535) {
+    int nq = Q - q0 < 65535 ? Q - q0 : 65535;
+    dim3 grid((S + 31) / 32, (Ls + 31) / 32, nq);
+    k_gather<<<grid, 256, 0, stream>>>(ref_triplets, closest + (size_t)q0 * L,
+                                       cons_nucls + (size_t)q0 * 3 * S, slot_of,
+                                       G + (size_t)q0 * S * Ls, S, L, Ls);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// parameter views with the proposal override folded in
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double eff_omega(const McqModel &m, const McqOverride &ov, int s) {
+  return (ov.kind == MCQ_PROP_SEL && s == ov.start) ? ov.v0 : m.omega[s];
+}
+__device__ __forceinline__ double eff_esc(const McqModel &m, const McqOverride &ov, int h, int s, int S) {
+  if (ov.kind == MCQ_PROP_ESC && h == ov.hla && s >= ov.start && s <= ov.end)
+    return s < ov.split ? ov.v0 : ov.v1;
+  return m.esc[(size_t)h * S + s];
+}
+__device__ __forceinline__ double eff_rev(const McqModel &m, const McqOverride &ov, int s) {
+  if (ov.kind == MCQ_PROP_REV && s >= ov.start && s <= ov.end) return s < ov.split ? ov.v0 : ov.v1;
+  return m.rev[s];
+}
+// rate_out_of_codons[c][s]; a SEL proposal recomputes it for the codons the panel shows at the
+// site (mcmc_moves.c:345-352), in the association order of dmodel.c:842-848
+__device__ __forceinline__ double eff_rate_out(const McqModel &m, const McqOverride &ov, int s, int c,
+                                               bool in_list) {
+  if (ov.kind == MCQ_PROP_SEL && s == ov.start && in_list)
+    return m.kappa * d_cnt[2][c] + d_cnt[3][c] + ov.v0 * (m.kappa * d_cnt[0][c] + d_cnt[1][c]);
+  return m.rate_out[(size_t)s * 64 + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: emission rows.  One thread per (query, site) of the range; it walks the site's slots.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_emission(const EmisArgs a) {
+  const int W = a.end - a.start + 1;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)a.st.Q * W) return;
+  const int q = (int)(idx / W), s = a.start + (int)(idx % W);
+  const int S = a.st.S, H = a.st.H;
+  const McqModel &m = a.m;
+  const uint8_t *hla = a.st.hla + (size_t)q * H;
+  const int k0 = a.st.eoff[s], k1 = a.st.eoff[s + 1];
+  const size_t row = (size_t)q * a.st.ES;
+  const bool copy_through = (a.Edst != a.Esrc);
+
+  // an ESC update of one HLA leaves non-carriers untouched (mcmc_moves.c:61-62)
+  const bool skip = (a.mode == 0 && a.which_hla >= 0 && hla[a.which_hla] == 0);
+  if (skip) {
+    if (copy_through)
+      for (int k = k0; k < k1; k++) { a.Edst[row + k] = a.Esrc[row + k]; a.Adst[row + k] = a.Asrc[row + k]; }
+    return;
+  }
+
+  const int cons = a.st.cons_codon[s], to = a.st.query_codon[(size_t)q * S + s];
+  const double omega = eff_omega(m, a.ov, s);
+  const double kappa = m.kappa, phi = m.phi, mu = m.mu;
+  const double N = (double)a.st.N;
+  double esc_prod = 1.0;
+  for (int h = 0; h < H; h++)
+    if (hla[h]) esc_prod *= eff_esc(m, a.ov, h, s, S);
+  const double rev = eff_rev(m, a.ov, s);
+  const double back = (1 - phi) * m.prior[to];
+
+  for (int k = k0; k < k1; k++) {
+    const int c1 = a.st.slot_codon[k];
+    const uint8_t fl = a.st.slot_flags[k];
+    const bool in_list = fl & 1, is_cons = fl & 2;
+    double A, v;
+    bool done = false;
+    if (!is_cons && in_list && a.mode != 0) {
+      // reversion part: a non-consensus codon of the panel (mcmc_moves.c:78-124)
+      const double rate = eff_rate_out(m, a.ov, s, c1, in_list) + (rev - 1) * step_rate(omega, kappa, c1, cons);
+      A = 1 - N / (N + rate * 4 * mu);
+      const double gamma = phi / rate;
+      const double mm = step_rate(omega, kappa, c1, to);
+      if (to == cons) v = A * (gamma * rev * mm + back);
+      else {
+        v = A * (gamma * mm + back);
+        if (c1 == to) v += (1 - A);
+      }
+      done = true;
+    } else if (is_cons && a.mode != 1) {
+      // escape part: the consensus row (mcmc_moves.c:125-167)
+      const double nsum = kappa * d_cnt[0][cons] + d_cnt[1][cons];
+      const double rate = eff_rate_out(m, a.ov, s, cons, in_list) + (esc_prod - 1) * omega * nsum;
+      A = 1 - N / (N + rate * 4 * mu);
+      if (cons == 15 || cons == 35) {
+        const double gamma = phi / nsum;
+        v = A * (gamma * ns_rate(kappa, cons, to) + back);
+      } else {
+        const double gamma = phi / rate;
+        v = A * (gamma * (esc_prod * omega * ns_rate(kappa, cons, to) + s_rate(kappa, cons, to)) + back);
+      }
+      if (to == cons) v = (1 - A) * (1 - back) + back;
+      done = true;
+    }
+    if (done) { a.Edst[row + k] = v; a.Adst[row + k] = A; }
+    else if (copy_through) { a.Edst[row + k] = a.Esrc[row + k]; a.Adst[row + k] = a.Asrc[row + k]; }
+  }
+}
+
+cudaError_t mcq_launch_emission(const EmisArgs &a, cudaStream_t stream) {
+  const size_t n = (size_t)a.st.Q * (a.end - a.start + 1);
+  k_emission<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b: mu rescale (mcmc_moves.c:1082-1111).  The reference walks ref_site_codons only; the
+// consensus slot of a site whose consensus codon no reference shows is rescaled as well (the
+// reference leaves that tmp entry unwritten - uninitialised memory, SURVEY.md §8c hazard 1).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mu_rescale(const McqStatic st, const McqModel m, double mu_new,
+                                                    const double *__restrict__ E, const double *__restrict__ A,
+                                                    double *__restrict__ Eo, double *__restrict__ Ao) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)st.Q * st.S) return;
+  const int q = (int)(idx / st.S), s = (int)(idx % st.S);
+  const int to = st.query_codon[(size_t)q * st.S + s];
+  const double N = (double)st.N;
+  const size_t row = (size_t)q * st.ES;
+  for (int k = st.eoff[s]; k < st.eoff[s + 1]; k++) {
+    const int c1 = st.slot_codon[k];
+    const double a = A[row + k];
+    double rate = 0.0;
+    if (a != 0) rate = (N / (1 - a) - N) / (4 * m.mu);
+    const double an = 1 - N / (N + rate * 4 * mu_new);
+    double v;
+    if (to != c1) v = (a == 0) ? 0.0 : E[row + k] * an / a;
+    else v = 1 - an + (1 - m.phi) * m.prior[c1] * an;
+    Ao[row + k] = an;
+    Eo[row + k] = v;
+  }
+}
+
+cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new,
+                                  const double *E, const double *A, double *Eo, double *Ao,
+                                  cudaStream_t stream) {
+  const size_t n = (size_t)st.Q * st.S;
+  k_mu_rescale<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(st, m, mu_new, E, A, Eo, Ao);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: forward recursion.  One warp per query; lane l holds states 64j+2l, 64j+2l+1 (j < NJ) of
+// the running column in registers.  Per site: one butterfly all-reduce (column sum, which both
+// decides the rescale and is the next site's recombination sum), one u16 load of G and one
+// 16-byte streaming store of F per lane per j, emission values gathered from the query's
+// compact row (L1-resident).
+// ------------------------------------------------------------------------------------------
+template <int NJ>
+__global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
+  const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= a.st.Q) return;
+  if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) {
+    if (lane == 0 && a.llk_out != nullptr) a.llk_out[q] = a.llk_keep[q];
+    return;
+  }
+  const int S = a.st.S, L = a.st.L, Ls = a.st.Ls;
+  const size_t qoff = (size_t)q * S * Ls;
+  const uint8_t *__restrict__ Gq = a.st.G + qoff;
+  const double *__restrict__ Eq = a.E + (size_t)q * a.st.ES;
+  const int *__restrict__ eoff = a.st.eoff;
+  double *__restrict__ Fo = a.Fout + qoff;
+  int *__restrict__ Fno = a.Fn_out + (size_t)q * S;
+  const double Nd = (double)a.st.N;
+
+  int r0[NJ];
+  bool inrow[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) { r0[j] = 64 * j + 2 * lane; inrow[j] = r0[j] < Ls; }
+
+  double p0[NJ], p1[NJ];   // the running column
+  int s = a.start, cnt;
+  double tot;
+
+  if (s == 0) {
+    // column 0 is the bare emission and is never rescaled (forward_backward.c:27-39,102-111)
+    const int eo = eoff[0];
+    double loc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      p0[j] = 0.0; p1[j] = 0.0;
+      if (inrow[j]) {
+        const unsigned gg = *reinterpret_cast<const uint16_t *>(Gq + r0[j]);
+        const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
+        if (g0 != MCQ_NOSLOT) p0[j] = Eq[eo + g0];
+        if (g1 != MCQ_NOSLOT) p1[j] = Eq[eo + g1];
+        __stcs(reinterpret_cast<double2 *>(Fo + r0[j]), make_double2(p0[j], p1[j]));
+      }
+      loc += p0[j]; loc += p1[j];
+    }
+    cnt = 0;
+    if (lane == 0) {
+      Fno[0] = 0;
+      // update_F with start 0 also zeroes the input counter (forward_backward.c:109)
+      if (a.Fn_in != nullptr) const_cast<int *>(a.Fn_in)[(size_t)q * S] = 0;
+    }
+    tot = warp_sum(loc);
+    s = 1;
+  } else {
+    const double *__restrict__ Fi = a.Fin + qoff + (size_t)(s - 1) * Ls;
+    double loc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      p0[j] = 0.0; p1[j] = 0.0;
+      if (inrow[j]) {
+        const double2 v = *reinterpret_cast<const double2 *>(Fi + r0[j]);
+        p0[j] = v.x; p1[j] = v.y;
+      }
+      loc += p0[j]; loc += p1[j];
+    }
+    cnt = a.Fn_in[(size_t)q * S + s - 1];
+    tot = warp_sum(loc);
+  }
+
+  // G of the current site is fetched one site ahead
+  unsigned gcur[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++)
+    gcur[j] = (inrow[j] && s <= a.end) ? *reinterpret_cast<const uint16_t *>(Gq + (size_t)s * Ls + r0[j]) : 0xFFFFu;
+
+  for (; s <= a.end; ++s) {
+    const int eo = eoff[s];
+    double e0[NJ], e1[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const unsigned g0 = gcur[j] & 0xFF, g1 = gcur[j] >> 8;
+      e0[j] = (g0 != MCQ_NOSLOT) ? Eq[eo + g0] : 0.0;
+      e1[j] = (g1 != MCQ_NOSLOT) ? Eq[eo + g1] : 0.0;
+    }
+    if (s < a.end) {
+#pragma unroll
+      for (int j = 0; j < NJ; j++)
+        if (inrow[j]) gcur[j] = __ldcs(reinterpret_cast<const uint16_t *>(Gq + (size_t)(s + 1) * Ls + r0[j]));
+    }
+    const double Rs = (s == a.r_site) ? a.r_value : a.R[s];
+    const double jump = tot * Rs / Nd;          // forward_backward.c:138
+    const double stay = 1 - Rs;
+    double loc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      double v0 = jump; v0 += stay * p0[j]; v0 *= e0[j];
+      double v1 = jump; v1 += stay * p1[j]; v1 *= e1[j];
+      p0[j] = v0; p1[j] = v1;
+      loc += v0; loc += v1;
+    }
+    tot = warp_sum(loc);
+    if (tot < MCQ_BIGI) {                       // forward_backward.c:163-167
+      ++cnt;
+#pragma unroll
+      for (int j = 0; j < NJ; j++) { p0[j] *= MCQ_BIG; p1[j] *= MCQ_BIG; }
+      tot *= MCQ_BIG;
+    }
+    double *__restrict__ Fs = Fo + (size_t)s * Ls;
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + r0[j]), make_double2(p0[j], p1[j]));
+    if (lane == 0) Fno[s] = cnt;
+  }
+
+  // K6 epilogue: the per-query log-likelihood at the last column of the range
+  if (a.llk_mode != 0) {
+    double dot;
+    int nrm = cnt;
+    if (a.llk_mode == 1) {                      // mcmc_moves.c:220-223
+      const double *__restrict__ Bc = a.B + qoff + (size_t)a.end * Ls;
+      double loc = 0.0;
+#pragma unroll
+      for (int j = 0; j < NJ; j++)
+        if (inrow[j]) {
+          const double2 b = *reinterpret_cast<const double2 *>(Bc + r0[j]);
+          loc += p0[j] * b.x; loc += p1[j] * b.y;
+        }
+      dot = warp_sum(loc);
+      nrm += a.Bn[(size_t)q * S + a.end];
+    } else {                                    // dmodel.c:899-901, mcmc_moves.c:1129-1134
+      dot = tot;
+    }
+    if (lane == 0) a.llk_out[q] = log(dot) - nrm * a.logBIG;
+  }
+  (void)L;
+}
+
+cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
+  const int nj = (a.st.Ls + 63) / 64;
+  const unsigned blocks = (unsigned)(((size_t)a.st.Q * 32 + 127) / 128);
+  if (nj <= 1) k_forward<1><<<blocks, 128, 0, stream>>>(a);
+  else if (nj <= 2) k_forward<2><<<blocks, 128, 0, stream>>>(a);
+  else if (nj <= 4) k_forward<4><<<blocks, 128, 0, stream>>>(a);
+  else if (nj <= 8) k_forward<8><<<blocks, 128, 0, stream>>>(a);
+  else if (nj <= 16) k_forward<16><<<blocks, 128, 0, stream>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: backward recursion, same mapping, descending sites.  b = B[.][s+1] (as stored), e = the
+// emission at s+1, sx = sum_r b*e.  The column sum of the new column and the next sx are
+// reduced together in one butterfly.
+// ------------------------------------------------------------------------------------------
+template <int NJ>
+__global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
+  const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= a.st.Q) return;
+  if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) return;
+  const int S = a.st.S, L = a.st.L, Ls = a.st.Ls;
+  const size_t qoff = (size_t)q * S * Ls;
+  const uint8_t *__restrict__ Gq = a.st.G + qoff;
+  const double *__restrict__ Eq = a.E + (size_t)q * a.st.ES;
+  const int *__restrict__ eoff = a.st.eoff;
+  double *__restrict__ Bq = a.B + qoff;
+  int *__restrict__ Bnq = a.Bn + (size_t)q * S;
+  const double Nd = (double)a.st.N;
+
+  int r0[NJ];
+  bool inrow[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) { r0[j] = 64 * j + 2 * lane; inrow[j] = r0[j] < Ls; }
+
+  double b0[NJ], b1[NJ], e0[NJ], e1[NJ];
+  int s = a.update, cnt;
+  if (s == S - 1) {                             // forward_backward.c:197-203
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      b0[j] = (r0[j] < L) ? 1.0 : 0.0;
+      b1[j] = (r0[j] + 1 < L) ? 1.0 : 0.0;
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bq + (size_t)s * Ls + r0[j]), make_double2(b0[j], b1[j]));
+    }
+    cnt = 0;
+    if (lane == 0) Bnq[s] = 0;
+    s--;
+  } else {
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      b0[j] = 0.0; b1[j] = 0.0;
+      if (inrow[j]) {
+        const double2 v = *reinterpret_cast<const double2 *>(Bq + (size_t)(s + 1) * Ls + r0[j]);
+        b0[j] = v.x; b1[j] = v.y;
+      }
+    }
+    cnt = Bnq[s + 1];
+  }
+  if (s < 0) return;
+  // emission at s+1 and sx
+  double sx;
+  {
+    const int eo = eoff[s + 1];
+    double loc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      unsigned gg = 0xFFFFu;
+      if (inrow[j]) gg = *reinterpret_cast<const uint16_t *>(Gq + (size_t)(s + 1) * Ls + r0[j]);
+      const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
+      e0[j] = (g0 != MCQ_NOSLOT) ? Eq[eo + g0] : 0.0;
+      e1[j] = (g1 != MCQ_NOSLOT) ? Eq[eo + g1] : 0.0;
+      loc += b0[j] * e0[j]; loc += b1[j] * e1[j];
+    }
+    sx = warp_sum(loc);
+  }
+  unsigned gcur[NJ];   // G at site s (needed for the NEXT iteration's emission)
+#pragma unroll
+  for (int j = 0; j < NJ; j++)
+    gcur[j] = inrow[j] ? *reinterpret_cast<const uint16_t *>(Gq + (size_t)s * Ls + r0[j]) : 0xFFFFu;
+
+  for (; s >= 0; --s) {
+    const double Rn = a.R[s + 1];
+    const double jump = sx * Rn / Nd;           // forward_backward.c:219
+    const double stay = 1 - Rn;
+    // emission at s (for the next step's products)
+    double n0[NJ], n1[NJ];
+    const int eo = eoff[s];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const unsigned g0 = gcur[j] & 0xFF, g1 = gcur[j] >> 8;
+      n0[j] = (g0 != MCQ_NOSLOT) ? Eq[eo + g0] : 0.0;
+      n1[j] = (g1 != MCQ_NOSLOT) ? Eq[eo + g1] : 0.0;
+    }
+    if (s > 0) {
+#pragma unroll
+      for (int j = 0; j < NJ; j++)
+        if (inrow[j]) gcur[j] = __ldcs(reinterpret_cast<const uint16_t *>(Gq + (size_t)(s - 1) * Ls + r0[j]));
+    }
+    double locv = 0.0, locy = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      // pad states (r >= L) must stay 0: they would otherwise pick up `jump`
+      double v0 = jump; v0 += stay * b0[j] * e0[j];
+      double v1 = jump; v1 += stay * b1[j] * e1[j];
+      if (r0[j] >= L) v0 = 0.0;
+      if (r0[j] + 1 >= L) v1 = 0.0;
+      b0[j] = v0; b1[j] = v1;
+      locv += v0; locv += v1;
+      locy += v0 * n0[j]; locy += v1 * n1[j];
+      e0[j] = n0[j]; e1[j] = n1[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      locv += __shfl_xor_sync(0xffffffffu, locv, o);
+      locy += __shfl_xor_sync(0xffffffffu, locy, o);
+    }
+    sx = locy;
+    if (locv < MCQ_BIGI) {                      // forward_backward.c:236-242
+      ++cnt;
+#pragma unroll
+      for (int j = 0; j < NJ; j++) { b0[j] *= MCQ_BIG; b1[j] *= MCQ_BIG; }
+      sx *= MCQ_BIG;
+    }
+    double *__restrict__ Bs = Bq + (size_t)s * Ls;
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bs + r0[j]), make_double2(b0[j], b1[j]));
+    if (lane == 0) Bnq[s] = cnt;
+  }
+}
+
+cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream) {
+  const int nj = (a.st.Ls + 63) / 64;
+  const unsigned blocks = (unsigned)(((size_t)a.st.Q * 32 + 127) / 128);
+  if (nj <= 1) k_backward<1><<<blocks, 128, 0, stream>>>(a);
+  else if (nj <= 2) k_backward<2><<<blocks, 128, 0, stream>>>(a);
+  else if (nj <= 4) k_backward<4><<<blocks, 128, 0, stream>>>(a);
+  else if (nj <= 8) k_backward<8><<<blocks, 128, 0, stream>>>(a);
+  else if (nj <= 16) k_backward<16><<<blocks, 128, 0, stream>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: accept-commit copies
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_commit_cols(const McqStatic st, const double *__restrict__ T,
+                                                     const int *__restrict__ Tn, double *__restrict__ F,
+                                                     int *__restrict__ Fn, int start, int end,
+                                                     const uint8_t *__restrict__ active, int active_hla) {
+  const int q = blockIdx.y;
+  if (active != nullptr && active[(size_t)q * st.H + active_hla] == 0) return;
+  const int W = end - start + 1;
+  const size_t base = ((size_t)q * st.S + start) * st.Ls;
+  const size_t n2 = (size_t)W * st.Ls / 2;
+  const double2 *__restrict__ src = reinterpret_cast<const double2 *>(T + base);
+  double2 *__restrict__ dst = reinterpret_cast<double2 *>(F + base);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+  if (blockIdx.x == 0)
+    for (int s = start + threadIdx.x; s <= end; s += blockDim.x)
+      Fn[(size_t)q * st.S + s] = Tn[(size_t)q * st.S + s];
+}
+
+cudaError_t mcq_launch_commit_cols(const McqStatic &st, const double *T, const int *Tn, double *F, int *Fn,
+                                   int start, int end, const uint8_t *active, int active_hla,
+                                   cudaStream_t stream) {
+  const size_t n2 = (size_t)(end - start + 1) * st.Ls / 2;
+  unsigned bx = (unsigned)((n2 + 255) / 256);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  for (int q0 = 0; q0 < st.Q; q0 += 65535) {
+    McqStatic s2 = st;
+    int nq = st.Q - q0 < 65535 ? st.Q - q0 : 65535;
+    dim3 grid(bx, nq);
+    s2.Q = nq;
+    k_commit_cols<<<grid, 256, 0, stream>>>(s2, T + (size_t)q0 * st.S * st.Ls, Tn + (size_t)q0 * st.S,
+                                            F + (size_t)q0 * st.S * st.Ls, Fn + (size_t)q0 * st.S, start, end,
+                                            active ? active + (size_t)q0 * st.H : nullptr, active_hla);
+  }
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_commit_rows(const McqStatic st, const double *__restrict__ Et,
+                                                     const double *__restrict__ At, double *__restrict__ E,
+                                                     double *__restrict__ A, int k0, int k1) {
+  const int W = k1 - k0;
+  const size_t n = (size_t)st.Q * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = (i / W) * st.ES + k0 + (i % W);
+    E[o] = Et[o];
+    A[o] = At[o];
+  }
+}
+
+cudaError_t mcq_launch_commit_rows(const McqStatic &st, const double *Et, const double *At, double *E, double *A,
+                                   int start, int end, cudaStream_t stream) {
+  // eoff lives on the device; the host keeps a copy, so the caller passes slot bounds via start/end
+  // already translated (see mcq_ctx.cu) - here start/end ARE slot bounds [k0,k1)
+  const size_t n = (size_t)st.Q * (end - start);
+  if (n == 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_commit_rows<<<blocks, 256, 0, stream>>>(st, Et, At, E, A, start, end);
+  return cudaGetLastError();
+}
+
+// make the proposal's parameter change current (R / omega+rate_out / esc / rev / mu)
+__global__ void k_commit_params(const McqStatic st, McqModel m, McqOverride ov) {
+  const int t = threadIdx.x;
+  switch (ov.kind) {
+    case MCQ_PROP_REC:
+      if (t == 0) m.R[ov.start] = ov.v0;
+      break;
+    case MCQ_PROP_SEL: {
+      const int s = ov.start;
+      if (t == 0) m.omega[s] = ov.v0;
+      for (int k = st.eoff[s] + t; k < st.eoff[s + 1]; k += blockDim.x)
+        if (st.slot_flags[k] & 1) {
+          const int c = st.slot_codon[k];
+          m.rate_out[(size_t)s * 64 + c] = m.kappa * d_cnt[2][c] + d_cnt[3][c] + ov.v0 * (m.kappa * d_cnt[0][c] + d_cnt[1][c]);
+        }
+      break;
+    }
+    case MCQ_PROP_ESC:
+      for (int s = ov.start + t; s <= ov.end; s += blockDim.x)
+        m.esc[(size_t)ov.hla * st.S + s] = s < ov.split ? ov.v0 : ov.v1;
+      break;
+    case MCQ_PROP_REV:
+      for (int s = ov.start + t; s <= ov.end; s += blockDim.x) m.rev[s] = s < ov.split ? ov.v0 : ov.v1;
+      break;
+    default: break;
+  }
+}
+
+cudaError_t mcq_launch_commit_params(const McqStatic &st, McqModel m, McqOverride ov, cudaStream_t stream) {
+  k_commit_params<<<1, 128, 0, stream>>>(st, m, ov);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K6b: total over queries.  One block; thread t adds elements t, t+1024, ... in ascending order,
+// then a fixed tree - the result does not depend on scheduling.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_sum(const double *__restrict__ v, int n, double *__restrict__ out) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += v[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+cudaError_t mcq_launch_sum(const double *v, int n, double *out, cudaStream_t stream) {
+  k_sum<<<1, 1024, 0, stream>>>(v, n, out);
+  return cudaGetLastError();
+}

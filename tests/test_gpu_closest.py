@@ -1,0 +1,98 @@
+"""Closest-L selection on the GPU against the CPU oracle: Hamming distances and the selected index
+lists are bit-exact, including their order and the number of libc random() draws consumed."""
+import numpy as np
+import pytest
+
+import cpu_libs
+from mcqueen_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def checker():
+    return cpu_libs.Checker("ref" if cpu_libs.have_ref() else "oracle")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from mcqueen_b200 import api as m
+    return m
+
+
+def _data(S=100, N=300, Q=40, seed=5, **kw):
+    return synth.make_dataset(seed=seed, S=S, N=N, Q=Q, H=4, ref_unknown_frac=0.1, query_gap=True, **kw)
+
+
+@pytest.mark.parametrize("S,N,Q", [(100, 300, 40), (7, 130, 33), (43, 1000, 5), (500, 257, 70)])
+def test_hamming_batch_bit_exact(api, S, N, Q):
+    d = _data(S, N, Q)
+    refs, qs = d["ref_seqs"].copy(), d["query_seqs"].copy()
+    refs[3, :5] = np.frombuffer(b"acgtn", np.uint8)       # lower case + unknown
+    qs[1, :4] = np.frombuffer(b"tg-a", np.uint8)
+    chk = checker()
+    got = api.hamming_batch(refs, qs)
+    for q in range(Q):
+        assert np.array_equal(got[q], chk.hamming(refs, qs[q])), q
+
+
+@pytest.mark.parametrize("L,skip", [(20, False), (20, True), (1, False), (298, False), (64, True)])
+def test_closest_batch_bit_exact(api, L, skip):
+    d = _data()
+    refs, qs = d["ref_seqs"], d["query_seqs"]
+    chk = checker()
+    n = L + 1 if skip else L
+    cpu_libs.srandom(99)
+    want = np.zeros((qs.shape[0], L), np.int32)
+    for q in range(qs.shape[0]):
+        c = chk.closest(chk.hamming(refs, qs[q]), n)
+        want[q] = c[1:] if skip else c
+    after_cpu = cpu_libs.libc_random()
+    cpu_libs.srandom(99)
+    got = api.closest_batch(refs, qs, L, skip_first=skip)
+    after_gpu = cpu_libs.libc_random()
+    assert np.array_equal(got, want)
+    assert after_cpu == after_gpu          # same number of draws consumed
+
+
+def test_engineered_ties(api):
+    """All references identical except a few: the tie window spans almost the whole panel."""
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 4, 60)
+    refs = np.frombuffer(b"TCAG", np.uint8)[np.repeat(base[None], 500, 0)].copy()
+    for r in range(0, 500, 50):
+        refs[r, :3] = ord("N")
+    qs = refs[:7].copy()
+    qs[:, 10] = ord("-")
+    chk = checker()
+    for L in (5, 10, 11, 490):
+        cpu_libs.srandom(7)
+        want = np.stack([chk.closest(chk.hamming(refs, qs[q]), L) for q in range(7)])
+        cpu_libs.srandom(7)
+        got = api.closest_batch(refs, qs, L)
+        assert np.array_equal(got, want), L
+
+
+def test_dropin_symbols(api):
+    d = _data(S=50, N=400, Q=6)
+    refs, qs = d["ref_seqs"], d["query_seqs"]
+    chk = checker()
+    for q in range(6):
+        ham = np.zeros(400, np.int32)
+        api.hamming_distance_considering_unknown(refs, qs[q], 400, 150, ham)
+        assert np.array_equal(ham, chk.hamming(refs, qs[q]))
+        for n in (1, 25, 399):
+            cpu_libs.srandom(q + n)
+            want = chk.closest(ham, n)
+            cpu_libs.srandom(q + n)
+            got = np.zeros(n, np.int32)
+            api.closest_sequences(400, ham, n, got)
+            assert np.array_equal(got, want)
+    # arbitrary int distances (negative, large) through the drop-in: same rule
+    ham = np.array([5, -3, 70000, 5, 5, -3, 9, 5, 100, 5], np.int32)
+    for n in (1, 2, 3, 6, 9):
+        cpu_libs.srandom(n)
+        want = chk.closest(ham, n)
+        cpu_libs.srandom(n)
+        got = np.zeros(n, np.int32)
+        api.closest_sequences(10, ham, n, got)
+        assert np.array_equal(got, want)

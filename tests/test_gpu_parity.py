@@ -1,0 +1,208 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): closest-L index lists bit-exact; log-likelihood within
+1e-9 relative.  What is asserted here is tighter: emission rows bit-exact (integer-free fp64 with
+FMA contraction off reproduces the reference's operation order), F/B cells within 1e-11 relative
+(they differ from the reference only through the order of the per-site sum over copy states),
+rescale counters exact, log-likelihoods within 1e-12 relative.
+"""
+import numpy as np
+import pytest
+
+import cpu_libs
+from cpu_chain import CpuState, REC, SEL, ESC, REV, MU
+from problems import make_problem
+
+pytestmark = pytest.mark.gpu
+
+RTOL_CELL = 1e-11
+RTOL_LLK = 1e-12
+RTOL_CONTRACT = 1e-9
+
+
+def checker():
+    # the compiled reference when it travelled with the snapshot, else the C restatement
+    return cpu_libs.Checker("ref" if cpu_libs.have_ref() else "oracle")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    den = np.maximum(np.abs(b), 1e-300)
+    return float(np.max(np.abs(a - b) / den)) if a.size else 0.0
+
+
+def assert_state_matches(ctx, cpu, queries):
+    from mcqueen_b200 import api
+    for q in queries:
+        for which, M, Mn in ((api.BUF_F, cpu.F, cpu.Fn), (api.BUF_B, cpu.B, cpu.Bn)):
+            g, gn = ctx.matrix(which, q)
+            assert np.array_equal(gn, Mn[q]), (which, q)
+            assert rel(g, M[q]) < RTOL_CELL, (which, q, rel(g, M[q]))
+        assert np.array_equal(ctx.table(api.TAB_C2C, q), cpu.c2c[q])
+        assert np.array_equal(ctx.table(api.TAB_A, q), cpu.A[q])
+
+
+@pytest.fixture(scope="module")
+def api():
+    from mcqueen_b200 import api as m
+    return m
+
+
+@pytest.mark.parametrize("gaps", [False, True])
+def test_init_state(api, gaps):
+    p = make_problem("toy", gaps=gaps)
+    cpu = CpuState(checker(), p)
+    ctx = api.Context.from_problem(p)
+    llk = ctx.init_state()
+    assert abs(llk - cpu.llk) <= RTOL_LLK * abs(cpu.llk)
+    assert rel(ctx.query_llk(), cpu.llk_q) < RTOL_LLK
+    assert_state_matches(ctx, cpu, range(p.Q))
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode,which", [(0, 1), (0, -1), (1, 0), (2, -1), (2, 3)])
+def test_emission_modes_bit_exact(api, mode, which):
+    p = make_problem("toy")
+    chk = checker()
+    c2c = np.zeros((p.Q, 64, p.S)); A = np.zeros_like(c2c)
+    chk.emission(p, c2c, A, 0, p.S - 1, -1, 2)
+    ctx = api.Context.from_problem(p)
+    ctx.emission(0, p.S - 1)
+    esc = p.esc.copy(); rev = p.rev.copy()
+    esc[:, 30:55] *= 1.7; rev[0, 30:55] *= 0.6
+    chk.emission(p, c2c, A, 30, 54, which, mode, esc=esc, rev=rev)
+    ctx.set_params(mu=p.mu, kappa=p.kappa, phi=p.phi, esc=esc, rev=rev[0])
+    ctx.emission(30, 54, which, mode)
+    for q in range(p.Q):
+        assert np.array_equal(ctx.table(api.TAB_C2C, q), c2c[q]), q
+        assert np.array_equal(ctx.table(api.TAB_A, q), A[q]), q
+    ctx.close()
+
+
+def _moves(p, rng):
+    S, H = p.S, p.H
+    out = []
+    s = int(rng.integers(1, S))
+    out.append(dict(kind=REC, start=s, value0=float(p.R[s] * np.exp(rng.uniform(-2, 2)))))
+    s = int(rng.integers(0, S))
+    out.append(dict(kind=SEL, start=s, value0=float(p.omega[s] * np.exp(rng.uniform(-1, 1)))))
+    a = int(rng.integers(0, S - 30)); b = a + int(rng.integers(1, 30))
+    out.append(dict(kind=ESC, start=a, end=b, hla=int(rng.integers(0, H)), split=(a + b) // 2 + 1,
+                    value0=float(np.exp(rng.normal())), value1=float(np.exp(rng.normal()))))
+    a = int(rng.integers(0, S - 30)); b = a + int(rng.integers(1, 30))
+    out.append(dict(kind=REV, start=a, end=b, value0=float(np.exp(rng.normal()))))
+    out.append(dict(kind=MU, start=0, value0=float(p.mu * np.exp(rng.uniform(-0.125, 0.125)))))
+    out.append(dict(kind=SEL, start=0, value0=0.7))
+    out.append(dict(kind=SEL, start=S - 1, value0=1.9))
+    out.append(dict(kind=REC, start=S - 1, value0=0.02))
+    out.append(dict(kind=ESC, start=0, end=S - 1, hla=0, value0=1.3))
+    return out
+
+
+@pytest.mark.parametrize("sparse", [0, 1])
+def test_proposals_and_accepts_track_the_oracle(api, sparse):
+    """A scripted chain: every proposal's total matches, rejected ones leave no trace, accepted ones
+    leave the same F/B/emission state as the reference's accept path."""
+    p = make_problem("toy", gaps=True)
+    cpu = CpuState(checker(), p)
+    ctx = api.Context.from_problem(p)
+    ctx.set_option(api.OPT_SPARSE_ESC, sparse)
+    ctx.init_state()
+    rng = np.random.default_rng(3)
+    for rnd in range(3):
+        for i, mv in enumerate(_moves(p, rng)):
+            want = cpu.propose(**mv)
+            got = ctx.propose(**mv)
+            # sparse mode reuses cached per-query values for non-carriers: same to ~1e-13
+            assert abs(got - want) <= (1e-11 if sparse else RTOL_LLK) * abs(want), (rnd, i, mv, got, want)
+            if (i + rnd) % 2 == 0:
+                cpu.accept(); ctx.accept()
+            else:
+                cpu.reject(); ctx.reject()
+        assert_state_matches(ctx, cpu, [0, 7, 23, p.Q - 1])
+        prm = ctx.params()
+        assert np.array_equal(prm["R"], cpu.R) and np.array_equal(prm["omega"], cpu.omega)
+        assert np.array_equal(prm["esc"], cpu.esc) and np.array_equal(prm["rev"], cpu.rev[0])
+        assert np.array_equal(prm["rate_out"], cpu.rate_out) and prm["mu"] == cpu.mu
+    ctx.close()
+
+
+def test_dropin_symbols_match(api):
+    p = make_problem("toy", gaps=True)
+    chk = checker()
+    base = cpu_libs.full_state(chk, p)
+    S, L, N = p.S, p.L, p.N
+    for q in (0, 11, p.Q - 1):
+        cl = np.ascontiguousarray(p.closest_refs[q]); cons = np.ascontiguousarray(p.cons_query_nucls[q])
+        F = np.zeros((L, S)); Fn = np.full(S, -1, np.int32)
+        api.initialise_F_numerical_recipes(S, L, N, base["c2c"][q], p.ref_codons, p.ref_triplets, p.R, F, Fn,
+                                           0, S - 1, cl, 3 * S, cons)
+        assert np.array_equal(Fn, base["Fn"][q]) and rel(F, base["F"][q]) < RTOL_CELL
+        B = np.zeros((L, S)); Bn = np.full(S, -1, np.int32)
+        api.update_B_numerical_recipes(S, L, N, base["c2c"][q], p.ref_codons, p.ref_triplets, p.R, B, Bn,
+                                       S - 1, cl, 3 * S, cons)
+        assert np.array_equal(Bn, base["Bn"][q]) and rel(B, base["B"][q]) < RTOL_CELL
+        # window update into a tmp matrix, then in-place suffix + prefix refills (the accept path)
+        R2 = p.R.copy(); R2[20:41] *= 1.5
+        tF = np.zeros((L, S)); tFn = np.zeros(S, np.int32)
+        wF = np.zeros((L, S)); wFn = np.zeros(S, np.int32)
+        api.update_F_numerical_recipes(S, L, N, base["c2c"][q], p.ref_codons, p.ref_triplets, R2, F, Fn, tFn, tF,
+                                       20, 40, cl, 3 * S, cons)
+        chk.forward(p, q, base["c2c"][q], R2, base["F"][q], base["Fn"][q], wFn, wF, 20, 40)
+        assert np.array_equal(tFn[20:41], wFn[20:41]) and rel(tF[:, 20:41], wF[:, 20:41]) < RTOL_CELL
+        F2, Fn2 = base["F"][q].copy(), base["Fn"][q].copy()
+        G2, Gn2 = base["F"][q].copy(), base["Fn"][q].copy()
+        api.update_F_numerical_recipes(S, L, N, base["c2c"][q], p.ref_codons, p.ref_triplets, R2, F2, Fn2, Fn2, F2,
+                                       41, S - 1, cl, 3 * S, cons)
+        chk.forward(p, q, base["c2c"][q], R2, G2, Gn2, Gn2, G2, 41, S - 1)
+        assert np.array_equal(Fn2, Gn2) and rel(F2, G2) < RTOL_CELL
+        B2, Bn2 = base["B"][q].copy(), base["Bn"][q].copy()
+        H2, Hn2 = base["B"][q].copy(), base["Bn"][q].copy()
+        api.update_B_numerical_recipes(S, L, N, base["c2c"][q], p.ref_codons, p.ref_triplets, R2, B2, Bn2, 40,
+                                       cl, 3 * S, cons)
+        chk.backward(p, q, base["c2c"][q], R2, H2, Hn2, 40)
+        assert np.array_equal(Bn2, Hn2) and rel(B2, H2) < RTOL_CELL
+
+
+@pytest.mark.parametrize("name,over", [("toy", {}), ("toy", dict(L=100, N=150)), ("toy", dict(L=37, S=33, Q=9))])
+def test_shapes_and_likelihood_identity(api, name, over):
+    """Ragged shapes (L not a multiple of 16 or 64, tiny S) and the F.B identity: for every site s,
+    log sum_r F[r][s] B[r][s] - (Fn+Bn) log BIG is the query's log-likelihood."""
+    p = make_problem(name, **over)
+    cpu = CpuState(checker(), p)
+    ctx = api.Context.from_problem(p)
+    llk = ctx.init_state()
+    assert abs(llk - cpu.llk) <= RTOL_LLK * abs(cpu.llk)
+    lq = ctx.query_llk()
+    for q in (0, p.Q - 1):
+        F, Fn = ctx.matrix(api.BUF_F, q)
+        B, Bn = ctx.matrix(api.BUF_B, q)
+        per_site = np.log((F * B).sum(0)) - (Fn + Bn) * np.log(1e6)
+        assert np.max(np.abs(per_site - lq[q])) < 1e-9 * abs(lq[q])
+    ctx.close()
+
+
+def test_contract_tolerance_on_c2_slice(api):
+    """A C2-shaped slice (S=500, L=100, N=2000, H=20; 24 queries so the oracle finishes in seconds):
+    total log-likelihood within the contract's 1e-9 relative (asserted at 1e-12)."""
+    p = make_problem("C2", Q=24)
+    chk = checker()
+    st = cpu_libs.full_state(chk, p)
+    ctx = api.Context.from_problem(p)
+    llk = ctx.init_state()
+    want = CpuState._seq_sum(st["llk"])
+    assert abs(llk - want) <= RTOL_LLK * abs(want) < RTOL_CONTRACT * abs(want)
+    assert rel(ctx.query_llk(), st["llk"]) < RTOL_LLK
+    for q in (0, 23):
+        g, gn = ctx.matrix(api.BUF_B, q)
+        assert np.array_equal(gn, st["Bn"][q]) and rel(g, st["B"][q]) < RTOL_CELL
+    ctx.close()
+
+
+def test_errors_are_loud(api):
+    with pytest.raises(api._lib.McqError):
+        api.Context(10, 2000, 100, 5, 1)          # closest_n > 1024
+    ctx = api.Context(10, 4, 100, 5, 1)
+    with pytest.raises(api._lib.McqError):
+        ctx.init_state()                           # nothing uploaded
+    ctx.close()
