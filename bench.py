@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""Benchmark of the McQueen likelihood path on B200 (contract: see DESIGN.md "Measurement").
+
+One *step* = one full likelihood evaluation of the shard's queries: emission table for all sites
+(K3), forward fill materialising F (K4), per-query log-likelihood (K6) and the cross-query /
+cross-GPU sum - what dmodel does at start-up and what mutation_move re-does per proposal
+(dmodel.c:873-902, mcmc_moves.c:1124-1134).  Metric: site x state cells per second = Q*S*L / time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C2|toy] [--impl reference]
+
+N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...`;
+queries are sharded over ranks (strong scaling: BASELINE.json names one fixed workload "sharded
+1/2/4/8"), the only exchange is the library's one-double NCCL all-reduce per evaluation.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mcqueen_b200 import genetics as gen, prep, synth  # noqa: E402
+
+METRIC = "query-HMM evals/sec (site x state cells/s)"
+UNIT = "cells/s"
+SEED = 20261019
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def workload_dims(name):
+    return dict(synth.CONFIGS[name])
+
+
+def make_data(name):
+    cfg = workload_dims(name)
+    cfg.pop("L")
+    return synth.make_dataset(seed=SEED, **cfg)
+
+
+def consensus_of_closest_torch(ref_codes, closest, device):
+    """Per-query majority base over its closest references (amino_acids.c:118-141) - set-up
+    plumbing done with torch on the GPU because the numpy version takes minutes at C4 size."""
+    import torch
+    rc = torch.from_numpy(ref_codes).to(device)
+    out = np.empty((closest.shape[0], ref_codes.shape[1]), np.int8)
+    step = max(1, (256 << 20) // (closest.shape[1] * ref_codes.shape[1]))
+    for i in range(0, closest.shape[0], step):
+        idx = torch.from_numpy(closest[i:i + step].astype(np.int64)).to(device)
+        g = rc[idx]
+        counts = torch.stack([(g == b).sum(1) for b in range(4)], 1)
+        out[i:i + step] = counts.argmax(1).to(torch.int8).cpu().numpy()
+    return out
+
+
+def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
+    """Problem restricted to queries q0..q1-1 (references are shared by every shard)."""
+    from mcqueen_b200 import api
+    cfg = workload_dims(name)
+    L = cfg["L"]
+    t0 = time.time()
+    data = make_data(name)
+    refs, qs, hla = data["ref_seqs"], np.ascontiguousarray(data["query_seqs"][q0:q1]), data["hla"][q0:q1]
+    t1 = time.time()
+    import ctypes
+    ctypes.CDLL("libc.so.6").srandom(SEED & 0x7fffffff)
+    closest = api.closest_batch(refs, qs, L, device=device_index)
+    t2 = time.time()
+    cons_q = consensus_of_closest_torch(gen.base_codes(refs), closest, f"cuda:{device_index}")
+    p = prep.build_problem(refs, qs, hla, closest, cons_q=cons_q)
+    prep.random_parameters(p, seed=1)
+    t3 = time.time()
+    log(f"[bench] data {t1 - t0:.1f}s  closest-L(GPU) {t2 - t1:.1f}s  prep {t3 - t2:.1f}s  "
+        f"Q={p.Q} S={p.S} L={p.L} N={p.N} H={p.H}")
+    p.closest_seconds = t2 - t1
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.path is None or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own code (oracle/_ref/ref_bench), host threads over query shards
+# ------------------------------------------------------------------------------------------------
+def write_ref_problem(p, path, nq):
+    nq = min(nq, p.Q)
+    with open(path, "wb") as f:
+        np.array([p.S, p.N, nq, p.L, p.H], np.int32).tofile(f)
+        np.array([p.mu, p.kappa, p.phi], np.float64).tofile(f)
+        p.prior.astype(np.float64).tofile(f)
+        p.ref_triplets.tofile(f); p.ref_codons.tofile(f); p.query_codons[:nq].tofile(f)
+        p.cons_query_nucls[:nq].tofile(f)
+        hl = np.zeros((nq, p.H + 1), np.uint8); hl[:, :p.H] = p.hla[:nq]; hl.tofile(f)
+        p.consensus_codons.tofile(f); p.site_codons.tofile(f); p.type_of_change.tofile(f)
+        p.closest_refs[:nq].astype(np.int32).tofile(f); p.n_site_codons.astype(np.int32).tofile(f)
+        p.ns_ts_sum.astype(np.int32).tofile(f); p.ns_tv_sum.astype(np.int32).tofile(f)
+        p.R.tofile(f); p.omega.tofile(f); np.ascontiguousarray(p.esc).tofile(f)
+        np.ascontiguousarray(p.rev).tofile(f); p.rate_out_of_codons().tofile(f)
+    return nq
+
+
+def run_ref_bench(p, threads, seconds, path=None):
+    """Times the reference on a bounded sample; returns (cells/s, description dict)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+    if not os.path.exists(exe):
+        return None, {"error": "oracle/_ref/ref_bench missing"}
+    own = path is None
+    if own:
+        fd, path = tempfile.mkstemp(suffix=".bin")
+        os.close(fd)
+    nq = write_ref_problem(p, path, max(threads * 4, 64))
+
+    def once(reps):
+        out = subprocess.run([exe, path, str(threads), str(nq), "0", str(reps)], capture_output=True, text=True,
+                             check=True).stdout
+        return json.loads(out.strip().splitlines()[-1])
+
+    probe = once(1)
+    reps = max(1, int(seconds / max(probe["seconds"], 1e-3)))
+    res = once(reps) if reps > 1 else probe
+    if own:
+        os.unlink(path)
+    desc = dict(kind="reference", cores=threads, value=res["cells_per_s"], unit=UNIT,
+                sample=f"{nq} of {p.Q} queries x {reps} repeats ({res['seconds']:.1f} s): "
+                       f"create_codon_to_codon_HLA + initialise_F_numerical_recipes + llk per query, "
+                       f"reference objects built -O3 (oracle/Makefile), {threads} host threads over query shards")
+    return res["cells_per_s"], desc
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4", choices=list(synth.CONFIGS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = workload_dims(args.workload)
+    Qtot, S, L, N, H = cfg["Q"], cfg["S"], cfg["L"], cfg["N"], cfg["H"]
+    config = {"workload": f"{args.workload}: synthetic {Qtot} queries x L={L} x {S} codons, N={N} refs, H={H} HLA "
+                          f"types; full likelihood evaluation (emission + forward fill + llk)",
+              "queries": Qtot, "sites": S, "closest_n": L, "refs": N, "hla_types": H,
+              "sharding": f"queries/{world}", "cache": "inputs+outputs per step (>20 GB at C4) exceed L2; no flush"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ncpu = os.cpu_count() or 1
+        # the reference arm needs a problem; build it without the GPU library where none is present
+        p = build_problem_cpu(args.workload, ncpu)
+        fd, path = tempfile.mkstemp(suffix=".bin")
+        os.close(fd)
+        vals = []
+        desc = None
+        per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+        for i in range(args.warmup + args.steps):
+            v, desc = run_ref_bench(p, ncpu, per_step, path)
+            if v is None:
+                print(json.dumps({"impl": "reference", "unavailable": desc["error"]}))
+                return 0
+            if i >= args.warmup:
+                vals.append(v)
+        os.unlink(path)
+        value = float(np.mean(vals))
+        desc["value"] = value
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": Qtot * S * L / value * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "cpu_baseline": desc,
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from mcqueen_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the McQueen path has no CPU fallback")
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = local_rank
+    q0, q1 = Qtot * rank // world, Qtot * (rank + 1) // world
+    p = build_shard(args.workload, q0, q1, dev)
+    ctx = api.Context.from_problem(p, device=dev)
+    if world > 1:
+        ids = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.attach_comm(world, rank, ids[0])
+    log(f"[bench] rank {rank}: context holds {ctx.device_bytes() / 2**30:.1f} GiB")
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    llk0 = ctx.init_state()
+    for _ in range(args.warmup):
+        ctx.full_llk(True)
+
+    # ---- timed region: K steps, device time via CUDA events on the library's stream
+    ctx.enable_timing(2)
+    ctx.kernel_time(api.K_FORWARD, reset=True)
+    barrier()
+    with ClockSampler(dev) as clk:
+        t_wall = time.perf_counter()
+        ctx.timer_start()
+        launches = 0
+        for _ in range(args.steps):
+            llk = ctx.full_llk(True)
+            launches += ctx.last_timing()[1]
+        ms_dev = ctx.timer_stop()
+        barrier()
+        t_wall = (time.perf_counter() - t_wall) * 1e3
+    fwd_ms, fwd_n = ctx.kernel_time(api.K_FORWARD)
+    emi_ms, emi_n = ctx.kernel_time(api.K_EMISSION)
+    ctx.enable_timing(0)
+    clocks = clk.summary()
+    assert abs(llk - llk0) <= 1e-12 * abs(llk0), (llk, llk0)
+
+    # ---- e2e: everything from (pinned) host buffers every step, per-query results back
+    host_arrays = [p.ref_triplets, p.closest_refs, p.cons_query_nucls, p.query_codons, p.hla]
+    for a in host_arrays:
+        api.host_register(a)
+    rate_out = p.rate_out_of_codons()
+    h2d = sum(a.nbytes for a in host_arrays) + p.consensus_codons.nbytes + p.n_site_codons.nbytes + \
+        p.site_codons.nbytes + 8 * (64 + 2 * S + 64 * S + H * S + S)
+    d2h = 8 * p.Q + 8
+
+    def e2e_step():
+        ctx.upload_static(p.ref_triplets, p.closest_refs, p.cons_query_nucls, p.query_codons, p.hla,
+                          p.consensus_codons, p.n_site_codons, p.site_codons)
+        ctx.set_params(mu=p.mu, kappa=p.kappa, phi=p.phi, prior=p.prior, R=p.R, omega=p.omega,
+                       rate_out=rate_out, esc=p.esc, rev=p.rev[0])
+        tot = ctx.full_llk(True)
+        per_q = ctx.query_llk()
+        return tot, per_q
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ctx.timer_start()
+    t_e2e = time.perf_counter()
+    for _ in range(args.steps):
+        tot, per_q = e2e_step()
+    ms_e2e_dev = ctx.timer_stop()
+    barrier()
+    t_e2e = (time.perf_counter() - t_e2e) * 1e3
+    for a in host_arrays:
+        api.host_unregister(a)
+    assert abs(tot - llk0) <= 1e-12 * abs(llk0)
+
+    # ---- extras: the other kernels of the path (reported, not the headline)
+    extras = {}
+    if not args.no_extras:
+        ctx.init_state()
+        ctx.enable_timing(1)
+
+        def timed(fn, reps=3):
+            best = 1e30
+            for _ in range(reps):
+                fn()
+                best = min(best, ctx.last_timing()[0])
+            return best
+
+        cells = p.Q * S * L
+        t = timed(ctx.backward_fill)
+        extras["backward_fill_cells_per_s"] = cells / t * 1e3
+        w0, w1 = S // 3, S // 3 + S // 6 - 1
+        t = timed(lambda: ctx.propose(api.PROP_REV, w0, w1, value0=1.1))
+        extras["window_proposal_ms"] = t
+        extras["window_proposal_cells_per_s"] = p.Q * (w1 - w0 + 1) * L / t * 1e3
+        t = timed(lambda: ctx.propose(api.PROP_REC, S // 2, value0=0.02), reps=5)
+        extras["single_site_proposal_ms"] = t
+        ctx.propose(api.PROP_REV, w0, w1, value0=1.1)
+        ctx.accept()
+        extras["window_accept_ms"] = ctx.last_timing()[0]
+        extras["closest_L_seconds_setup"] = p.closest_seconds
+        ctx.enable_timing(0)
+
+    # ---- gather over ranks (max time)
+    stats = np.array([ms_dev, t_wall, ms_e2e_dev, t_e2e, fwd_ms / max(fwd_n, 1)], np.float64)
+    if world > 1:
+        tt = torch.from_numpy(stats)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        stats = tt.numpy()
+    ms_step = max(stats[0], 0.0) / args.steps
+    ms_step_wall = stats[1] / args.steps
+    ms_e2e = max(stats[2], stats[3]) / args.steps
+    fwd_ms_avg = stats[4]
+
+    if rank == 0:
+        total_cells = Qtot * S * L
+        value = total_cells / (ms_step * 1e-3)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bytes_per_cell = 9.0 + 520.0 / L
+        alg_bytes = bytes_per_cell * p.Q * S * L
+        achieved = alg_bytes / (fwd_ms_avg * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "forward_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == args.workload and tj.get("queries_per_gpu") == p.Q:
+                traffic = tj["dram_bytes_per_launch"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": total_cells / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                    "what": "mcq_ctx_upload_static + mcq_ctx_set_params + mcq_ctx_full_llk + per-query llk "
+                            "read-back, all inputs from pinned host buffers every step"},
+            "roofline": {"bound": "hbm", "kernel": "k_forward", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_cell": bytes_per_cell, "launch_ms": fwd_ms_avg,
+                         "cells_per_launch": p.Q * S * L},
+            "ms_per_step_wall": ms_step_wall, "llk": llk0, "extras": extras,
+            "kernel_share": {"forward_ms_per_step": fwd_ms / max(args.steps, 1),
+                             "emission_ms_per_step": emi_ms / max(args.steps, 1)},
+        }
+        if world == 1 and args.cpu_seconds > 0:
+            ncpu = os.cpu_count() or 1
+            v, desc = run_ref_bench(p, ncpu, args.cpu_seconds)
+            line["cpu_baseline"] = desc if v is not None else {"value": None, "unit": UNIT, "cores": ncpu,
+                                                               "kind": "reference", "sample": desc["error"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def build_problem_cpu(name, ncpu):
+    """Reference arm only: a problem for ref_bench without needing the exact closest-L lists of the
+    full workload (the CPU sample covers a few hundred queries).  Closest lists come from the GPU
+    library when a device is present, else from the oracle on the sampled queries."""
+    cfg = workload_dims(name)
+    L = cfg["L"]
+    data = make_data(name)
+    nq = min(cfg["Q"], max(ncpu * 4, 64))
+    refs, qs, hla = data["ref_seqs"], np.ascontiguousarray(data["query_seqs"][:nq]), data["hla"][:nq]
+    import ctypes
+    ctypes.CDLL("libc.so.6").srandom(SEED & 0x7fffffff)
+    closest = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from mcqueen_b200 import api
+            closest = api.closest_batch(refs, qs, L)
+    except Exception:
+        closest = None
+    if closest is None:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import cpu_libs
+        orc = cpu_libs.Checker("ref" if cpu_libs.have_ref() else "oracle")
+        closest = np.stack([orc.closest(orc.hamming(refs, qs[q]), L) for q in range(nq)])
+    p = prep.build_problem(refs, qs, hla, closest)
+    prep.random_parameters(p, seed=1)
+    return p
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -99,7 +99,8 @@ void mcq_ctx_destroy(mcq_ctx *ctx);
  *   consensus_codons[S] (dmodel.c:757), num_ref_site_codons[S] + ref_site_codons[S][64]
  *   (amino_acids.c:155-176).
  * Builds the device-side gathered codon table (triplet_to_codon, amino_acids.c:50-66, is
- * evaluated once here instead of once per cell per sweep). */
+ * evaluated once here instead of once per cell per sweep).  May be called again with new data of
+ * the same shape and the same per-site codon lists (re-uploads and re-gathers, no allocation). */
 int mcq_ctx_upload_static(mcq_ctx *ctx, const char *ref_triplets, const int *closest_refs,
                           const char *cons_query_nucls, const char *query_codons,
                           const char *hla_types, const char *consensus_codons,
@@ -189,8 +190,22 @@ size_t mcq_ctx_device_bytes(const mcq_ctx *ctx);
 /* Device time (ms, CUDA events on the context's stream) and launch count of the kernels
  * issued by the previous API call on this context. */
 int mcq_ctx_last_timing(const mcq_ctx *ctx, float *ms, int *launches);
-/* When enabled every API call brackets its kernels with CUDA events (costs a sync). */
+/* When enabled every API call brackets its kernels with CUDA events (costs a sync).
+ * on == 2 additionally brackets every kernel launch, accumulated per kernel class. */
 int mcq_ctx_enable_timing(mcq_ctx *ctx, int on);
+enum { MCQ_K_GATHER = 0, MCQ_K_EMISSION = 1, MCQ_K_FORWARD = 2, MCQ_K_BACKWARD = 3, MCQ_K_COMMIT = 4,
+       MCQ_K_SUM = 5, MCQ_K_CLASSES = 6 };
+/* Accumulated device time and launch count of one kernel class since the last reset
+ * (needs mcq_ctx_enable_timing(ctx, 2)); reset != 0 clears all classes after reading. */
+int mcq_ctx_kernel_time(mcq_ctx *ctx, int kclass, float *ms_total, int *launches, int reset);
+/* Stopwatch on the context's stream (CUDA events): start records, stop records + waits. */
+int mcq_ctx_timer_start(mcq_ctx *ctx);
+int mcq_ctx_timer_stop(mcq_ctx *ctx, float *ms);
+/* Wait for everything queued on the context's stream. */
+int mcq_ctx_synchronize(mcq_ctx *ctx);
+/* Page-lock / unlock a caller-owned host buffer so that uploads from it run at full PCIe rate. */
+int mcq_host_register(void *ptr, size_t bytes);
+int mcq_host_unregister(void *ptr);
 
 /* ---- multi-GPU: queries are sharded over ranks, one scalar is exchanged ---------------- */
 /* 128-byte NCCL unique id, created on rank 0 and passed to the others by the launcher. */

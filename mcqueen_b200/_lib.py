@@ -61,6 +61,12 @@ SYMBOLS = {
     "mcq_ctx_device_bytes": (C.c_size_t, [_V]),
     "mcq_ctx_last_timing": (C.c_int, [_V, C.POINTER(C.c_float), c_int_p]),
     "mcq_ctx_enable_timing": (C.c_int, [_V, C.c_int]),
+    "mcq_ctx_kernel_time": (C.c_int, [_V, C.c_int, C.POINTER(C.c_float), c_int_p, C.c_int]),
+    "mcq_ctx_timer_start": (C.c_int, [_V]),
+    "mcq_ctx_timer_stop": (C.c_int, [_V, C.POINTER(C.c_float)]),
+    "mcq_ctx_synchronize": (C.c_int, [_V]),
+    "mcq_host_register": (C.c_int, [_V, C.c_size_t]),
+    "mcq_host_unregister": (C.c_int, [_V]),
     "mcq_comm_unique_id": (C.c_int, [_V]),
     "mcq_ctx_attach_comm": (C.c_int, [_V, C.c_int, C.c_int, _V]),
     "mcq_closest_batch": (C.c_int, [C.c_int, _V, C.c_size_t, C.c_int, _V, C.c_size_t, C.c_int, C.c_int,

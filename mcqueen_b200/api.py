@@ -22,6 +22,7 @@ DO_HLA_ESC, DO_HLA_REV, DO_HLA_BOTH, DO_ALL_HLAS = 0, 1, 2, -1   # mcmc_moves.h:
 BUF_F, BUF_B, BUF_TMP_F = 0, 1, 2
 TAB_C2C, TAB_A, TAB_TMP_C2C, TAB_TMP_A = 0, 1, 2, 3
 OPT_SPARSE_ESC = 1
+K_GATHER, K_EMISSION, K_FORWARD, K_BACKWARD, K_COMMIT, K_SUM = range(6)
 
 
 def _vp(a):
@@ -220,8 +221,26 @@ class Context:
     def set_option(self, option, value):
         check(self.lib.mcq_ctx_set_option(self._h, option, value))
 
-    def enable_timing(self, on=True):
-        check(self.lib.mcq_ctx_enable_timing(self._h, 1 if on else 0))
+    def enable_timing(self, level=1):
+        """0 off, 1 CUDA events around each API call, 2 also around each kernel launch."""
+        check(self.lib.mcq_ctx_enable_timing(self._h, int(level)))
+
+    def kernel_time(self, kclass, reset=False):
+        """(total device ms, launches) of one kernel class since the last reset."""
+        ms, n = C.c_float(), C.c_int()
+        check(self.lib.mcq_ctx_kernel_time(self._h, kclass, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
+
+    def timer_start(self):
+        check(self.lib.mcq_ctx_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.lib.mcq_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        check(self.lib.mcq_ctx_synchronize(self._h))
 
     def last_timing(self):
         ms, n = C.c_float(), C.c_int()
@@ -259,6 +278,15 @@ class Context:
     def attach_comm(self, nranks, rank, unique_id: bytes):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         check(self.lib.mcq_ctx_attach_comm(self._h, nranks, rank, C.cast(buf, C.c_void_p)))
+
+
+def host_register(arr):
+    """Page-lock a numpy array's buffer (uploads from it then run at full PCIe rate)."""
+    check(_lib.load().mcq_host_register(_vp(arr), arr.nbytes))
+
+
+def host_unregister(arr):
+    check(_lib.load().mcq_host_unregister(_vp(arr)))
 
 
 def comm_unique_id() -> bytes:

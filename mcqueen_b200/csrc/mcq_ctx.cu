@@ -108,10 +108,20 @@ struct mcq_ctx {
   bool has_pending = false;
   int opt_sparse_esc = 0;
 
-  bool timing = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int timing = 0;            // 0 off, 1 per API call, 2 per kernel launch as well
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   float last_ms = 0.f;
   int last_launches = 0, launches = 0;
+  std::vector<cudaEvent_t> kev;      // pairs of events bracketing single launches
+  std::vector<int> kev_class;
+  float k_ms[MCQ_K_CLASSES] = {0};
+  int k_n[MCQ_K_CLASSES] = {0};
+
+  // staging buffers of mcq_ctx_upload_static (kept so that a re-upload allocates nothing)
+  int8_t *st_trip = nullptr, *st_cons = nullptr;
+  int *st_closest = nullptr;
+  uint8_t *st_slot_of = nullptr;
+  std::vector<uint8_t> st_bits;
 
   ncclComm_t comm = nullptr;
   int nranks = 1;
@@ -143,6 +153,7 @@ struct CallScope {   // brackets one API call for mcq_ctx_last_timing
   mcq_ctx *c;
   explicit CallScope(mcq_ctx *ctx) : c(ctx) {
     c->launches = 0;
+    c->kev_class.clear();
     if (c->timing) cudaEventRecord(c->ev0, c->stream);
   }
   ~CallScope() {
@@ -151,7 +162,34 @@ struct CallScope {   // brackets one API call for mcq_ctx_last_timing
       cudaEventRecord(c->ev1, c->stream);
       cudaEventSynchronize(c->ev1);
       cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+      for (size_t i = 0; i < c->kev_class.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->kev[2 * i], c->kev[2 * i + 1]);
+        c->k_ms[c->kev_class[i]] += ms;
+      }
     }
+  }
+};
+
+struct KScope {      // brackets one kernel launch (timing level 2) and counts it
+  mcq_ctx *c;
+  int idx = -1;
+  KScope(mcq_ctx *ctx, int kclass) : c(ctx) {
+    c->launches++;
+    c->k_n[kclass]++;
+    if (c->timing >= 2) {
+      idx = (int)c->kev_class.size();
+      while (c->kev.size() < (size_t)2 * (idx + 1)) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->kev.push_back(e);
+      }
+      c->kev_class.push_back(kclass);
+      cudaEventRecord(c->kev[2 * idx], c->stream);
+    }
+  }
+  ~KScope() {
+    if (idx >= 0) cudaEventRecord(c->kev[2 * idx + 1], c->stream);
   }
 };
 
@@ -177,6 +215,8 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
+  CK(cudaEventCreate(&c->evt0));
+  CK(cudaEventCreate(&c->evt1));
   const size_t S = dims->num_sites, Q = dims->num_query, H = dims->num_hla_types;
   ALLOC(c->m.R, S); ALLOC(c->m.omega, S); ALLOC(c->m.rate_out, S * 64);
   ALLOC(c->m.esc, H * S); ALLOC(c->m.rev, S); ALLOC(c->m.prior, 64);
@@ -194,13 +234,16 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   void *ptrs[] = {c->G, c->slot_codon, c->slot_flags, c->cons_codon, c->query_codon, c->hla, c->eoff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->E, c->A, c->Et, c->At,
-                  c->llk_cur, c->llk_prop, c->d_sum};
+                  c->llk_cur, c->llk_prop, c->d_sum, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->evt0);
+  cudaEventDestroy(c->evt1);
+  for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -209,7 +252,46 @@ extern "C" size_t mcq_ctx_device_bytes(const mcq_ctx *c) { return c ? c->bytes :
 
 extern "C" int mcq_ctx_enable_timing(mcq_ctx *c, int on) {
   REQUIRE(c, "null context");
-  c->timing = on != 0;
+  c->timing = on;
+  return 0;
+}
+extern "C" int mcq_ctx_kernel_time(mcq_ctx *c, int kclass, float *ms_total, int *launches, int reset) {
+  REQUIRE(c, "null context");
+  REQUIRE(kclass >= 0 && kclass < MCQ_K_CLASSES, "kernel class");
+  if (ms_total) *ms_total = c->k_ms[kclass];
+  if (launches) *launches = c->k_n[kclass];
+  if (reset)
+    for (int i = 0; i < MCQ_K_CLASSES; i++) { c->k_ms[i] = 0.f; c->k_n[i] = 0; }
+  return 0;
+}
+extern "C" int mcq_ctx_timer_start(mcq_ctx *c) {
+  REQUIRE(c, "null context");
+  CK(cudaSetDevice(c->d.device));
+  CK(cudaEventRecord(c->evt0, c->stream));
+  return 0;
+}
+extern "C" int mcq_ctx_timer_stop(mcq_ctx *c, float *ms) {
+  REQUIRE(c && ms, "null argument");
+  CK(cudaSetDevice(c->d.device));
+  CK(cudaEventRecord(c->evt1, c->stream));
+  CK(cudaEventSynchronize(c->evt1));
+  CK(cudaEventElapsedTime(ms, c->evt0, c->evt1));
+  return 0;
+}
+extern "C" int mcq_ctx_synchronize(mcq_ctx *c) {
+  REQUIRE(c, "null context");
+  CK(cudaSetDevice(c->d.device));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int mcq_host_register(void *ptr, size_t bytes) {
+  REQUIRE(ptr && bytes, "null argument");
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+extern "C" int mcq_host_unregister(void *ptr) {
+  REQUIRE(ptr, "null argument");
+  CK(cudaHostUnregister(ptr));
   return 0;
 }
 extern "C" int mcq_ctx_last_timing(const mcq_ctx *c, float *ms, int *launches) {
@@ -234,14 +316,15 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   REQUIRE(c, "null context");
   REQUIRE(ref_triplets && closest_refs && cons_query_nucls && query_codons && hla_types &&
               consensus_codons && num_ref_site_codons && ref_site_codons, "null argument");
-  REQUIRE(!c->have_static, "static data already uploaded");
   CK(cudaSetDevice(c->d.device));
   const int S = c->d.num_sites, Q = c->d.num_query, L = c->d.closest_n, N = c->d.total_num_refs,
             H = c->d.num_hla_types;
+  CallScope scope(c);
 
   // slot lists: the codons the panel shows at the site (ascending, amino_acids.c:155-176), plus
   // the consensus codon when no reference shows it (create_codon_to_codon_HLA writes that row too)
-  c->eoff_h.assign(S + 1, 0);
+  std::vector<int> eoff_h(S + 1, 0);
+  std::vector<uint8_t> slot_codon_h, slot_flags_h;
   std::vector<uint8_t> slot_of((size_t)S * 64, MCQ_NOSLOT);
   for (int s = 0; s < S; s++) {
     const int n = num_ref_site_codons[s];
@@ -255,67 +338,68 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
       REQUIRE(cd < 64, "reference codon out of range");
       REQUIRE(slot_of[(size_t)s * 64 + cd] == MCQ_NOSLOT, "duplicate codon in ref_site_codons");
       slot_of[(size_t)s * 64 + cd] = (uint8_t)k++;
-      c->slot_codon_h.push_back((uint8_t)cd);
-      c->slot_flags_h.push_back((uint8_t)(1 | (cd == cons ? 2 : 0)));
+      slot_codon_h.push_back((uint8_t)cd);
+      slot_flags_h.push_back((uint8_t)(1 | (cd == cons ? 2 : 0)));
       has_cons |= (cd == cons);
     }
     if (!has_cons) {
       slot_of[(size_t)s * 64 + cons] = (uint8_t)k++;
-      c->slot_codon_h.push_back((uint8_t)cons);
-      c->slot_flags_h.push_back(2);
+      slot_codon_h.push_back((uint8_t)cons);
+      slot_flags_h.push_back(2);
     }
-    c->eoff_h[s + 1] = c->eoff_h[s] + k;
+    eoff_h[s + 1] = eoff_h[s] + k;
   }
-  c->ES = (c->eoff_h[S] + 1) / 2 * 2;
-
-  ALLOC(c->eoff, (size_t)S + 1);
-  ALLOC(c->slot_codon, c->slot_codon_h.size());
-  ALLOC(c->slot_flags, c->slot_flags_h.size());
-  ALLOC(c->cons_codon, (size_t)S);
-  ALLOC(c->query_codon, (size_t)Q * S);
-  ALLOC(c->hla, (size_t)Q * H);
-  ALLOC(c->G, (size_t)Q * S * c->Ls);
-  CK(cudaMemcpy(c->eoff, c->eoff_h.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->slot_codon, c->slot_codon_h.data(), c->slot_codon_h.size(), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->slot_flags, c->slot_flags_h.data(), c->slot_flags_h.size(), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->query_codon, query_codons, (size_t)Q * S, cudaMemcpyHostToDevice));
-  {
-    std::vector<uint8_t> bits((size_t)Q * H);
-    for (size_t i = 0; i < bits.size(); i++) bits[i] = (hla_types[i] == '1');
-    CK(cudaMemcpy(c->hla, bits.data(), bits.size(), cudaMemcpyHostToDevice));
-  }
-
-  // temporaries for the gather
-  int8_t *d_trip = nullptr, *d_cons = nullptr;
-  int *d_closest = nullptr;
-  uint8_t *d_slot_of = nullptr;
   for (size_t i = 0; i < (size_t)Q * L; i++)
     REQUIRE(closest_refs[i] >= 0 && closest_refs[i] < N, "closest_refs entry out of range");
-  CK(cudaMalloc((void **)&d_trip, (size_t)N * S));
-  CK(cudaMalloc((void **)&d_cons, (size_t)Q * 3 * S));
-  CK(cudaMalloc((void **)&d_closest, (size_t)Q * L * sizeof(int)));
-  CK(cudaMalloc((void **)&d_slot_of, (size_t)S * 64));
-  CK(cudaMemcpyAsync(d_trip, ref_triplets, (size_t)N * S, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_cons, cons_query_nucls, (size_t)Q * 3 * S, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_closest, closest_refs, (size_t)Q * L * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
-  CK(mcq_launch_gather(d_trip, d_closest, d_cons, d_slot_of, c->G, Q, S, L, c->Ls, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_trip); cudaFree(d_cons); cudaFree(d_closest); cudaFree(d_slot_of);
 
-  const size_t cells = (size_t)Q * S * c->Ls;
-  ALLOC(c->F, cells); ALLOC(c->B, cells); ALLOC(c->T, cells);
-  ALLOC(c->Fn, (size_t)Q * S); ALLOC(c->Bn, (size_t)Q * S); ALLOC(c->Tn, (size_t)Q * S);
-  const size_t rows = (size_t)Q * c->ES;
-  ALLOC(c->E, rows); ALLOC(c->A, rows); ALLOC(c->Et, rows); ALLOC(c->At, rows);
-  CK(cudaMemsetAsync(c->E, 0, rows * sizeof(double), c->stream));
-  CK(cudaMemsetAsync(c->A, 0, rows * sizeof(double), c->stream));
-  CK(cudaMemsetAsync(c->Et, 0, rows * sizeof(double), c->stream));
-  CK(cudaMemsetAsync(c->At, 0, rows * sizeof(double), c->stream));
-  CK(cudaMemsetAsync(c->Fn, 0, (size_t)Q * S * sizeof(int), c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  if (!c->have_static) {
+    c->eoff_h = eoff_h; c->slot_codon_h = slot_codon_h; c->slot_flags_h = slot_flags_h;
+    c->ES = (eoff_h[S] + 1) / 2 * 2;
+    ALLOC(c->eoff, (size_t)S + 1);
+    ALLOC(c->slot_codon, slot_codon_h.size());
+    ALLOC(c->slot_flags, slot_flags_h.size());
+    ALLOC(c->cons_codon, (size_t)S);
+    ALLOC(c->query_codon, (size_t)Q * S);
+    ALLOC(c->hla, (size_t)Q * H);
+    ALLOC(c->G, (size_t)Q * S * c->Ls);
+    ALLOC(c->st_trip, (size_t)N * S);
+    ALLOC(c->st_cons, (size_t)Q * 3 * S);
+    ALLOC(c->st_closest, (size_t)Q * L);
+    ALLOC(c->st_slot_of, (size_t)S * 64);
+    const size_t cells = (size_t)Q * S * c->Ls;
+    ALLOC(c->F, cells); ALLOC(c->B, cells); ALLOC(c->T, cells);
+    ALLOC(c->Fn, (size_t)Q * S); ALLOC(c->Bn, (size_t)Q * S); ALLOC(c->Tn, (size_t)Q * S);
+    const size_t rows = (size_t)Q * c->ES;
+    ALLOC(c->E, rows); ALLOC(c->A, rows); ALLOC(c->Et, rows); ALLOC(c->At, rows);
+    CK(cudaMemsetAsync(c->E, 0, rows * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->A, 0, rows * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->Et, 0, rows * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->At, 0, rows * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->Fn, 0, (size_t)Q * S * sizeof(int), c->stream));
+    c->st_bits.resize((size_t)Q * H);
+  } else {
+    REQUIRE(eoff_h == c->eoff_h && slot_codon_h == c->slot_codon_h && slot_flags_h == c->slot_flags_h,
+            "re-upload changes the per-site codon lists: create a new context");
+  }
+  CK(cudaMemcpyAsync(c->eoff, c->eoff_h.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->slot_codon, c->slot_codon_h.data(), c->slot_codon_h.size(), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->slot_flags, c->slot_flags_h.data(), c->slot_flags_h.size(), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->query_codon, query_codons, (size_t)Q * S, cudaMemcpyHostToDevice, c->stream));
+  for (size_t i = 0; i < c->st_bits.size(); i++) c->st_bits[i] = (hla_types[i] == '1');
+  CK(cudaMemcpyAsync(c->hla, c->st_bits.data(), c->st_bits.size(), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->st_trip, ref_triplets, (size_t)N * S, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->st_cons, cons_query_nucls, (size_t)Q * 3 * S, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->st_closest, closest_refs, (size_t)Q * L * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
+  {
+    KScope ks(c, MCQ_K_GATHER);
+    CK(mcq_launch_gather(c->st_trip, c->st_closest, c->st_cons, c->st_slot_of, c->G, Q, S, L, c->Ls, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   c->have_static = true;
+  c->have_state = false;
+  c->has_pending = false;
   return 0;
 }
 
@@ -374,8 +458,8 @@ static int run_emission(mcq_ctx *c, int start, int end, int which_hla, int mode,
   a.st = make_static(c); a.m = c->m; a.ov = ov;
   a.start = start; a.end = end; a.which_hla = which_hla; a.mode = mode;
   a.Esrc = Es; a.Asrc = As; a.Edst = Ed; a.Adst = Ad;
+  KScope ks(c, MCQ_K_EMISSION);
   CK(mcq_launch_emission(a, c->stream));
-  c->launches++;
   return 0;
 }
 
@@ -390,8 +474,8 @@ static int run_forward(mcq_ctx *c, const double *E, int start, int end, const do
   a.B = c->B; a.Bn = c->Bn; a.llk_out = llk_out; a.llk_keep = c->llk_cur;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
   a.logBIG = c->logBIG;
+  KScope ks(c, MCQ_K_FORWARD);
   CK(mcq_launch_forward(a, c->stream));
-  c->launches++;
   return 0;
 }
 
@@ -400,15 +484,17 @@ static int run_backward(mcq_ctx *c, int update, bool sparse, int hla) {
   a.st = make_static(c);
   a.E = c->E; a.R = c->m.R; a.B = c->B; a.Bn = c->Bn; a.update = update;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
+  KScope ks(c, MCQ_K_BACKWARD);
   CK(mcq_launch_backward(a, c->stream));
-  c->launches++;
   return 0;
 }
 
 // total over the shard (+ all ranks), brought to the host
 static int reduce_llk(mcq_ctx *c, const double *per_query, double *out) {
-  CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->stream));
-  c->launches++;
+  {
+    KScope ks(c, MCQ_K_SUM);
+    CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->stream));
+  }
   if (c->comm) {
     int r = g_nccl.AllReduce(c->d_sum, c->d_sum, 1, kNcclDouble, kNcclSum, c->comm, c->stream);
     if (r != 0) return mcq_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce failed");
@@ -508,8 +594,10 @@ extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_ll
       if (run_forward(c, c->Et, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
       break;
     case MCQ_PROP_MU:
-      CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->E, c->A, c->Et, c->At, c->stream));
-      c->launches++;
+      {
+        KScope ks(c, MCQ_K_EMISSION);
+        CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->E, c->A, c->Et, c->At, c->stream));
+      }
       if (run_forward(c, c->Et, 0, S - 1, c->F, c->Fn, c->T, c->Tn, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
       break;
     default:
@@ -544,14 +632,18 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
     if (run_backward(c, S - 1, false, 0)) return 1;
   } else {
     const bool sparse = (ov.kind == MCQ_PROP_ESC) && c->opt_sparse_esc != 0;
-    CK(mcq_launch_commit_params(st, c->m, ov, c->stream));
-    c->launches++;
-    if (ov.kind != MCQ_PROP_REC) {
-      CK(mcq_launch_commit_rows(st, c->Et, c->At, c->E, c->A, c->eoff_h[ov.start], c->eoff_h[ov.end + 1], c->stream));
-      c->launches++;
+    {
+      KScope ks(c, MCQ_K_COMMIT);
+      CK(mcq_launch_commit_params(st, c->m, ov, c->stream));
     }
-    CK(mcq_launch_commit_cols(st, c->T, c->Tn, c->F, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
-    c->launches++;
+    if (ov.kind != MCQ_PROP_REC) {
+      KScope ks(c, MCQ_K_COMMIT);
+      CK(mcq_launch_commit_rows(st, c->Et, c->At, c->E, c->A, c->eoff_h[ov.start], c->eoff_h[ov.end + 1], c->stream));
+    }
+    {
+      KScope ks(c, MCQ_K_COMMIT);
+      CK(mcq_launch_commit_cols(st, c->T, c->Tn, c->F, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
+    }
     if (ov.end + 1 < S)
       if (run_forward(c, c->E, ov.end + 1, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
     if (run_backward(c, ov.end, sparse, ov.hla)) return 1;

@@ -63,7 +63,9 @@ class Problem:
 
 
 def build_problem(ref_seqs, query_seqs, hla, closest_refs, kappa=gen.KAPPA, phi=gen.PHI,
-                  prior=None) -> Problem:
+                  prior=None, cons_q=None) -> Problem:
+    """``cons_q`` (Q,3S) may carry precomputed per-query consensus codes (same rule, computed
+    elsewhere, e.g. on the GPU for large shapes)."""
     ref_seqs = np.asarray(ref_seqs, np.uint8)
     query_seqs = np.asarray(query_seqs, np.uint8)
     N, nb = ref_seqs.shape
@@ -79,9 +81,11 @@ def build_problem(ref_seqs, query_seqs, hla, closest_refs, kappa=gen.KAPPA, phi=
     qry_codes = gen.base_codes(query_seqs)
     consensus = majority_codes(ref_codes)       # consensus of the references (default -c)
 
-    cons_q = np.empty((Q, nb), np.int8)
-    for q in range(Q):
-        cons_q[q] = majority_codes(ref_codes[closest_refs[q]])
+    if cons_q is None:
+        cons_q = np.empty((Q, nb), np.int8)
+        for q in range(Q):
+            cons_q[q] = majority_codes(ref_codes[closest_refs[q]])
+    cons_q = np.ascontiguousarray(cons_q, np.int8)
     qry_filled = np.where(qry_codes == 4, cons_q, qry_codes)
 
     ref_triplets = gen.to_triplets(ref_codes)
@@ -92,10 +96,8 @@ def build_problem(ref_seqs, query_seqs, hla, closest_refs, kappa=gen.KAPPA, phi=
 
     n_site = np.zeros(S, np.int32)
     site_codons = np.zeros((S, 64), np.int8)
-    seen = np.zeros((S, 64), bool)
-    seen[np.arange(S)[None, :].repeat(N, 0), ref_codons.astype(np.int64)] = True
     for s in range(S):
-        cs = np.nonzero(seen[s])[0]
+        cs = np.nonzero(np.bincount(ref_codons[:, s].astype(np.int64), minlength=64))[0]
         n_site[s] = cs.size
         site_codons[s, :cs.size] = cs
 
