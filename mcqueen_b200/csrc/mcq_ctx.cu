@@ -92,7 +92,7 @@ struct mcq_ctx {
   // static (device)
   uint8_t *G = nullptr, *slot_codon = nullptr, *slot_flags = nullptr, *cons_codon = nullptr;
   uint8_t *query_codon = nullptr, *hla = nullptr;
-  int *eoff = nullptr;
+  int *eoff = nullptr, *slot_site = nullptr;
   // static (host mirrors)
   std::vector<int> eoff_h;
   std::vector<uint8_t> slot_codon_h, slot_flags_h;
@@ -145,6 +145,7 @@ static McqStatic make_static(const mcq_ctx *c) {
   st.Q = c->d.num_query; st.S = c->d.num_sites; st.L = c->d.closest_n; st.Ls = c->Ls;
   st.N = c->d.total_num_refs; st.H = c->d.num_hla_types; st.ES = c->ES;
   st.G = c->G; st.eoff = c->eoff; st.slot_codon = c->slot_codon; st.slot_flags = c->slot_flags;
+  st.slot_site = c->slot_site;
   st.cons_codon = c->cons_codon; st.query_codon = c->query_codon; st.hla = c->hla;
   return st;
 }
@@ -231,7 +232,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->d.device);
   cudaStreamSynchronize(c->stream);
-  void *ptrs[] = {c->G, c->slot_codon, c->slot_flags, c->cons_codon, c->query_codon, c->hla, c->eoff,
+  void *ptrs[] = {c->slot_site, c->G, c->slot_codon, c->slot_flags, c->cons_codon, c->query_codon, c->hla, c->eoff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->E, c->A, c->Et, c->At,
                   c->llk_cur, c->llk_prop, c->d_sum, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of};
@@ -358,6 +359,13 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     ALLOC(c->eoff, (size_t)S + 1);
     ALLOC(c->slot_codon, slot_codon_h.size());
     ALLOC(c->slot_flags, slot_flags_h.size());
+    ALLOC(c->slot_site, slot_flags_h.size());
+    {
+      std::vector<int> site_of(slot_flags_h.size());
+      for (int s = 0; s < S; s++)
+        for (int k = eoff_h[s]; k < eoff_h[s + 1]; k++) site_of[k] = s;
+      CK(cudaMemcpy(c->slot_site, site_of.data(), site_of.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     ALLOC(c->cons_codon, (size_t)S);
     ALLOC(c->query_codon, (size_t)Q * S);
     ALLOC(c->hla, (size_t)Q * H);
@@ -457,6 +465,7 @@ static int run_emission(mcq_ctx *c, int start, int end, int which_hla, int mode,
   EmisArgs a;
   a.st = make_static(c); a.m = c->m; a.ov = ov;
   a.start = start; a.end = end; a.which_hla = which_hla; a.mode = mode;
+  a.k0 = c->eoff_h[start]; a.k1 = c->eoff_h[end + 1];
   a.Esrc = Es; a.Asrc = As; a.Edst = Ed; a.Adst = Ad;
   KScope ks(c, MCQ_K_EMISSION);
   CK(mcq_launch_emission(a, c->stream));
@@ -596,7 +605,7 @@ extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_ll
     case MCQ_PROP_MU:
       {
         KScope ks(c, MCQ_K_EMISSION);
-        CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->E, c->A, c->Et, c->At, c->stream));
+        CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->E, c->A, c->Et, c->At, c->eoff_h[S], c->stream));
       }
       if (run_forward(c, c->Et, 0, S - 1, c->F, c->Fn, c->T, c->Tn, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
       break;

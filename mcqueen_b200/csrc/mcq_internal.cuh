@@ -36,6 +36,7 @@ struct McqStatic {           // device-resident static tables
   const int *eoff;           // [S+1]
   const uint8_t *slot_codon; // [ES]  codon of each slot
   const uint8_t *slot_flags; // [ES]  bit0: codon is in ref_site_codons[s]; bit1: codon is the consensus
+  const int *slot_site;      // [ES]  site each slot belongs to
   const uint8_t *cons_codon; // [S]
   const uint8_t *query_codon;// [Q][S]
   const uint8_t *hla;        // [Q][H] 0/1
@@ -79,6 +80,7 @@ struct EmisArgs {
   McqModel m;
   McqOverride ov;
   int start, end, which_hla, mode;
+  int k0, k1;                // slot bounds of the site range: eoff[start], eoff[end+1]
   const double *Esrc, *Asrc;
   double *Edst, *Adst;
 };
@@ -92,7 +94,7 @@ cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_emission(const EmisArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new,
-                                  const double *E, const double *A, double *Eo, double *Ao,
+                                  const double *E, const double *A, double *Eo, double *Ao, int nslots,
                                   cudaStream_t stream);
 cudaError_t mcq_launch_commit_cols(const McqStatic &st, const double *T, const int *Tn, double *F, int *Fn,
                                    int start, int end, const uint8_t *active, int active_hla,

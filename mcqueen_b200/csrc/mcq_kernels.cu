@@ -63,44 +63,58 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K0: gathered codon-slot table.  Tile = 32 sites x 32 states through shared memory: reads of
-// ref_triplets run along a reference's row (sites), writes of G along states.
+// K0: gathered codon-slot table.  Tile = 128 sites x 64 states through shared memory: a warp
+// reads 128 consecutive sites of one reference row (4 per lane), and writes 64 consecutive
+// states of two site rows (4 per lane), so both sides move whole 32-byte sectors.
 // ------------------------------------------------------------------------------------------
+#define GT_S 128
+#define GT_R 64
 __global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_triplets,
                                                 const int *__restrict__ closest,
                                                 const int8_t *__restrict__ cons_nucls,
                                                 const uint8_t *__restrict__ slot_of,
                                                 uint8_t *__restrict__ G, int S, int L, int Ls) {
-  __shared__ uint8_t tile[32][33];
+  __shared__ uint8_t tile[GT_S][GT_R + 1];   // odd row stride: conflict-free transposed stores
   const int q = blockIdx.z;
-  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows per pass
-  const int s = s0 + tx;
-  int c0 = 0, c1 = 0, c2 = 0;
-  if (s < S) {
-    const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
-    c0 = cn[0]; c1 = cn[1]; c2 = cn[2];
+  const int s0 = blockIdx.x * GT_S, r0 = blockIdx.y * GT_R;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // read phase: lane owns sites s0+4*lane .. +3
+  int cn[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int s = s0 + 4 * lane + i;
+#pragma unroll
+    for (int p = 0; p < 3; p++) cn[i][p] = (s < S) ? cons_nucls[(size_t)q * 3 * S + 3 * s + p] : 0;
   }
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
-    const int rr = ty + 8 * p, r = r0 + rr;
-    uint8_t slot = MCQ_NOSLOT;
-    if (s < S && r < L) {
-      const int ref = closest[(size_t)q * L + r];
-      const int t = ref_triplets[(size_t)ref * S + s];
-      int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
-      if (d0 == 4) d0 = c0;
-      if (d1 == 4) d1 = c1;
-      if (d2 == 4) d2 = c2;
-      slot = slot_of[s * 64 + (d0 * 16 + d1 * 4 + d2)];
+  for (int pass = 0; pass < GT_R / 8; pass++) {
+    const int rr = warp + 8 * pass, r = r0 + rr;
+    const int ref = (r < L) ? closest[(size_t)q * L + r] : 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int s = s0 + 4 * lane + i;
+      uint8_t slot = MCQ_NOSLOT;
+      if (s < S && r < L) {
+        const int t = ref_triplets[(size_t)ref * S + s];
+        int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
+        if (d0 == 4) d0 = cn[i][0];
+        if (d1 == 4) d1 = cn[i][1];
+        if (d2 == 4) d2 = cn[i][2];
+        slot = slot_of[s * 64 + (d0 * 16 + d1 * 4 + d2)];
+      }
+      tile[4 * lane + i][rr] = slot;
     }
-    tile[rr][tx] = slot;
   }
   __syncthreads();
+  // write phase: half a warp covers the 64 states of one site row
+  const int sub = lane >> 4, l16 = lane & 15;
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
-    const int ss = ty + 8 * p, so = s0 + ss, r = r0 + tx;
-    if (so < S && r < Ls) G[((size_t)q * S + so) * Ls + r] = tile[tx][ss];
+  for (int pass = 0; pass < GT_S / 16; pass++) {
+    const int ss = 2 * (warp + 8 * pass) + sub, so = s0 + ss, r = r0 + 4 * l16;
+    if (so < S && r < Ls) {   // Ls is a multiple of 16, so r..r+3 stay inside the row
+      const uchar4 v = make_uchar4(tile[ss][4 * l16], tile[ss][4 * l16 + 1], tile[ss][4 * l16 + 2], tile[ss][4 * l16 + 3]);
+      *reinterpret_cast<uchar4 *>(G + ((size_t)q * S + so) * Ls + r) = v;
+    }
   }
 }
 
@@ -110,7 +124,7 @@ cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, co
   // gridDim.z is limited to 65535: walk the queries in slabs
   for (int q0 = 0; q0 < Q; q0 += 65535) {
     int nq = Q - q0 < 65535 ? Q - q0 : 65535;
-    dim3 grid((S + 31) / 32, (Ls + 31) / 32, nq);
+    dim3 grid((S + GT_S - 1) / GT_S, (Ls + GT_R - 1) / GT_R, nq);
     k_gather<<<grid, 256, 0, stream>>>(ref_triplets, closest + (size_t)q0 * L,
                                        cons_nucls + (size_t)q0 * 3 * S, slot_of,
                                        G + (size_t)q0 * S * Ls, S, L, Ls);
@@ -143,135 +157,174 @@ __device__ __forceinline__ double eff_rate_out(const McqModel &m, const McqOverr
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: emission rows.  One thread per (query, site) of the range; it walks the site's slots.
+// K3: emission rows.  One thread per (query, slot) of the site range: consecutive threads write
+// consecutive entries of the query's compact row (coalesced 8-byte stores to E and A).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_emission(const EmisArgs a) {
-  const int W = a.end - a.start + 1;
+__global__ void __launch_bounds__(256) k_emission(const EmisArgs a) {
+  const int k0 = a.st.eoff[a.start], W = a.st.eoff[a.end + 1] - k0;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)a.st.Q * W) return;
-  const int q = (int)(idx / W), s = a.start + (int)(idx % W);
+  const int q = (int)(idx / W), k = k0 + (int)(idx % W);
+  const int s = a.st.slot_site[k];
   const int S = a.st.S, H = a.st.H;
   const McqModel &m = a.m;
-  const uint8_t *hla = a.st.hla + (size_t)q * H;
-  const int k0 = a.st.eoff[s], k1 = a.st.eoff[s + 1];
-  const size_t row = (size_t)q * a.st.ES;
+  const uint8_t *__restrict__ hla = a.st.hla + (size_t)q * H;
+  const size_t o = (size_t)q * a.st.ES + k;
   const bool copy_through = (a.Edst != a.Esrc);
 
+  const int c1 = a.st.slot_codon[k];
+  const uint8_t fl = a.st.slot_flags[k];
+  const bool in_list = fl & 1, is_cons = fl & 2;
   // an ESC update of one HLA leaves non-carriers untouched (mcmc_moves.c:61-62)
   const bool skip = (a.mode == 0 && a.which_hla >= 0 && hla[a.which_hla] == 0);
-  if (skip) {
-    if (copy_through)
-      for (int k = k0; k < k1; k++) { a.Edst[row + k] = a.Esrc[row + k]; a.Adst[row + k] = a.Asrc[row + k]; }
+  const bool do_rev = !skip && !is_cons && in_list && a.mode != 0;
+  const bool do_esc = !skip && is_cons && a.mode != 1;
+  if (!do_rev && !do_esc) {
+    if (copy_through) { a.Edst[o] = a.Esrc[o]; a.Adst[o] = a.Asrc[o]; }
     return;
   }
-
   const int cons = a.st.cons_codon[s], to = a.st.query_codon[(size_t)q * S + s];
   const double omega = eff_omega(m, a.ov, s);
   const double kappa = m.kappa, phi = m.phi, mu = m.mu;
   const double N = (double)a.st.N;
-  double esc_prod = 1.0;
-  for (int h = 0; h < H; h++)
-    if (hla[h]) esc_prod *= eff_esc(m, a.ov, h, s, S);
-  const double rev = eff_rev(m, a.ov, s);
   const double back = (1 - phi) * m.prior[to];
-
-  for (int k = k0; k < k1; k++) {
-    const int c1 = a.st.slot_codon[k];
-    const uint8_t fl = a.st.slot_flags[k];
-    const bool in_list = fl & 1, is_cons = fl & 2;
-    double A, v;
-    bool done = false;
-    if (!is_cons && in_list && a.mode != 0) {
-      // reversion part: a non-consensus codon of the panel (mcmc_moves.c:78-124)
-      const double rate = eff_rate_out(m, a.ov, s, c1, in_list) + (rev - 1) * step_rate(omega, kappa, c1, cons);
-      A = 1 - N / (N + rate * 4 * mu);
-      const double gamma = phi / rate;
-      const double mm = step_rate(omega, kappa, c1, to);
-      if (to == cons) v = A * (gamma * rev * mm + back);
-      else {
-        v = A * (gamma * mm + back);
-        if (c1 == to) v += (1 - A);
-      }
-      done = true;
-    } else if (is_cons && a.mode != 1) {
-      // escape part: the consensus row (mcmc_moves.c:125-167)
-      const double nsum = kappa * d_cnt[0][cons] + d_cnt[1][cons];
-      const double rate = eff_rate_out(m, a.ov, s, cons, in_list) + (esc_prod - 1) * omega * nsum;
-      A = 1 - N / (N + rate * 4 * mu);
-      if (cons == 15 || cons == 35) {
-        const double gamma = phi / nsum;
-        v = A * (gamma * ns_rate(kappa, cons, to) + back);
-      } else {
-        const double gamma = phi / rate;
-        v = A * (gamma * (esc_prod * omega * ns_rate(kappa, cons, to) + s_rate(kappa, cons, to)) + back);
-      }
-      if (to == cons) v = (1 - A) * (1 - back) + back;
-      done = true;
+  double A, v;
+  if (do_rev) {
+    // reversion part: a non-consensus codon of the panel (mcmc_moves.c:78-124)
+    const double rev = eff_rev(m, a.ov, s);
+    const double rate = eff_rate_out(m, a.ov, s, c1, in_list) + (rev - 1) * step_rate(omega, kappa, c1, cons);
+    A = 1 - N / (N + rate * 4 * mu);
+    const double gamma = phi / rate;
+    const double mm = step_rate(omega, kappa, c1, to);
+    if (to == cons) v = A * (gamma * rev * mm + back);
+    else {
+      v = A * (gamma * mm + back);
+      if (c1 == to) v += (1 - A);
     }
-    if (done) { a.Edst[row + k] = v; a.Adst[row + k] = A; }
-    else if (copy_through) { a.Edst[row + k] = a.Esrc[row + k]; a.Adst[row + k] = a.Asrc[row + k]; }
+  } else {
+    // escape part: the consensus row (mcmc_moves.c:125-167)
+    double esc_prod = 1.0;
+    for (int h = 0; h < H; h++)
+      if (hla[h]) esc_prod *= eff_esc(m, a.ov, h, s, S);
+    const double nsum = kappa * d_cnt[0][cons] + d_cnt[1][cons];
+    const double rate = eff_rate_out(m, a.ov, s, cons, in_list) + (esc_prod - 1) * omega * nsum;
+    A = 1 - N / (N + rate * 4 * mu);
+    if (cons == 15 || cons == 35) {
+      const double gamma = phi / nsum;
+      v = A * (gamma * ns_rate(kappa, cons, to) + back);
+    } else {
+      const double gamma = phi / rate;
+      v = A * (gamma * (esc_prod * omega * ns_rate(kappa, cons, to) + s_rate(kappa, cons, to)) + back);
+    }
+    if (to == cons) v = (1 - A) * (1 - back) + back;
   }
+  a.Edst[o] = v;
+  a.Adst[o] = A;
 }
 
 cudaError_t mcq_launch_emission(const EmisArgs &a, cudaStream_t stream) {
-  const size_t n = (size_t)a.st.Q * (a.end - a.start + 1);
-  k_emission<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(a);
+  // the slot bounds of the range are needed for the grid size: they come with the args
+  const size_t n = (size_t)a.st.Q * (a.k1 - a.k0);
+  if (n == 0) return cudaSuccess;
+  k_emission<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
-// K3b: mu rescale (mcmc_moves.c:1082-1111).  The reference walks ref_site_codons only; the
-// consensus slot of a site whose consensus codon no reference shows is rescaled as well (the
-// reference leaves that tmp entry unwritten - uninitialised memory, SURVEY.md §8c hazard 1).
+// K3b: mu rescale (mcmc_moves.c:1082-1111), one thread per (query, slot).  The reference walks
+// ref_site_codons only; the consensus slot of a site whose consensus codon no reference shows is
+// rescaled as well (the reference leaves that tmp entry unwritten - uninitialised memory,
+// SURVEY.md §8c hazard 1).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_mu_rescale(const McqStatic st, const McqModel m, double mu_new,
+__global__ void __launch_bounds__(256) k_mu_rescale(const McqStatic st, const McqModel m, double mu_new,
                                                     const double *__restrict__ E, const double *__restrict__ A,
-                                                    double *__restrict__ Eo, double *__restrict__ Ao) {
+                                                    double *__restrict__ Eo, double *__restrict__ Ao, int nslots) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)st.Q * st.S) return;
-  const int q = (int)(idx / st.S), s = (int)(idx % st.S);
+  if (idx >= (size_t)st.Q * nslots) return;
+  const int q = (int)(idx / nslots), k = (int)(idx % nslots);
+  const int s = st.slot_site[k];
   const int to = st.query_codon[(size_t)q * st.S + s];
   const double N = (double)st.N;
-  const size_t row = (size_t)q * st.ES;
-  for (int k = st.eoff[s]; k < st.eoff[s + 1]; k++) {
-    const int c1 = st.slot_codon[k];
-    const double a = A[row + k];
-    double rate = 0.0;
-    if (a != 0) rate = (N / (1 - a) - N) / (4 * m.mu);
-    const double an = 1 - N / (N + rate * 4 * mu_new);
-    double v;
-    if (to != c1) v = (a == 0) ? 0.0 : E[row + k] * an / a;
-    else v = 1 - an + (1 - m.phi) * m.prior[c1] * an;
-    Ao[row + k] = an;
-    Eo[row + k] = v;
-  }
+  const size_t o = (size_t)q * st.ES + k;
+  const int c1 = st.slot_codon[k];
+  const double a = A[o];
+  double rate = 0.0;
+  if (a != 0) rate = (N / (1 - a) - N) / (4 * m.mu);
+  const double an = 1 - N / (N + rate * 4 * mu_new);
+  double v;
+  if (to != c1) v = (a == 0) ? 0.0 : E[o] * an / a;
+  else v = 1 - an + (1 - m.phi) * m.prior[c1] * an;
+  Ao[o] = an;
+  Eo[o] = v;
 }
 
 cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new,
-                                  const double *E, const double *A, double *Eo, double *Ao,
+                                  const double *E, const double *A, double *Eo, double *Ao, int nslots,
                                   cudaStream_t stream) {
-  const size_t n = (size_t)st.Q * st.S;
-  k_mu_rescale<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(st, m, mu_new, E, A, Eo, Ao);
+  const size_t n = (size_t)st.Q * nslots;
+  k_mu_rescale<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, m, mu_new, E, A, Eo, Ao, nslots);
   return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// asynchronous global->shared copies (LDGSTS): a warp stages the codon-slot row G[q][s][.] and the
+// emission row E[q][eoff[s]..] of the sites ahead of the one it is computing
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+#define MCQ_PF 3                 // sites staged ahead of the one being computed
+#define MCQ_RING (MCQ_PF + 1)    // ring slots per warp
+
+// stage rows of site s into ring slot `slot` (one commit group per site, empty past the range)
+template <int NJ>
+__device__ __forceinline__ void stage_site(uint8_t *gring, double *ering, int slot, int s, bool valid,
+                                           const uint8_t *__restrict__ Gq, const double *__restrict__ Eq,
+                                           const int *__restrict__ eoff, int Ls, int lane) {
+  if (valid) {
+    const uint8_t *src = Gq + (size_t)s * Ls;
+    uint8_t *dst = gring + slot * (64 * NJ);
+#pragma unroll
+    for (int i = 0; i < (NJ + 7) / 8; i++) {
+      const int o = (lane + 32 * i) * 16;
+      if (o < Ls) cp_async16(dst + o, src + o);
+    }
+    const int k0 = eoff[s], K = eoff[s + 1] - k0;
+    double *ed = ering + slot * 64;
+    for (int k = lane; k < K; k += 32) cp_async8(ed + k, Eq + k0 + k);
+  }
+  cp_async_commit();
 }
 
 // ------------------------------------------------------------------------------------------
 // K4: forward recursion.  One warp per query; lane l holds states 64j+2l, 64j+2l+1 (j < NJ) of
-// the running column in registers.  Per site: one butterfly all-reduce (column sum, which both
-// decides the rescale and is the next site's recombination sum), one u16 load of G and one
-// 16-byte streaming store of F per lane per j, emission values gathered from the query's
-// compact row (L1-resident).
+// the running column in registers.  Per site: the site's G row (Ls bytes) and emission row
+// (K_s doubles) arrive in shared memory through cp.async, staged MCQ_PF sites ahead so that no
+// global-load latency sits on the recurrence; one butterfly all-reduce (the column sum, which
+// both decides the rescale and is the next site's recombination sum); one 16-byte streaming
+// store of F per lane per j (512 contiguous bytes per warp instruction).
 // ------------------------------------------------------------------------------------------
 template <int NJ>
 __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
+  __shared__ __align__(16) uint8_t s_g[4][MCQ_RING][64 * NJ];
+  __shared__ __align__(16) double s_e[4][MCQ_RING][64];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (q >= a.st.Q) return;
   if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) {
     if (lane == 0 && a.llk_out != nullptr) a.llk_out[q] = a.llk_keep[q];
     return;
   }
-  const int S = a.st.S, L = a.st.L, Ls = a.st.Ls;
+  const int S = a.st.S, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
   const uint8_t *__restrict__ Gq = a.st.G + qoff;
   const double *__restrict__ Eq = a.E + (size_t)q * a.st.ES;
@@ -279,11 +332,19 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
   double *__restrict__ Fo = a.Fout + qoff;
   int *__restrict__ Fno = a.Fn_out + (size_t)q * S;
   const double Nd = (double)a.st.N;
+  uint8_t *gring = &s_g[wib][0][0];
+  double *ering = &s_e[wib][0][0];
 
   int r0[NJ];
   bool inrow[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; j++) { r0[j] = 64 * j + 2 * lane; inrow[j] = r0[j] < Ls; }
+
+  // first site whose rows are needed: the seed column when start == 0
+  const int first = a.start;
+#pragma unroll
+  for (int i = 0; i < MCQ_PF; i++)
+    stage_site<NJ>(gring, ering, (first + i) % MCQ_RING, first + i, first + i <= a.end, Gq, Eq, eoff, Ls, lane);
 
   double p0[NJ], p1[NJ];   // the running column
   int s = a.start, cnt;
@@ -291,16 +352,20 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
 
   if (s == 0) {
     // column 0 is the bare emission and is never rescaled (forward_backward.c:27-39,102-111)
-    const int eo = eoff[0];
+    cp_async_wait<MCQ_PF - 1>();
+    __syncwarp();
+    stage_site<NJ>(gring, ering, (s + MCQ_PF) % MCQ_RING, s + MCQ_PF, s + MCQ_PF <= a.end, Gq, Eq, eoff, Ls, lane);
+    const uint8_t *gs = gring + (s % MCQ_RING) * (64 * NJ);
+    const double *es = ering + (s % MCQ_RING) * 64;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       p0[j] = 0.0; p1[j] = 0.0;
       if (inrow[j]) {
-        const unsigned gg = *reinterpret_cast<const uint16_t *>(Gq + r0[j]);
+        const unsigned gg = *reinterpret_cast<const uint16_t *>(gs + r0[j]);
         const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
-        if (g0 != MCQ_NOSLOT) p0[j] = Eq[eo + g0];
-        if (g1 != MCQ_NOSLOT) p1[j] = Eq[eo + g1];
+        if (g0 != MCQ_NOSLOT) p0[j] = es[g0];
+        if (g1 != MCQ_NOSLOT) p1[j] = es[g1];
         __stcs(reinterpret_cast<double2 *>(Fo + r0[j]), make_double2(p0[j], p1[j]));
       }
       loc += p0[j]; loc += p1[j];
@@ -329,34 +394,25 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
     tot = warp_sum(loc);
   }
 
-  // G of the current site is fetched one site ahead
-  unsigned gcur[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; j++)
-    gcur[j] = (inrow[j] && s <= a.end) ? *reinterpret_cast<const uint16_t *>(Gq + (size_t)s * Ls + r0[j]) : 0xFFFFu;
-
   for (; s <= a.end; ++s) {
-    const int eo = eoff[s];
-    double e0[NJ], e1[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      const unsigned g0 = gcur[j] & 0xFF, g1 = gcur[j] >> 8;
-      e0[j] = (g0 != MCQ_NOSLOT) ? Eq[eo + g0] : 0.0;
-      e1[j] = (g1 != MCQ_NOSLOT) ? Eq[eo + g1] : 0.0;
-    }
-    if (s < a.end) {
-#pragma unroll
-      for (int j = 0; j < NJ; j++)
-        if (inrow[j]) gcur[j] = __ldcs(reinterpret_cast<const uint16_t *>(Gq + (size_t)(s + 1) * Ls + r0[j]));
-    }
+    cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed (this lane's copies)
+    __syncwarp();                  // ... and every other lane's; slot of site s-1 is free again
+    stage_site<NJ>(gring, ering, (s + MCQ_PF) % MCQ_RING, s + MCQ_PF, s + MCQ_PF <= a.end, Gq, Eq, eoff, Ls, lane);
+    const uint8_t *gs = gring + (s % MCQ_RING) * (64 * NJ);
+    const double *es = ering + (s % MCQ_RING) * 64;
     const double Rs = (s == a.r_site) ? a.r_value : a.R[s];
     const double jump = tot * Rs / Nd;          // forward_backward.c:138
     const double stay = 1 - Rs;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      double v0 = jump; v0 += stay * p0[j]; v0 *= e0[j];
-      double v1 = jump; v1 += stay * p1[j]; v1 *= e1[j];
+      unsigned gg = 0xFFFFu;
+      if (inrow[j]) gg = *reinterpret_cast<const uint16_t *>(gs + r0[j]);
+      const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
+      const double e0 = (g0 != MCQ_NOSLOT) ? es[g0] : 0.0;
+      const double e1 = (g1 != MCQ_NOSLOT) ? es[g1] : 0.0;
+      double v0 = jump; v0 += stay * p0[j]; v0 *= e0;
+      double v1 = jump; v1 += stay * p1[j]; v1 *= e1;
       p0[j] = v0; p1[j] = v1;
       loc += v0; loc += v1;
     }
@@ -373,6 +429,7 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
       if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + r0[j]), make_double2(p0[j], p1[j]));
     if (lane == 0) Fno[s] = cnt;
   }
+  cp_async_wait<0>();
 
   // K6 epilogue: the per-query log-likelihood at the last column of the range
   if (a.llk_mode != 0) {
@@ -394,7 +451,6 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
     }
     if (lane == 0) a.llk_out[q] = log(dot) - nrm * a.logBIG;
   }
-  (void)L;
 }
 
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
