@@ -84,23 +84,26 @@ static const int kNcclSum = 0;     // ncclSum
 // ------------------------------------------------------------------------------------------
 struct mcq_ctx {
   mcq_dims d;
-  int Ls = 0, ES = 0;
+  int Ls = 0, NA = 0;          // NA = number of non-consensus slots (sum_s K_s)
+  size_t TL = 0;               // length of the shared emission table (64 * NA)
   cudaStream_t stream = nullptr;
   size_t bytes = 0;
   bool have_static = false, have_params = false, have_state = false;
 
   // static (device)
-  uint8_t *G = nullptr, *slot_codon = nullptr, *slot_flags = nullptr, *cons_codon = nullptr;
+  uint8_t *G = nullptr, *ncodon = nullptr, *cons_in_list = nullptr, *cons_codon = nullptr;
   uint8_t *query_codon = nullptr, *hla = nullptr;
-  int *eoff = nullptr, *slot_site = nullptr;
+  int *aoff = nullptr, *toff = nullptr, *nsite = nullptr;
   // static (host mirrors)
-  std::vector<int> eoff_h;
-  std::vector<uint8_t> slot_codon_h, slot_flags_h;
+  std::vector<int> aoff_h, toff_h;
+  std::vector<uint8_t> ncodon_h, cons_in_list_h, cons_codon_h, slot_of_h;
 
   McqModel m{};
   double *F = nullptr, *B = nullptr, *T = nullptr;
   int *Fn = nullptr, *Bn = nullptr, *Tn = nullptr;
-  double *E = nullptr, *A = nullptr, *Et = nullptr, *At = nullptr;
+  // emission rows: shared table + per-query consensus values, current and proposal ("tmp") sets
+  double *tab = nullptr, *atab = nullptr, *ec = nullptr, *ac = nullptr;
+  double *tab_t = nullptr, *atab_t = nullptr, *ec_t = nullptr, *ac_t = nullptr;
   double *llk_cur = nullptr, *llk_prop = nullptr, *d_sum = nullptr;
   double *h_sum = nullptr;   // pinned
 
@@ -143,9 +146,9 @@ static int dev_alloc(mcq_ctx *c, T **p, size_t n) {
 static McqStatic make_static(const mcq_ctx *c) {
   McqStatic st;
   st.Q = c->d.num_query; st.S = c->d.num_sites; st.L = c->d.closest_n; st.Ls = c->Ls;
-  st.N = c->d.total_num_refs; st.H = c->d.num_hla_types; st.ES = c->ES;
-  st.G = c->G; st.eoff = c->eoff; st.slot_codon = c->slot_codon; st.slot_flags = c->slot_flags;
-  st.slot_site = c->slot_site;
+  st.N = c->d.total_num_refs; st.H = c->d.num_hla_types;
+  st.G = c->G; st.aoff = c->aoff; st.toff = c->toff; st.ncodon = c->ncodon; st.nsite = c->nsite;
+  st.cons_in_list = c->cons_in_list;
   st.cons_codon = c->cons_codon; st.query_codon = c->query_codon; st.hla = c->hla;
   return st;
 }
@@ -232,9 +235,9 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->d.device);
   cudaStreamSynchronize(c->stream);
-  void *ptrs[] = {c->slot_site, c->G, c->slot_codon, c->slot_flags, c->cons_codon, c->query_codon, c->hla, c->eoff,
+  void *ptrs[] = {c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
-                  c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->E, c->A, c->Et, c->At,
+                  c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
                   c->llk_cur, c->llk_prop, c->d_sum, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -322,50 +325,47 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
             H = c->d.num_hla_types;
   CallScope scope(c);
 
-  // slot lists: the codons the panel shows at the site (ascending, amino_acids.c:155-176), plus
-  // the consensus codon when no reference shows it (create_codon_to_codon_HLA writes that row too)
-  std::vector<int> eoff_h(S + 1, 0);
-  std::vector<uint8_t> slot_codon_h, slot_flags_h;
+  // slots per site: 0 = the consensus codon, 1..K_s = the other codons the panel shows at the
+  // site in ascending order (amino_acids.c:155-176); everything else has no slot
+  std::vector<int> aoff_h(S + 1, 0), toff_h(S + 1, 0);
+  std::vector<uint8_t> ncodon_h, cons_in_list_h(S, 0), cons_codon_h(S, 0);
   std::vector<uint8_t> slot_of((size_t)S * 64, MCQ_NOSLOT);
   for (int s = 0; s < S; s++) {
     const int n = num_ref_site_codons[s];
     REQUIRE(n >= 0 && n <= 64, "num_ref_site_codons out of range");
     const int cons = (unsigned char)consensus_codons[s];
     REQUIRE(cons < 64, "consensus codon out of range");
-    bool has_cons = false;
+    cons_codon_h[s] = (uint8_t)cons;
+    slot_of[(size_t)s * 64 + cons] = 0;
     int k = 0;
     for (int i = 0; i < n; i++) {
       const int cd = (unsigned char)ref_site_codons[(size_t)s * 64 + i];
       REQUIRE(cd < 64, "reference codon out of range");
+      if (cd == cons) {
+        REQUIRE(!cons_in_list_h[s], "duplicate codon in ref_site_codons");
+        cons_in_list_h[s] = 1;
+        continue;
+      }
       REQUIRE(slot_of[(size_t)s * 64 + cd] == MCQ_NOSLOT, "duplicate codon in ref_site_codons");
-      slot_of[(size_t)s * 64 + cd] = (uint8_t)k++;
-      slot_codon_h.push_back((uint8_t)cd);
-      slot_flags_h.push_back((uint8_t)(1 | (cd == cons ? 2 : 0)));
-      has_cons |= (cd == cons);
+      slot_of[(size_t)s * 64 + cd] = (uint8_t)(1 + k++);
+      ncodon_h.push_back((uint8_t)cd);
     }
-    if (!has_cons) {
-      slot_of[(size_t)s * 64 + cons] = (uint8_t)k++;
-      slot_codon_h.push_back((uint8_t)cons);
-      slot_flags_h.push_back(2);
-    }
-    eoff_h[s + 1] = eoff_h[s] + k;
+    aoff_h[s + 1] = aoff_h[s] + k;
+    toff_h[s + 1] = toff_h[s] + 64 * k;
   }
   for (size_t i = 0; i < (size_t)Q * L; i++)
     REQUIRE(closest_refs[i] >= 0 && closest_refs[i] < N, "closest_refs entry out of range");
 
   if (!c->have_static) {
-    c->eoff_h = eoff_h; c->slot_codon_h = slot_codon_h; c->slot_flags_h = slot_flags_h;
-    c->ES = (eoff_h[S] + 1) / 2 * 2;
-    ALLOC(c->eoff, (size_t)S + 1);
-    ALLOC(c->slot_codon, slot_codon_h.size());
-    ALLOC(c->slot_flags, slot_flags_h.size());
-    ALLOC(c->slot_site, slot_flags_h.size());
-    {
-      std::vector<int> site_of(slot_flags_h.size());
-      for (int s = 0; s < S; s++)
-        for (int k = eoff_h[s]; k < eoff_h[s + 1]; k++) site_of[k] = s;
-      CK(cudaMemcpy(c->slot_site, site_of.data(), site_of.size() * sizeof(int), cudaMemcpyHostToDevice));
-    }
+    c->aoff_h = aoff_h; c->toff_h = toff_h; c->ncodon_h = ncodon_h; c->cons_in_list_h = cons_in_list_h;
+    c->cons_codon_h = cons_codon_h; c->slot_of_h = slot_of;
+    c->NA = aoff_h[S];
+    c->TL = (size_t)toff_h[S];
+    ALLOC(c->aoff, (size_t)S + 1);
+    ALLOC(c->toff, (size_t)S + 1);
+    ALLOC(c->ncodon, (size_t)c->NA);
+    ALLOC(c->nsite, (size_t)c->NA);
+    ALLOC(c->cons_in_list, (size_t)S);
     ALLOC(c->cons_codon, (size_t)S);
     ALLOC(c->query_codon, (size_t)Q * S);
     ALLOC(c->hla, (size_t)Q * H);
@@ -377,21 +377,27 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     const size_t cells = (size_t)Q * S * c->Ls;
     ALLOC(c->F, cells); ALLOC(c->B, cells); ALLOC(c->T, cells);
     ALLOC(c->Fn, (size_t)Q * S); ALLOC(c->Bn, (size_t)Q * S); ALLOC(c->Tn, (size_t)Q * S);
-    const size_t rows = (size_t)Q * c->ES;
-    ALLOC(c->E, rows); ALLOC(c->A, rows); ALLOC(c->Et, rows); ALLOC(c->At, rows);
-    CK(cudaMemsetAsync(c->E, 0, rows * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->A, 0, rows * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->Et, 0, rows * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->At, 0, rows * sizeof(double), c->stream));
+    ALLOC(c->tab, c->TL); ALLOC(c->tab_t, c->TL); ALLOC(c->atab, (size_t)c->NA); ALLOC(c->atab_t, (size_t)c->NA);
+    const size_t qs = (size_t)Q * S;
+    ALLOC(c->ec, qs); ALLOC(c->ac, qs); ALLOC(c->ec_t, qs); ALLOC(c->ac_t, qs);
+    double *zero[] = {c->tab, c->tab_t, c->atab, c->atab_t, c->ec, c->ac, c->ec_t, c->ac_t};
+    const size_t zn[] = {c->TL, c->TL, (size_t)c->NA, (size_t)c->NA, qs, qs, qs, qs};
+    for (int i = 0; i < 8; i++) CK(cudaMemsetAsync(zero[i], 0, (zn[i] ? zn[i] : 1) * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->Fn, 0, (size_t)Q * S * sizeof(int), c->stream));
     c->st_bits.resize((size_t)Q * H);
+    std::vector<int> site_of((size_t)c->NA);
+    for (int s = 0; s < S; s++)
+      for (int k = aoff_h[s]; k < aoff_h[s + 1]; k++) site_of[k] = s;
+    CK(cudaMemcpy(c->nsite, site_of.data(), site_of.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->aoff, aoff_h.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->toff, toff_h.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->ncodon, ncodon_h.data(), ncodon_h.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->cons_in_list, cons_in_list_h.data(), S, cudaMemcpyHostToDevice));
   } else {
-    REQUIRE(eoff_h == c->eoff_h && slot_codon_h == c->slot_codon_h && slot_flags_h == c->slot_flags_h,
+    REQUIRE(aoff_h == c->aoff_h && ncodon_h == c->ncodon_h && cons_in_list_h == c->cons_in_list_h &&
+                cons_codon_h == c->cons_codon_h,
             "re-upload changes the per-site codon lists: create a new context");
   }
-  CK(cudaMemcpyAsync(c->eoff, c->eoff_h.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->slot_codon, c->slot_codon_h.data(), c->slot_codon_h.size(), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->slot_flags, c->slot_flags_h.data(), c->slot_flags_h.size(), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->query_codon, query_codons, (size_t)Q * S, cudaMemcpyHostToDevice, c->stream));
   for (size_t i = 0; i < c->st_bits.size(); i++) c->st_bits[i] = (hla_types[i] == '1');
@@ -460,24 +466,37 @@ extern "C" int mcq_ctx_get_params(mcq_ctx *c, double *mu, double *R, double *ome
 // ------------------------------------------------------------------------------------------
 // kernels sequencing helpers
 // ------------------------------------------------------------------------------------------
+struct EmisSet { double *tab, *atab, *ec, *ac; };
+static EmisSet cur_set(mcq_ctx *c) { return {c->tab, c->atab, c->ec, c->ac}; }
+static EmisSet tmp_set(mcq_ctx *c) { return {c->tab_t, c->atab_t, c->ec_t, c->ac_t}; }
+
+// create_codon_to_codon_HLA over sites start..end: mode 0 ESC (consensus values), 1 REV (shared table), 2 BOTH
 static int run_emission(mcq_ctx *c, int start, int end, int which_hla, int mode, const McqOverride &ov,
-                        const double *Es, const double *As, double *Ed, double *Ad) {
+                        const EmisSet &src, const EmisSet &dst) {
   EmisArgs a;
   a.st = make_static(c); a.m = c->m; a.ov = ov;
-  a.start = start; a.end = end; a.which_hla = which_hla; a.mode = mode;
-  a.k0 = c->eoff_h[start]; a.k1 = c->eoff_h[end + 1];
-  a.Esrc = Es; a.Asrc = As; a.Edst = Ed; a.Adst = Ad;
-  KScope ks(c, MCQ_K_EMISSION);
-  CK(mcq_launch_emission(a, c->stream));
+  a.start = start; a.end = end;
+  a.which_hla = (mode == 0) ? which_hla : -1;   // only an ESC-only update skips non-carriers (mcmc_moves.c:61-62)
+  a.a0 = c->aoff_h[start]; a.a1 = c->aoff_h[end + 1];
+  a.tab_src = src.tab; a.atab_src = src.atab; a.ec_src = src.ec; a.ac_src = src.ac;
+  a.tab_dst = dst.tab; a.atab_dst = dst.atab; a.ec_dst = dst.ec; a.ac_dst = dst.ac;
+  if (mode != 0) {
+    KScope ks(c, MCQ_K_EMISSION);
+    CK(mcq_launch_emission_table(a, c->stream));
+  }
+  if (mode != 1) {
+    KScope ks(c, MCQ_K_EMISSION);
+    CK(mcq_launch_emission_cons(a, c->stream));
+  }
   return 0;
 }
 
-static int run_forward(mcq_ctx *c, const double *E, int start, int end, const double *Fin, const int *Fn_in,
+static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int start, int end, const double *Fin, const int *Fn_in,
                        double *Fout, int *Fn_out, int llk_mode, double *llk_out, int r_site, double r_value,
                        bool sparse, int hla) {
   FwdArgs a;
   a.st = make_static(c);
-  a.E = E; a.R = c->m.R; a.r_site = r_site; a.r_value = r_value;
+  a.em.tab = tab; a.em.ec = ec; a.R = c->m.R; a.r_site = r_site; a.r_value = r_value;
   a.Fin = Fin; a.Fn_in = Fn_in; a.Fout = Fout; a.Fn_out = Fn_out;
   a.start = start; a.end = end; a.llk_mode = llk_mode;
   a.B = c->B; a.Bn = c->Bn; a.llk_out = llk_out; a.llk_keep = c->llk_cur;
@@ -491,7 +510,7 @@ static int run_forward(mcq_ctx *c, const double *E, int start, int end, const do
 static int run_backward(mcq_ctx *c, int update, bool sparse, int hla) {
   BwdArgs a;
   a.st = make_static(c);
-  a.E = c->E; a.R = c->m.R; a.B = c->B; a.Bn = c->Bn; a.update = update;
+  a.em.tab = c->tab; a.em.ec = c->ec; a.R = c->m.R; a.B = c->B; a.Bn = c->Bn; a.update = update;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
   KScope ks(c, MCQ_K_BACKWARD);
   CK(mcq_launch_backward(a, c->stream));
@@ -528,7 +547,7 @@ extern "C" int mcq_ctx_emission(mcq_ctx *c, int start, int end, int which_hla, i
   REQUIRE(mode >= 0 && mode <= 2 && which_hla >= -1 && which_hla < c->d.num_hla_types, "mode / HLA");
   CallScope scope(c);
   McqOverride none{}; none.kind = -1;
-  if (run_emission(c, start, end, which_hla, mode, none, c->E, c->A, c->E, c->A)) return 1;
+  if (run_emission(c, start, end, which_hla, mode, none, cur_set(c), cur_set(c))) return 1;
   if (!c->timing) CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -538,8 +557,8 @@ extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
   CallScope scope(c);
   const int S = c->d.num_sites;
   McqOverride none{}; none.kind = -1;
-  if (with_emission && run_emission(c, 0, S - 1, -1, 2, none, c->E, c->A, c->E, c->A)) return 1;
-  if (run_forward(c, c->E, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (with_emission && run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->has_pending = false;
   return 0;
@@ -558,8 +577,8 @@ extern "C" int mcq_ctx_init_state(mcq_ctx *c, double *llk) {
   CallScope scope(c);
   const int S = c->d.num_sites;
   McqOverride none{}; none.kind = -1;
-  if (run_emission(c, 0, S - 1, -1, 2, none, c->E, c->A, c->E, c->A)) return 1;
-  if (run_forward(c, c->E, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
   if (run_backward(c, S - 1, false, 0)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->have_state = true;
@@ -584,30 +603,32 @@ extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_ll
   switch (p->kind) {
     case MCQ_PROP_REC:
       REQUIRE(ov.start == ov.end, "REC proposal covers one site");
-      if (run_forward(c, c->E, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, ov.start, ov.v0, false, 0)) return 1;
+      if (run_forward(c, c->tab, c->ec, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, ov.start, ov.v0, false, 0)) return 1;
       break;
     case MCQ_PROP_SEL:
       REQUIRE(ov.start == ov.end, "SEL proposal covers one site");
-      if (run_emission(c, ov.start, ov.end, -1, 2, ov, c->E, c->A, c->Et, c->At)) return 1;
-      if (run_forward(c, c->Et, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      if (run_emission(c, ov.start, ov.end, -1, 2, ov, cur_set(c), tmp_set(c))) return 1;
+      if (run_forward(c, c->tab_t, c->ec_t, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
       break;
     case MCQ_PROP_ESC: {
       REQUIRE(ov.hla >= 0 && ov.hla < c->d.num_hla_types, "ESC proposal HLA index");
-      if (run_emission(c, ov.start, ov.end, ov.hla, 0, ov, c->E, c->A, c->Et, c->At)) return 1;
+      if (run_emission(c, ov.start, ov.end, ov.hla, 0, ov, cur_set(c), tmp_set(c))) return 1;
       const bool sparse = c->opt_sparse_esc != 0;
-      if (run_forward(c, c->Et, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, sparse, ov.hla)) return 1;
+      if (run_forward(c, c->tab, c->ec_t, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, sparse, ov.hla)) return 1;
       break;
     }
     case MCQ_PROP_REV:
-      if (run_emission(c, ov.start, ov.end, -1, 1, ov, c->E, c->A, c->Et, c->At)) return 1;
-      if (run_forward(c, c->Et, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      if (run_emission(c, ov.start, ov.end, -1, 1, ov, cur_set(c), tmp_set(c))) return 1;
+      if (run_forward(c, c->tab_t, c->ec, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
       break;
     case MCQ_PROP_MU:
       {
         KScope ks(c, MCQ_K_EMISSION);
-        CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->E, c->A, c->Et, c->At, c->eoff_h[S], c->stream));
+        CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->NA, (int)c->TL, c->tab, c->atab, c->ec, c->ac,
+                                 c->tab_t, c->atab_t, c->ec_t, c->ac_t, c->stream));
+        c->launches++;   // two kernels
       }
-      if (run_forward(c, c->Et, 0, S - 1, c->F, c->Fn, c->T, c->Tn, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      if (run_forward(c, c->tab_t, c->ec_t, 0, S - 1, c->F, c->Fn, c->T, c->Tn, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
       break;
     default:
       return mcq_fail(__FILE__, __LINE__, "unknown proposal kind");
@@ -636,7 +657,8 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
   const McqStatic st = make_static(c);
   if (ov.kind == MCQ_PROP_MU) {
     // the reference swaps the roles of the tmp and current arrays (mcmc_moves.c:1166-1169)
-    swap_ptr(c->F, c->T); swap_ptr(c->Fn, c->Tn); swap_ptr(c->E, c->Et); swap_ptr(c->A, c->At);
+    swap_ptr(c->F, c->T); swap_ptr(c->Fn, c->Tn); swap_ptr(c->tab, c->tab_t); swap_ptr(c->atab, c->atab_t);
+    swap_ptr(c->ec, c->ec_t); swap_ptr(c->ac, c->ac_t);
     c->m.mu = ov.v0;
     if (run_backward(c, S - 1, false, 0)) return 1;
   } else {
@@ -645,16 +667,24 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
       KScope ks(c, MCQ_K_COMMIT);
       CK(mcq_launch_commit_params(st, c->m, ov, c->stream));
     }
-    if (ov.kind != MCQ_PROP_REC) {
+    if (ov.kind == MCQ_PROP_SEL || ov.kind == MCQ_PROP_REV) {   // shared rows of the range
+      const size_t t0 = (size_t)c->toff_h[ov.start], t1 = (size_t)c->toff_h[ov.end + 1];
+      const size_t a0 = (size_t)c->aoff_h[ov.start], a1 = (size_t)c->aoff_h[ov.end + 1];
       KScope ks(c, MCQ_K_COMMIT);
-      CK(mcq_launch_commit_rows(st, c->Et, c->At, c->E, c->A, c->eoff_h[ov.start], c->eoff_h[ov.end + 1], c->stream));
+      CK(mcq_launch_copy(c->tab_t + t0, c->tab + t0, t1 - t0, c->stream));
+      CK(mcq_launch_copy(c->atab_t + a0, c->atab + a0, a1 - a0, c->stream));
+      c->launches++;
+    }
+    if (ov.kind == MCQ_PROP_SEL || ov.kind == MCQ_PROP_ESC) {   // per-query consensus values of the range
+      KScope ks(c, MCQ_K_COMMIT);
+      CK(mcq_launch_commit_cons(st, c->ec_t, c->ac_t, c->ec, c->ac, ov.start, ov.end, c->stream));
     }
     {
       KScope ks(c, MCQ_K_COMMIT);
       CK(mcq_launch_commit_cols(st, c->T, c->Tn, c->F, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
     }
     if (ov.end + 1 < S)
-      if (run_forward(c, c->E, ov.end + 1, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
+      if (run_forward(c, c->tab, c->ec, ov.end + 1, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
     if (run_backward(c, ov.end, sparse, ov.hla)) return 1;
   }
   swap_ptr(c->llk_cur, c->llk_prop);
@@ -689,13 +719,24 @@ extern "C" int mcq_ctx_get_table(mcq_ctx *c, int which, int q, double *out) {
   REQUIRE(q >= 0 && q < c->d.num_query, "query index");
   CK(cudaSetDevice(c->d.device));
   const int S = c->d.num_sites;
-  const double *src = which == MCQ_TAB_C2C ? c->E : which == MCQ_TAB_A ? c->A : which == MCQ_TAB_TMP_C2C ? c->Et : c->At;
+  const bool tmp = (which == MCQ_TAB_TMP_C2C || which == MCQ_TAB_TMP_A);
+  const bool want_a = (which == MCQ_TAB_A || which == MCQ_TAB_TMP_A);
   CK(cudaStreamSynchronize(c->stream));
-  std::vector<double> row(c->ES);
-  CK(cudaMemcpy(row.data(), src + (size_t)q * c->ES, row.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<double> cons(S), shared(want_a ? (size_t)c->NA : c->TL);
+  std::vector<uint8_t> qc(S);
+  const double *cons_src = want_a ? (tmp ? c->ac_t : c->ac) : (tmp ? c->ec_t : c->ec);
+  const double *sh_src = want_a ? (tmp ? c->atab_t : c->atab) : (tmp ? c->tab_t : c->tab);
+  CK(cudaMemcpy(cons.data(), cons_src + (size_t)q * S, S * sizeof(double), cudaMemcpyDeviceToHost));
+  if (!shared.empty()) CK(cudaMemcpy(shared.data(), sh_src, shared.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(qc.data(), c->query_codon + (size_t)q * S, S, cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof(double) * 64 * S);
-  for (int s = 0; s < S; s++)
-    for (int k = c->eoff_h[s]; k < c->eoff_h[s + 1]; k++) out[(size_t)c->slot_codon_h[k] * S + s] = row[k];
+  for (int s = 0; s < S; s++) {
+    out[(size_t)c->cons_codon_h[s] * S + s] = cons[s];
+    const int a0 = c->aoff_h[s], kr = c->aoff_h[s + 1] - a0;
+    for (int k = 0; k < kr; k++)
+      out[(size_t)c->ncodon_h[a0 + k] * S + s] =
+          want_a ? shared[a0 + k] : shared[(size_t)c->toff_h[s] + (size_t)qc[s] * kr + k];
+  }
   return 0;
 }
 

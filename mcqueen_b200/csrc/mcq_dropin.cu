@@ -6,7 +6,8 @@
 // batched mcq_ctx_* API.
 //
 // Layout bridge: the reference's F[L][S] (state-major) <-> the device's [S][Ls] (site-major);
-// codon_to_codon_HLA[64][S] <-> dense emission rows E[s][64] (slot == codon).
+// codon_to_codon_HLA[64][S] <-> one dense emission row per site, E[s][64] (slot == codon + 1; the
+// table degenerates to a single row per site because the caller's table is already per query).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -36,8 +37,8 @@ struct Scratch {
   cudaStream_t stream = nullptr;
   // device
   int8_t *trip = nullptr, *cons = nullptr;
-  int *closest = nullptr, *eoff = nullptr, *Fn = nullptr, *Tn = nullptr;
-  uint8_t *slot_of = nullptr, *slot_codon = nullptr, *G = nullptr;
+  int *closest = nullptr, *aoff = nullptr, *Fn = nullptr, *Tn = nullptr;
+  uint8_t *slot_of = nullptr, *G = nullptr;
   double *E = nullptr, *R = nullptr, *F = nullptr, *T = nullptr;
   // host staging
   std::vector<int8_t> h_trip;
@@ -45,10 +46,10 @@ struct Scratch {
   std::vector<int> h_n;
 
   void release() {
-    void *p[] = {trip, cons, closest, eoff, Fn, Tn, slot_of, slot_codon, G, E, R, F, T};
+    void *p[] = {trip, cons, closest, aoff, Fn, Tn, slot_of, G, E, R, F, T};
     for (void *x : p)
       if (x) cudaFree(x);
-    trip = cons = nullptr; closest = eoff = Fn = Tn = nullptr; slot_of = slot_codon = G = nullptr;
+    trip = cons = nullptr; closest = aoff = Fn = Tn = nullptr; slot_of = G = nullptr;
     E = R = F = T = nullptr;
   }
 
@@ -70,26 +71,24 @@ struct Scratch {
     DK(cudaMalloc((void **)&trip, (size_t)L * S));
     DK(cudaMalloc((void **)&cons, (size_t)3 * S));
     DK(cudaMalloc((void **)&closest, (size_t)L * sizeof(int)));
-    DK(cudaMalloc((void **)&eoff, (size_t)(S + 1) * sizeof(int)));
+    DK(cudaMalloc((void **)&aoff, (size_t)(S + 1) * sizeof(int)));
     DK(cudaMalloc((void **)&Fn, (size_t)S * sizeof(int)));
     DK(cudaMalloc((void **)&Tn, (size_t)S * sizeof(int)));
     DK(cudaMalloc((void **)&slot_of, (size_t)S * 64));
-    DK(cudaMalloc((void **)&slot_codon, (size_t)S * 64));
     DK(cudaMalloc((void **)&G, (size_t)S * Ls));
     DK(cudaMalloc((void **)&E, (size_t)S * 64 * sizeof(double)));
     DK(cudaMalloc((void **)&R, (size_t)S * sizeof(double)));
     DK(cudaMalloc((void **)&F, (size_t)S * Ls * sizeof(double)));
     DK(cudaMalloc((void **)&T, (size_t)S * Ls * sizeof(double)));
-    // identity slot scheme: 64 slots per site, slot == codon
+    // identity slot scheme: slots 1..64 of every site are codons 0..63, slot 0 is unused
     std::vector<int> eo(S + 1);
-    std::vector<uint8_t> so((size_t)S * 64), ident((size_t)L);
+    std::vector<uint8_t> so((size_t)S * 64);
     std::vector<int> cl(L);
     for (int s = 0; s <= S; s++) eo[s] = 64 * s;
-    for (size_t i = 0; i < so.size(); i++) so[i] = (uint8_t)(i & 63);
+    for (size_t i = 0; i < so.size(); i++) so[i] = (uint8_t)((i & 63) + 1);
     for (int r = 0; r < L; r++) cl[r] = r;
-    DK(cudaMemcpy(eoff, eo.data(), eo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    DK(cudaMemcpy(aoff, eo.data(), eo.size() * sizeof(int), cudaMemcpyHostToDevice));
     DK(cudaMemcpy(slot_of, so.data(), so.size(), cudaMemcpyHostToDevice));
-    DK(cudaMemcpy(slot_codon, so.data(), so.size(), cudaMemcpyHostToDevice));
     DK(cudaMemcpy(closest, cl.data(), cl.size() * sizeof(int), cudaMemcpyHostToDevice));
     DK(cudaMemset(F, 0, (size_t)S * Ls * sizeof(double)));
     DK(cudaMemset(T, 0, (size_t)S * Ls * sizeof(double)));
@@ -97,9 +96,9 @@ struct Scratch {
 
   McqStatic statics(int N) const {
     McqStatic st{};
-    st.Q = 1; st.S = S; st.L = L; st.Ls = Ls; st.N = N; st.H = 1; st.ES = 64 * S;
-    st.G = G; st.eoff = eoff; st.slot_codon = slot_codon; st.slot_flags = nullptr;
-    st.cons_codon = nullptr; st.query_codon = nullptr; st.hla = nullptr;
+    st.Q = 1; st.S = S; st.L = L; st.Ls = Ls; st.N = N; st.H = 1;
+    st.G = G; st.aoff = aoff; st.toff = aoff;   // one row of 64 entries per site
+    st.query_codon = nullptr;                   // -> always row 0 of the site's block
     return st;
   }
 
@@ -141,7 +140,7 @@ struct Scratch {
   void forward(int N, int start, int end, const double *Fin, const int *Fn_in, double *Fout, int *Fn_out) {
     FwdArgs a{};
     a.st = statics(N);
-    a.E = E; a.R = R; a.r_site = -1; a.r_value = 0.0;
+    a.em.tab = E; a.em.ec = nullptr; a.R = R; a.r_site = -1; a.r_value = 0.0;
     a.Fin = Fin; a.Fn_in = Fn_in; a.Fout = Fout; a.Fn_out = Fn_out;
     a.start = start; a.end = end; a.llk_mode = 0;
     a.active = nullptr; a.logBIG = log(MCQ_BIG);
@@ -217,7 +216,7 @@ extern "C" void update_B_numerical_recipes(int num_sites, int closest_n, int tot
   }
   BwdArgs a{};
   a.st = k.statics(total_num_refs);
-  a.E = k.E; a.R = k.R; a.B = k.F; a.Bn = k.Fn; a.update = update; a.active = nullptr;
+  a.em.tab = k.E; a.em.ec = nullptr; a.R = k.R; a.B = k.F; a.Bn = k.Fn; a.update = update; a.active = nullptr;
   DK(mcq_launch_backward(a, k.stream));
   const int top = update;   // update == S-1 rewrites the last column too
   k.get_columns(k.F, B, 0, top);

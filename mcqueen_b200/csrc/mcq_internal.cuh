@@ -1,14 +1,22 @@
 // mcq_internal.cuh - device-side data layout and kernel launch interfaces of libmcq_b200.
 //
 // Layout in HBM (one context = one shard of Q queries on one GPU):
-//   G      u8  [Q][S][Ls]   slot of the codon that copy state r shows at site s (0xFF = none/pad)
-//   F,B,T  f64 [Q][S][Ls]   forward, backward, proposal("tmp") forward; SITE-major, state fastest
+//   G      u8  [Q][S][Ls]   slot of the codon that copy state r shows at site s
+//                           (0 = the site's consensus codon, 1..K_s = its other reference codons in
+//                           ascending order, 0xFF = a codon no reference shows / padding)
+//   F,B,T  f64 [Q][S][Ls]   forward, backward, proposal ("tmp") forward; SITE-major, state fastest
 //   Fn,Bn,Tn i32 [Q][S]     rescale counters (F_rnorm etc. of the reference)
-//   E,A,Et,At f64 [Q][ES]   emission / "A" rows, compact: site s owns slots eoff[s]..eoff[s]+K_s-1,
-//                           slot k <-> codon slot_codon[eoff[s]+k]; ES = sum_s K_s (padded even)
 //   llk_cur, llk_prop f64 [Q]
 // Ls = L rounded up to 16 (128-byte rows).  A warp owns one query; lane l owns states
 // 64*j + 2*l + {0,1}, j < NJ = ceil(Ls/64).
+//
+// Emission rows.  The reference stores codon_to_codon_HLA[q][c1][s] per query (mcmc_moves.c:33-170).
+// For a non-consensus c1 the value depends on the query only through its codon `to` at the site
+// (the reversion coefficient is shared by all queries, mcmc_moves.c:70), so those rows are kept once
+// per (site, to):   TAB f64 [sum_s 64*K_s]: site s owns 64 rows (one per `to`) of K_s entries at
+// toff[s]; ATAB f64 [sum_s K_s] holds the matching "A" values (independent of `to`).  Only the
+// consensus row depends on the query's HLA profile: EC, AC f64 [Q][S].  A warp stages, per site,
+// row (s, to(q,s)) of TAB into shared-memory slots 1..K_s and EC[q][s] into slot 0.
 #ifndef MCQ_INTERNAL_CUH_
 #define MCQ_INTERNAL_CUH_
 
@@ -31,15 +39,21 @@ struct McqModel {            // device-resident parameter block (all device poin
 };
 
 struct McqStatic {           // device-resident static tables
-  int Q, S, L, Ls, N, H, ES;
+  int Q, S, L, Ls, N, H;
   const uint8_t *G;          // [Q][S][Ls]
-  const int *eoff;           // [S+1]
-  const uint8_t *slot_codon; // [ES]  codon of each slot
-  const uint8_t *slot_flags; // [ES]  bit0: codon is in ref_site_codons[s]; bit1: codon is the consensus
-  const int *slot_site;      // [ES]  site each slot belongs to
+  const int *aoff;           // [S+1] first non-consensus slot of site s in ATAB / ncodon; K_s = aoff[s+1]-aoff[s]
+  const int *toff;           // [S+1] offset of site s's block of rows in TAB
+  const uint8_t *ncodon;     // [aoff[S]] codon of each non-consensus slot
+  const int *nsite;          // [aoff[S]] site of each non-consensus slot
   const uint8_t *cons_codon; // [S]
-  const uint8_t *query_codon;// [Q][S]
+  const uint8_t *cons_in_list;  // [S] 1 when some reference shows the consensus codon at the site
+  const uint8_t *query_codon;// [Q][S]; nullptr = every row is row 0 (the drop-in symbols)
   const uint8_t *hla;        // [Q][H] 0/1
+};
+
+struct McqEmis {             // one consistent set of emission rows
+  const double *tab;         // TAB
+  const double *ec;          // EC [Q][S]; nullptr = slot 0 is never referenced
 };
 
 // ---- proposal overrides applied on top of McqModel inside a kernel (no H2D copy per step)
@@ -51,7 +65,7 @@ struct McqOverride {
 
 struct FwdArgs {
   McqStatic st;
-  const double *E;           // emission rows read for sites start..end
+  McqEmis em;                // emission rows read for sites start..end
   const double *R;
   int r_site; double r_value;     // R override at one site (-1 = none)
   const double *Fin; const int *Fn_in;
@@ -68,7 +82,7 @@ struct FwdArgs {
 
 struct BwdArgs {
   McqStatic st;
-  const double *E;
+  McqEmis em;
   const double *R;
   double *B; int *Bn;
   int update;                // start column (S-1 = fresh)
@@ -79,10 +93,10 @@ struct EmisArgs {
   McqStatic st;
   McqModel m;
   McqOverride ov;
-  int start, end, which_hla, mode;
-  int k0, k1;                // slot bounds of the site range: eoff[start], eoff[end+1]
-  const double *Esrc, *Asrc;
-  double *Edst, *Adst;
+  int start, end, which_hla;
+  int a0, a1;                // non-consensus slot bounds of the range: aoff[start], aoff[end+1]
+  const double *tab_src, *atab_src, *ec_src, *ac_src;
+  double *tab_dst, *atab_dst, *ec_dst, *ac_dst;
 };
 
 // launchers (mcq_kernels.cu); all asynchronous on `stream`, return cudaGetLastError()
@@ -92,15 +106,19 @@ cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, co
                               cudaStream_t stream);
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
-cudaError_t mcq_launch_emission(const EmisArgs &a, cudaStream_t stream);
-cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new,
-                                  const double *E, const double *A, double *Eo, double *Ao, int nslots,
-                                  cudaStream_t stream);
+// the reversion part (rows of non-consensus codons) / the escape part (the consensus row) of
+// create_codon_to_codon_HLA
+cudaError_t mcq_launch_emission_table(const EmisArgs &a, cudaStream_t stream);
+cudaError_t mcq_launch_emission_cons(const EmisArgs &a, cudaStream_t stream);
+cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots, int tab_len,
+                                  const double *tab, const double *atab, const double *ec, const double *ac,
+                                  double *tab_o, double *atab_o, double *ec_o, double *ac_o, cudaStream_t stream);
 cudaError_t mcq_launch_commit_cols(const McqStatic &st, const double *T, const int *Tn, double *F, int *Fn,
                                    int start, int end, const uint8_t *active, int active_hla,
                                    cudaStream_t stream);
-cudaError_t mcq_launch_commit_rows(const McqStatic &st, const double *Et, const double *At, double *E, double *A,
-                                   int start, int end, cudaStream_t stream);
+cudaError_t mcq_launch_copy(const double *src, double *dst, size_t n, cudaStream_t stream);
+cudaError_t mcq_launch_commit_cons(const McqStatic &st, const double *ec_t, const double *ac_t, double *ec,
+                                   double *ac, int start, int end, cudaStream_t stream);
 cudaError_t mcq_launch_commit_params(const McqStatic &st, McqModel m, McqOverride ov, cudaStream_t stream);
 cudaError_t mcq_launch_sum(const double *v, int n, double *out, cudaStream_t stream);
 

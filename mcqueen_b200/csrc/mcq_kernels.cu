@@ -1,8 +1,9 @@
 // mcq_kernels.cu - the CUDA kernels of the McQueen likelihood path (sm_100a).
 //
 //   K0  k_gather        triplet_to_codon (amino_acids.c:50-66) evaluated once into G[q][s][r]
-//   K3  k_emission      create_codon_to_codon_HLA (mcmc_moves.c:33-170), compact rows
-//   K3b k_mu_rescale    the mu-rescale of mutation_move (mcmc_moves.c:1082-1111)
+//   K3a k_emission_table  create_codon_to_codon_HLA, reversion part (mcmc_moves.c:78-124), shared rows
+//   K3c k_emission_cons   create_codon_to_codon_HLA, escape part (mcmc_moves.c:125-167), per query
+//   K3b k_mu_rescale_*    the mu-rescale of mutation_move (mcmc_moves.c:1082-1111)
 //   K4  k_forward<NJ>   initialise_F / update_F (forward_backward.c:11-171) + K6 llk epilogue
 //   K5  k_backward<NJ>  update_B (forward_backward.c:173-244)
 //   K7  k_commit_*      accept-commit copies (mcmc_moves.c:263-265,447-449,959-965)
@@ -157,118 +158,148 @@ __device__ __forceinline__ double eff_rate_out(const McqModel &m, const McqOverr
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: emission rows.  One thread per (query, slot) of the site range: consecutive threads write
-// consecutive entries of the query's compact row (coalesced 8-byte stores to E and A).
+// K3a: the reversion part of create_codon_to_codon_HLA (mcmc_moves.c:78-124): rows of the
+// non-consensus codons.  Nothing in it depends on the query except its codon `to`, so it is
+// evaluated once per (slot, to): one thread each, 64 x (non-consensus slots of the range).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_emission(const EmisArgs a) {
-  const int k0 = a.st.eoff[a.start], W = a.st.eoff[a.end + 1] - k0;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)a.st.Q * W) return;
-  const int q = (int)(idx / W), k = k0 + (int)(idx % W);
-  const int s = a.st.slot_site[k];
-  const int S = a.st.S, H = a.st.H;
+__global__ void __launch_bounds__(256) k_emission_table(const EmisArgs a) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)(a.a1 - a.a0) * 64u) return;
+  const int j = a.a0 + (int)(idx >> 6), to = (int)(idx & 63);
+  const int s = a.st.nsite[j], c1 = a.st.ncodon[j];
   const McqModel &m = a.m;
-  const uint8_t *__restrict__ hla = a.st.hla + (size_t)q * H;
-  const size_t o = (size_t)q * a.st.ES + k;
-  const bool copy_through = (a.Edst != a.Esrc);
-
-  const int c1 = a.st.slot_codon[k];
-  const uint8_t fl = a.st.slot_flags[k];
-  const bool in_list = fl & 1, is_cons = fl & 2;
-  // an ESC update of one HLA leaves non-carriers untouched (mcmc_moves.c:61-62)
-  const bool skip = (a.mode == 0 && a.which_hla >= 0 && hla[a.which_hla] == 0);
-  const bool do_rev = !skip && !is_cons && in_list && a.mode != 0;
-  const bool do_esc = !skip && is_cons && a.mode != 1;
-  if (!do_rev && !do_esc) {
-    if (copy_through) { a.Edst[o] = a.Esrc[o]; a.Adst[o] = a.Asrc[o]; }
-    return;
-  }
-  const int cons = a.st.cons_codon[s], to = a.st.query_codon[(size_t)q * S + s];
+  const int cons = a.st.cons_codon[s];
   const double omega = eff_omega(m, a.ov, s);
   const double kappa = m.kappa, phi = m.phi, mu = m.mu;
   const double N = (double)a.st.N;
   const double back = (1 - phi) * m.prior[to];
-  double A, v;
-  if (do_rev) {
-    // reversion part: a non-consensus codon of the panel (mcmc_moves.c:78-124)
-    const double rev = eff_rev(m, a.ov, s);
-    const double rate = eff_rate_out(m, a.ov, s, c1, in_list) + (rev - 1) * step_rate(omega, kappa, c1, cons);
-    A = 1 - N / (N + rate * 4 * mu);
-    const double gamma = phi / rate;
-    const double mm = step_rate(omega, kappa, c1, to);
-    if (to == cons) v = A * (gamma * rev * mm + back);
-    else {
-      v = A * (gamma * mm + back);
-      if (c1 == to) v += (1 - A);
-    }
-  } else {
-    // escape part: the consensus row (mcmc_moves.c:125-167)
-    double esc_prod = 1.0;
-    for (int h = 0; h < H; h++)
-      if (hla[h]) esc_prod *= eff_esc(m, a.ov, h, s, S);
-    const double nsum = kappa * d_cnt[0][cons] + d_cnt[1][cons];
-    const double rate = eff_rate_out(m, a.ov, s, cons, in_list) + (esc_prod - 1) * omega * nsum;
-    A = 1 - N / (N + rate * 4 * mu);
-    if (cons == 15 || cons == 35) {
-      const double gamma = phi / nsum;
-      v = A * (gamma * ns_rate(kappa, cons, to) + back);
-    } else {
-      const double gamma = phi / rate;
-      v = A * (gamma * (esc_prod * omega * ns_rate(kappa, cons, to) + s_rate(kappa, cons, to)) + back);
-    }
-    if (to == cons) v = (1 - A) * (1 - back) + back;
+  const double rev = eff_rev(m, a.ov, s);
+  const double rate = eff_rate_out(m, a.ov, s, c1, true) + (rev - 1) * step_rate(omega, kappa, c1, cons);
+  const double A = 1 - N / (N + rate * 4 * mu);
+  const double gamma = phi / rate;
+  const double mm = step_rate(omega, kappa, c1, to);
+  double v;
+  if (to == cons) v = A * (gamma * rev * mm + back);
+  else {
+    v = A * (gamma * mm + back);
+    if (c1 == to) v += (1 - A);
   }
-  a.Edst[o] = v;
-  a.Adst[o] = A;
+  const int as = a.st.aoff[s], kr = a.st.aoff[s + 1] - as;
+  a.tab_dst[(size_t)a.st.toff[s] + (size_t)to * kr + (j - as)] = v;
+  if (to == 0) a.atab_dst[j] = A;
 }
 
-cudaError_t mcq_launch_emission(const EmisArgs &a, cudaStream_t stream) {
-  // the slot bounds of the range are needed for the grid size: they come with the args
-  const size_t n = (size_t)a.st.Q * (a.k1 - a.k0);
+cudaError_t mcq_launch_emission_table(const EmisArgs &a, cudaStream_t stream) {
+  const unsigned n = (unsigned)(a.a1 - a.a0) * 64u;
   if (n == 0) return cudaSuccess;
-  k_emission<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
+  k_emission_table<<<(n + 255) / 256, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
-// K3b: mu rescale (mcmc_moves.c:1082-1111), one thread per (query, slot).  The reference walks
-// ref_site_codons only; the consensus slot of a site whose consensus codon no reference shows is
-// rescaled as well (the reference leaves that tmp entry unwritten - uninitialised memory,
-// SURVEY.md §8c hazard 1).
+// K3c: the escape part (mcmc_moves.c:125-167): the consensus row, one thread per (query, site).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_mu_rescale(const McqStatic st, const McqModel m, double mu_new,
-                                                    const double *__restrict__ E, const double *__restrict__ A,
-                                                    double *__restrict__ Eo, double *__restrict__ Ao, int nslots) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)st.Q * nslots) return;
-  const int q = (int)(idx / nslots), k = (int)(idx % nslots);
-  const int s = st.slot_site[k];
-  const int to = st.query_codon[(size_t)q * st.S + s];
-  const double N = (double)st.N;
-  const size_t o = (size_t)q * st.ES + k;
-  const int c1 = st.slot_codon[k];
-  const double a = A[o];
-  double rate = 0.0;
-  if (a != 0) rate = (N / (1 - a) - N) / (4 * m.mu);
-  const double an = 1 - N / (N + rate * 4 * mu_new);
+__global__ void __launch_bounds__(256) k_emission_cons(const EmisArgs a) {
+  const unsigned W = (unsigned)(a.end - a.start + 1);
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)a.st.Q * W) return;
+  const int q = (int)(idx / W), s = a.start + (int)(idx % W);
+  const int S = a.st.S, H = a.st.H;
+  const McqModel &m = a.m;
+  const uint8_t *__restrict__ hla = a.st.hla + (size_t)q * H;
+  const size_t o = (size_t)q * S + s;
+  // an ESC update of one HLA leaves non-carriers untouched (mcmc_moves.c:61-62)
+  if (a.which_hla >= 0 && hla[a.which_hla] == 0) {
+    if (a.ec_dst != a.ec_src) { a.ec_dst[o] = a.ec_src[o]; a.ac_dst[o] = a.ac_src[o]; }
+    return;
+  }
+  const int cons = a.st.cons_codon[s], to = a.st.query_codon[o];
+  const double omega = eff_omega(m, a.ov, s);
+  const double kappa = m.kappa, phi = m.phi, mu = m.mu;
+  const double N = (double)a.st.N;
+  const double back = (1 - phi) * m.prior[to];
+  double esc_prod = 1.0;
+  for (int h = 0; h < H; h++)
+    if (hla[h]) esc_prod *= eff_esc(m, a.ov, h, s, S);
+  const double nsum = kappa * d_cnt[0][cons] + d_cnt[1][cons];
+  const double rate = eff_rate_out(m, a.ov, s, cons, a.st.cons_in_list[s] != 0) + (esc_prod - 1) * omega * nsum;
+  const double A = 1 - N / (N + rate * 4 * mu);
   double v;
-  if (to != c1) v = (a == 0) ? 0.0 : E[o] * an / a;
-  else v = 1 - an + (1 - m.phi) * m.prior[c1] * an;
-  Ao[o] = an;
-  Eo[o] = v;
+  if (cons == 15 || cons == 35) {
+    const double gamma = phi / nsum;
+    v = A * (gamma * ns_rate(kappa, cons, to) + back);
+  } else {
+    const double gamma = phi / rate;
+    v = A * (gamma * (esc_prod * omega * ns_rate(kappa, cons, to) + s_rate(kappa, cons, to)) + back);
+  }
+  if (to == cons) v = (1 - A) * (1 - back) + back;
+  a.ec_dst[o] = v;
+  a.ac_dst[o] = A;
 }
 
-cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new,
-                                  const double *E, const double *A, double *Eo, double *Ao, int nslots,
-                                  cudaStream_t stream) {
-  const size_t n = (size_t)st.Q * nslots;
-  k_mu_rescale<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, m, mu_new, E, A, Eo, Ao, nslots);
+cudaError_t mcq_launch_emission_cons(const EmisArgs &a, cudaStream_t stream) {
+  const unsigned n = (unsigned)a.st.Q * (unsigned)(a.end - a.start + 1);
+  k_emission_cons<<<(n + 255) / 256, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b: mu rescale (mcmc_moves.c:1082-1111), entry by entry, on the shared table and on the
+// per-query consensus values.  The reference walks ref_site_codons only; the consensus value of a
+// site whose consensus codon no reference shows is rescaled as well (the reference leaves that tmp
+// entry unwritten - uninitialised memory, SURVEY.md §8c hazard 1).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rescale_entry(double a, double e, bool same, double N, double mu, double mu_new,
+                                              double phi, double prior_c1, double &an, double &v) {
+  double rate = 0.0;
+  if (a != 0) rate = (N / (1 - a) - N) / (4 * mu);
+  an = 1 - N / (N + rate * 4 * mu_new);
+  if (!same) v = (a == 0) ? 0.0 : e * an / a;
+  else v = 1 - an + (1 - phi) * prior_c1 * an;
+}
+
+__global__ void __launch_bounds__(256) k_mu_rescale_table(const McqStatic st, const McqModel m, double mu_new,
+                                                          int nslots, const double *__restrict__ tab,
+                                                          const double *__restrict__ atab,
+                                                          double *__restrict__ tab_o, double *__restrict__ atab_o) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)nslots * 64u) return;
+  const int j = (int)(idx >> 6), to = (int)(idx & 63);
+  const int s = st.nsite[j], c1 = st.ncodon[j];
+  const int as = st.aoff[s], kr = st.aoff[s + 1] - as;
+  const size_t o = (size_t)st.toff[s] + (size_t)to * kr + (j - as);
+  double an, v;
+  rescale_entry(atab[j], tab[o], to == c1, (double)st.N, m.mu, mu_new, m.phi, m.prior[c1], an, v);
+  tab_o[o] = v;
+  if (to == 0) atab_o[j] = an;
+}
+
+__global__ void __launch_bounds__(256) k_mu_rescale_cons(const McqStatic st, const McqModel m, double mu_new,
+                                                         const double *__restrict__ ec, const double *__restrict__ ac,
+                                                         double *__restrict__ ec_o, double *__restrict__ ac_o) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)st.Q * (unsigned)st.S) return;
+  const int s = (int)(idx % (unsigned)st.S);
+  const int c1 = st.cons_codon[s], to = st.query_codon[idx];
+  double an, v;
+  rescale_entry(ac[idx], ec[idx], to == c1, (double)st.N, m.mu, mu_new, m.phi, m.prior[c1], an, v);
+  ec_o[idx] = v;
+  ac_o[idx] = an;
+}
+
+cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots, int tab_len,
+                                  const double *tab, const double *atab, const double *ec, const double *ac,
+                                  double *tab_o, double *atab_o, double *ec_o, double *ac_o, cudaStream_t stream) {
+  (void)tab_len;
+  const unsigned n1 = (unsigned)nslots * 64u, n2 = (unsigned)st.Q * (unsigned)st.S;
+  if (n1) k_mu_rescale_table<<<(n1 + 255) / 256, 256, 0, stream>>>(st, m, mu_new, nslots, tab, atab, tab_o, atab_o);
+  k_mu_rescale_cons<<<(n2 + 255) / 256, 256, 0, stream>>>(st, m, mu_new, ec, ac, ec_o, ac_o);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
 // asynchronous global->shared copies (LDGSTS): a warp stages the codon-slot row G[q][s][.] and the
-// emission row E[q][eoff[s]..] of the sites ahead of the one it is computing
+// emission row of the sites ahead of the one it is computing
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -284,39 +315,44 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 #define MCQ_PF 3                 // sites staged ahead of the one being computed
 #define MCQ_RING (MCQ_PF + 1)    // ring slots per warp
+#define MCQ_ES 66                // doubles per staged emission row: slot 0 + up to 64 others, padded
 
-// stage rows of site s into ring slot `slot` (one commit group per site, empty past the range)
+// Stage the rows of site t into ring slot t % MCQ_RING: one commit group per call, empty when the
+// site lies outside the range.  `to` is the query's codon at t (selects the table row).
 template <int NJ>
-__device__ __forceinline__ void stage_site(uint8_t *gring, double *ering, int slot, int s, bool valid,
-                                           const uint8_t *__restrict__ Gq, const double *__restrict__ Eq,
-                                           const int *__restrict__ eoff, int Ls, int lane) {
+__device__ __forceinline__ void stage_site(uint8_t *gring, double *ering, int t, bool valid, int to, int q,
+                                           const McqStatic &st, const McqEmis &em,
+                                           const uint8_t *__restrict__ Gq, int lane) {
   if (valid) {
-    const uint8_t *src = Gq + (size_t)s * Ls;
+    const int slot = t % MCQ_RING, Ls = st.Ls;
+    const uint8_t *src = Gq + (size_t)t * Ls;
     uint8_t *dst = gring + slot * (64 * NJ);
 #pragma unroll
     for (int i = 0; i < (NJ + 7) / 8; i++) {
       const int o = (lane + 32 * i) * 16;
       if (o < Ls) cp_async16(dst + o, src + o);
     }
-    const int k0 = eoff[s], K = eoff[s + 1] - k0;
-    double *ed = ering + slot * 64;
-    for (int k = lane; k < K; k += 32) cp_async8(ed + k, Eq + k0 + k);
+    const int kr = st.aoff[t + 1] - st.aoff[t];
+    const double *row = em.tab + (size_t)st.toff[t] + (size_t)to * kr;
+    double *ed = ering + slot * MCQ_ES;
+    for (int k = lane; k < kr; k += 32) cp_async8(ed + 1 + k, row + k);
+    if (lane == 0 && em.ec != nullptr) cp_async8(ed, em.ec + (size_t)q * st.S + t);
   }
   cp_async_commit();
 }
 
 // ------------------------------------------------------------------------------------------
 // K4: forward recursion.  One warp per query; lane l holds states 64j+2l, 64j+2l+1 (j < NJ) of
-// the running column in registers.  Per site: the site's G row (Ls bytes) and emission row
-// (K_s doubles) arrive in shared memory through cp.async, staged MCQ_PF sites ahead so that no
-// global-load latency sits on the recurrence; one butterfly all-reduce (the column sum, which
-// both decides the rescale and is the next site's recombination sum); one 16-byte streaming
-// store of F per lane per j (512 contiguous bytes per warp instruction).
+// the running column in registers.  Per site: the site's G row (Ls bytes) and emission row arrive
+// in shared memory through cp.async, staged MCQ_PF sites ahead so that no global-load latency sits
+// on the recurrence; one butterfly all-reduce (the column sum, which both decides the rescale and
+// is the next site's recombination sum); one 16-byte streaming store of F per lane per j
+// (512 contiguous bytes per warp instruction).
 // ------------------------------------------------------------------------------------------
 template <int NJ>
 __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[4][MCQ_RING][64 * NJ];
-  __shared__ __align__(16) double s_e[4][MCQ_RING][64];
+  __shared__ __align__(16) double s_e[4][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (q >= a.st.Q) return;
@@ -327,8 +363,7 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
   const int S = a.st.S, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
   const uint8_t *__restrict__ Gq = a.st.G + qoff;
-  const double *__restrict__ Eq = a.E + (size_t)q * a.st.ES;
-  const int *__restrict__ eoff = a.st.eoff;
+  const uint8_t *__restrict__ qc = a.st.query_codon ? a.st.query_codon + (size_t)q * S : nullptr;
   double *__restrict__ Fo = a.Fout + qoff;
   int *__restrict__ Fno = a.Fn_out + (size_t)q * S;
   const double Nd = (double)a.st.N;
@@ -340,11 +375,13 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
 #pragma unroll
   for (int j = 0; j < NJ; j++) { r0[j] = 64 * j + 2 * lane; inrow[j] = r0[j] < Ls; }
 
-  // first site whose rows are needed: the seed column when start == 0
-  const int first = a.start;
+  // prologue: rows of the first MCQ_PF sites of the range; the query's codon is fetched one site
+  // further ahead than the rows it selects
+  int t = a.start;
 #pragma unroll
-  for (int i = 0; i < MCQ_PF; i++)
-    stage_site<NJ>(gring, ering, (first + i) % MCQ_RING, first + i, first + i <= a.end, Gq, Eq, eoff, Ls, lane);
+  for (int i = 0; i < MCQ_PF; i++, t++)
+    stage_site<NJ>(gring, ering, t, t <= a.end, (qc && t <= a.end) ? qc[t] : 0, q, a.st, a.em, Gq, lane);
+  int to_next = (qc && t <= a.end) ? qc[t] : 0;   // codon at site t = start + MCQ_PF
 
   double p0[NJ], p1[NJ];   // the running column
   int s = a.start, cnt;
@@ -354,9 +391,14 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
     // column 0 is the bare emission and is never rescaled (forward_backward.c:27-39,102-111)
     cp_async_wait<MCQ_PF - 1>();
     __syncwarp();
-    stage_site<NJ>(gring, ering, (s + MCQ_PF) % MCQ_RING, s + MCQ_PF, s + MCQ_PF <= a.end, Gq, Eq, eoff, Ls, lane);
-    const uint8_t *gs = gring + (s % MCQ_RING) * (64 * NJ);
-    const double *es = ering + (s % MCQ_RING) * 64;
+    {
+      const int to = to_next;
+      to_next = (qc && t + 1 <= a.end) ? qc[t + 1] : 0;
+      stage_site<NJ>(gring, ering, t, t <= a.end, to, q, a.st, a.em, Gq, lane);
+      t++;
+    }
+    const uint8_t *gs = gring;              // ring slot 0
+    const double *es = ering;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
@@ -396,10 +438,15 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
 
   for (; s <= a.end; ++s) {
     cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed (this lane's copies)
-    __syncwarp();                  // ... and every other lane's; slot of site s-1 is free again
-    stage_site<NJ>(gring, ering, (s + MCQ_PF) % MCQ_RING, s + MCQ_PF, s + MCQ_PF <= a.end, Gq, Eq, eoff, Ls, lane);
+    __syncwarp();                  // ... and every other lane's; the slot of site s-1 is free again
+    {
+      const int to = to_next;
+      to_next = (qc && t + 1 <= a.end) ? qc[t + 1] : 0;
+      stage_site<NJ>(gring, ering, t, t <= a.end, to, q, a.st, a.em, Gq, lane);
+      t++;
+    }
     const uint8_t *gs = gring + (s % MCQ_RING) * (64 * NJ);
-    const double *es = ering + (s % MCQ_RING) * 64;
+    const double *es = ering + (s % MCQ_RING) * MCQ_ES;
     const double Rs = (s == a.r_site) ? a.r_value : a.R[s];
     const double jump = tot * Rs / Nd;          // forward_backward.c:138
     const double stay = 1 - Rs;
@@ -466,24 +513,27 @@ cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K5: backward recursion, same mapping, descending sites.  b = B[.][s+1] (as stored), e = the
-// emission at s+1, sx = sum_r b*e.  The column sum of the new column and the next sx are
+// K5: backward recursion, same mapping and staging, descending sites.  b = B[.][s+1] (as stored),
+// e = the emission at s+1, sx = sum_r b*e.  The column sum of the new column and the next sx are
 // reduced together in one butterfly.
 // ------------------------------------------------------------------------------------------
 template <int NJ>
 __global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
+  __shared__ __align__(16) uint8_t s_g[4][MCQ_RING][64 * NJ];
+  __shared__ __align__(16) double s_e[4][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (q >= a.st.Q) return;
   if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) return;
   const int S = a.st.S, L = a.st.L, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
   const uint8_t *__restrict__ Gq = a.st.G + qoff;
-  const double *__restrict__ Eq = a.E + (size_t)q * a.st.ES;
-  const int *__restrict__ eoff = a.st.eoff;
+  const uint8_t *__restrict__ qc = a.st.query_codon ? a.st.query_codon + (size_t)q * S : nullptr;
   double *__restrict__ Bq = a.B + qoff;
   int *__restrict__ Bnq = a.Bn + (size_t)q * S;
   const double Nd = (double)a.st.N;
+  uint8_t *gring = &s_g[wib][0][0];
+  double *ering = &s_e[wib][0][0];
 
   int r0[NJ];
   bool inrow[NJ];
@@ -514,48 +564,62 @@ __global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
     cnt = Bnq[s + 1];
   }
   if (s < 0) return;
+
+  // rows are consumed in the order s+1, s, s-1, ..., 0
+  int t = s + 1;
+#pragma unroll
+  for (int i = 0; i < MCQ_PF; i++, t--)
+    stage_site<NJ>(gring, ering, t, t >= 0, (qc && t >= 0) ? qc[t] : 0, q, a.st, a.em, Gq, lane);
+  int to_next = (qc && t >= 0) ? qc[t] : 0;
+
   // emission at s+1 and sx
   double sx;
   {
-    const int eo = eoff[s + 1];
+    cp_async_wait<MCQ_PF - 1>();
+    __syncwarp();
+    {
+      const int to = to_next;
+      to_next = (qc && t - 1 >= 0) ? qc[t - 1] : 0;
+      stage_site<NJ>(gring, ering, t, t >= 0, to, q, a.st, a.em, Gq, lane);
+      t--;
+    }
+    const uint8_t *gs = gring + ((s + 1) % MCQ_RING) * (64 * NJ);
+    const double *es = ering + ((s + 1) % MCQ_RING) * MCQ_ES;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       unsigned gg = 0xFFFFu;
-      if (inrow[j]) gg = *reinterpret_cast<const uint16_t *>(Gq + (size_t)(s + 1) * Ls + r0[j]);
+      if (inrow[j]) gg = *reinterpret_cast<const uint16_t *>(gs + r0[j]);
       const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
-      e0[j] = (g0 != MCQ_NOSLOT) ? Eq[eo + g0] : 0.0;
-      e1[j] = (g1 != MCQ_NOSLOT) ? Eq[eo + g1] : 0.0;
+      e0[j] = (g0 != MCQ_NOSLOT) ? es[g0] : 0.0;
+      e1[j] = (g1 != MCQ_NOSLOT) ? es[g1] : 0.0;
       loc += b0[j] * e0[j]; loc += b1[j] * e1[j];
     }
     sx = warp_sum(loc);
   }
-  unsigned gcur[NJ];   // G at site s (needed for the NEXT iteration's emission)
-#pragma unroll
-  for (int j = 0; j < NJ; j++)
-    gcur[j] = inrow[j] ? *reinterpret_cast<const uint16_t *>(Gq + (size_t)s * Ls + r0[j]) : 0xFFFFu;
 
   for (; s >= 0; --s) {
+    cp_async_wait<MCQ_PF - 1>();   // rows of site s
+    __syncwarp();
+    {
+      const int to = to_next;
+      to_next = (qc && t - 1 >= 0) ? qc[t - 1] : 0;
+      stage_site<NJ>(gring, ering, t, t >= 0, to, q, a.st, a.em, Gq, lane);
+      t--;
+    }
+    const uint8_t *gs = gring + (s % MCQ_RING) * (64 * NJ);
+    const double *es = ering + (s % MCQ_RING) * MCQ_ES;
     const double Rn = a.R[s + 1];
     const double jump = sx * Rn / Nd;           // forward_backward.c:219
     const double stay = 1 - Rn;
-    // emission at s (for the next step's products)
-    double n0[NJ], n1[NJ];
-    const int eo = eoff[s];
-#pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      const unsigned g0 = gcur[j] & 0xFF, g1 = gcur[j] >> 8;
-      n0[j] = (g0 != MCQ_NOSLOT) ? Eq[eo + g0] : 0.0;
-      n1[j] = (g1 != MCQ_NOSLOT) ? Eq[eo + g1] : 0.0;
-    }
-    if (s > 0) {
-#pragma unroll
-      for (int j = 0; j < NJ; j++)
-        if (inrow[j]) gcur[j] = __ldcs(reinterpret_cast<const uint16_t *>(Gq + (size_t)(s - 1) * Ls + r0[j]));
-    }
     double locv = 0.0, locy = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
+      unsigned gg = 0xFFFFu;
+      if (inrow[j]) gg = *reinterpret_cast<const uint16_t *>(gs + r0[j]);
+      const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
+      const double n0 = (g0 != MCQ_NOSLOT) ? es[g0] : 0.0;   // emission at s, for the next step's products
+      const double n1 = (g1 != MCQ_NOSLOT) ? es[g1] : 0.0;
       // pad states (r >= L) must stay 0: they would otherwise pick up `jump`
       double v0 = jump; v0 += stay * b0[j] * e0[j];
       double v1 = jump; v1 += stay * b1[j] * e1[j];
@@ -563,8 +627,8 @@ __global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
       if (r0[j] + 1 >= L) v1 = 0.0;
       b0[j] = v0; b1[j] = v1;
       locv += v0; locv += v1;
-      locy += v0 * n0[j]; locy += v1 * n1[j];
-      e0[j] = n0[j]; e1[j] = n1[j];
+      locy += v0 * n0; locy += v1 * n1;
+      e0[j] = n0; e1[j] = n1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -584,6 +648,7 @@ __global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
       if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bs + r0[j]), make_double2(b0[j], b1[j]));
     if (lane == 0) Bnq[s] = cnt;
   }
+  cp_async_wait<0>();
 }
 
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream) {
@@ -638,27 +703,37 @@ cudaError_t mcq_launch_commit_cols(const McqStatic &st, const double *T, const i
   return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) k_commit_rows(const McqStatic st, const double *__restrict__ Et,
-                                                     const double *__restrict__ At, double *__restrict__ E,
-                                                     double *__restrict__ A, int k0, int k1) {
-  const int W = k1 - k0;
-  const size_t n = (size_t)st.Q * W;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t o = (i / W) * st.ES + k0 + (i % W);
-    E[o] = Et[o];
-    A[o] = At[o];
+__global__ void __launch_bounds__(256) k_copy(const double *__restrict__ src, double *__restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+cudaError_t mcq_launch_copy(const double *src, double *dst, size_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_copy<<<blocks, 256, 0, stream>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+// per-query consensus values of sites start..end: tmp -> current
+__global__ void __launch_bounds__(256) k_commit_cons(const McqStatic st, const double *__restrict__ ec_t,
+                                                     const double *__restrict__ ac_t, double *__restrict__ ec,
+                                                     double *__restrict__ ac, int start, int W) {
+  const unsigned n = (unsigned)st.Q * (unsigned)W;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)(i / W) * st.S + start + (i % W);
+    ec[o] = ec_t[o];
+    ac[o] = ac_t[o];
   }
 }
 
-cudaError_t mcq_launch_commit_rows(const McqStatic &st, const double *Et, const double *At, double *E, double *A,
-                                   int start, int end, cudaStream_t stream) {
-  // eoff lives on the device; the host keeps a copy, so the caller passes slot bounds via start/end
-  // already translated (see mcq_ctx.cu) - here start/end ARE slot bounds [k0,k1)
-  const size_t n = (size_t)st.Q * (end - start);
-  if (n == 0) return cudaSuccess;
-  unsigned blocks = (unsigned)((n + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  k_commit_rows<<<blocks, 256, 0, stream>>>(st, Et, At, E, A, start, end);
+cudaError_t mcq_launch_commit_cons(const McqStatic &st, const double *ec_t, const double *ac_t, double *ec,
+                                   double *ac, int start, int end, cudaStream_t stream) {
+  const unsigned n = (unsigned)st.Q * (unsigned)(end - start + 1);
+  unsigned blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_commit_cons<<<blocks, 256, 0, stream>>>(st, ec_t, ac_t, ec, ac, start, end - start + 1);
   return cudaGetLastError();
 }
 
@@ -672,11 +747,15 @@ __global__ void k_commit_params(const McqStatic st, McqModel m, McqOverride ov) 
     case MCQ_PROP_SEL: {
       const int s = ov.start;
       if (t == 0) m.omega[s] = ov.v0;
-      for (int k = st.eoff[s] + t; k < st.eoff[s + 1]; k += blockDim.x)
-        if (st.slot_flags[k] & 1) {
-          const int c = st.slot_codon[k];
-          m.rate_out[(size_t)s * 64 + c] = m.kappa * d_cnt[2][c] + d_cnt[3][c] + ov.v0 * (m.kappa * d_cnt[0][c] + d_cnt[1][c]);
-        }
+      // rate_out_of_codons is refreshed for the codons the panel shows at the site (mcmc_moves.c:345-352)
+      for (int k = st.aoff[s] + t - 1; k < st.aoff[s + 1]; k += blockDim.x) {
+        int c;
+        if (k < st.aoff[s]) {               // t == 0 also handles the consensus codon when listed
+          if (!st.cons_in_list[s]) continue;
+          c = st.cons_codon[s];
+        } else c = st.ncodon[k];
+        m.rate_out[(size_t)s * 64 + c] = m.kappa * d_cnt[2][c] + d_cnt[3][c] + ov.v0 * (m.kappa * d_cnt[0][c] + d_cnt[1][c]);
+      }
       break;
     }
     case MCQ_PROP_ESC:
