@@ -93,7 +93,7 @@ def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -105,7 +105,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -119,24 +119,38 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
+    def mark(self):
+        """Wall-clock mark (start / end of the timed region) in nvidia-smi's timestamp format."""
+        import datetime
+        return datetime.datetime.now()
+
+    def summary(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons over the samples taken between t0 and t1 (all
+        samples when the window caught none)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.path is None or not os.path.exists(self.path):
             return out
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(f[1]), float(f[2]), f[4:8]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+        os.unlink(self.path)
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        out["window"] = "timed region" if inside else "whole run (timed region shorter than the sampling period)"
+        sm, mx, reasons = [], [], set()
+        for ts, a, b, flags in (inside or rows):
+            sm.append(a); mx.append(b)
+            for n, v in zip(names, flags):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        os.unlink(self.path)
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
         out["reasons"] = sorted(reasons)
@@ -195,7 +209,7 @@ def run_ref_bench(p, threads, seconds, path=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=list(synth.CONFIGS))
@@ -252,12 +266,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the McQueen path has no CPU fallback")
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("gloo", rank=rank, world_size=world)
     dev = local_rank
     q0, q1 = Qtot * rank // world, Qtot * (rank + 1) // world
     p = build_shard(args.workload, q0, q1, dev)
     ctx = api.Context.from_problem(p, device=dev)
-    if world > 1:
+    if world > 1 and not os.environ.get("MCQ_BENCH_NO_COMM"):
         ids = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.attach_comm(world, rank, ids[0])
@@ -268,6 +285,8 @@ def main():
         if world > 1:
             dist.barrier()
 
+    clk = ClockSampler(dev)
+    clk.__enter__()
     llk0 = ctx.init_state()
     for _ in range(args.warmup):
         ctx.full_llk(True)
@@ -276,7 +295,8 @@ def main():
     ctx.enable_timing(2)
     ctx.kernel_time(api.K_FORWARD, reset=True)
     barrier()
-    with ClockSampler(dev) as clk:
+    if True:
+        mark0 = clk.mark()
         t_wall = time.perf_counter()
         ctx.timer_start()
         launches = 0
@@ -286,10 +306,12 @@ def main():
         ms_dev = ctx.timer_stop()
         barrier()
         t_wall = (time.perf_counter() - t_wall) * 1e3
+        mark1 = clk.mark()
+    clk.__exit__()
     fwd_ms, fwd_n = ctx.kernel_time(api.K_FORWARD)
     emi_ms, emi_n = ctx.kernel_time(api.K_EMISSION)
     ctx.enable_timing(0)
-    clocks = clk.summary()
+    clocks = clk.summary(mark0, mark1)
     assert abs(llk - llk0) <= 1e-12 * abs(llk0), (llk, llk0)
 
     # ---- e2e: everything from (pinned) host buffers every step, per-query results back
@@ -301,18 +323,27 @@ def main():
         p.site_codons.nbytes + 8 * (64 + 2 * S + 64 * S + H * S + S)
     d2h = 8 * p.Q + 8
 
+    e2e_parts = np.zeros(4)
+
     def e2e_step():
+        t0 = time.perf_counter()
         ctx.upload_static(p.ref_triplets, p.closest_refs, p.cons_query_nucls, p.query_codons, p.hla,
                           p.consensus_codons, p.n_site_codons, p.site_codons)
+        t1 = time.perf_counter()
         ctx.set_params(mu=p.mu, kappa=p.kappa, phi=p.phi, prior=p.prior, R=p.R, omega=p.omega,
                        rate_out=rate_out, esc=p.esc, rev=p.rev[0])
+        t2 = time.perf_counter()
         tot = ctx.full_llk(True)
+        t3 = time.perf_counter()
         per_q = ctx.query_llk()
+        t4 = time.perf_counter()
+        e2e_parts[:] += (t1 - t0, t2 - t1, t3 - t2, t4 - t3)
         return tot, per_q
 
     for _ in range(2):
         e2e_step()
     barrier()
+    e2e_parts[:] = 0
     ctx.timer_start()
     t_e2e = time.perf_counter()
     for _ in range(args.steps):
@@ -354,7 +385,11 @@ def main():
 
     # ---- gather over ranks (max time)
     stats = np.array([ms_dev, t_wall, ms_e2e_dev, t_e2e, fwd_ms / max(fwd_n, 1)], np.float64)
+    per_rank = [stats.tolist()]
     if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, stats.tolist())
+        per_rank = gathered
         tt = torch.from_numpy(stats)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         stats = tt.numpy()
@@ -387,6 +422,8 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": total_cells / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                    "breakdown_ms": dict(zip(["upload_static", "set_params", "full_llk", "read_back"],
+                                             (e2e_parts / args.steps * 1e3).round(3).tolist())),
                     "what": "mcq_ctx_upload_static + mcq_ctx_set_params + mcq_ctx_full_llk + per-query llk "
                             "read-back, all inputs from pinned host buffers every step"},
             "roofline": {"bound": "hbm", "kernel": "k_forward", "achieved": achieved, "peak": peak,
@@ -394,6 +431,8 @@ def main():
                          "algorithmic_bytes_per_cell": bytes_per_cell, "launch_ms": fwd_ms_avg,
                          "cells_per_launch": p.Q * S * L},
             "ms_per_step_wall": ms_step_wall, "llk": llk0, "extras": extras,
+            "per_rank": [dict(zip(["timed_ms", "timed_wall_ms", "e2e_ms", "e2e_wall_ms", "forward_launch_ms"], r))
+                         for r in per_rank],
             "kernel_share": {"forward_ms_per_step": fwd_ms / max(args.steps, 1),
                              "emission_ms_per_step": emi_ms / max(args.steps, 1)},
         }

@@ -84,7 +84,7 @@ static const int kNcclSum = 0;     // ncclSum
 // ------------------------------------------------------------------------------------------
 struct mcq_ctx {
   mcq_dims d;
-  int Ls = 0, NA = 0;          // NA = number of non-consensus slots (sum_s K_s)
+  int Ls = 0, Lg = 0, NA = 0;          // NA = number of non-consensus slots (sum_s K_s)
   size_t TL = 0;               // length of the shared emission table (64 * NA)
   cudaStream_t stream = nullptr;
   size_t bytes = 0;
@@ -145,7 +145,7 @@ static int dev_alloc(mcq_ctx *c, T **p, size_t n) {
 
 static McqStatic make_static(const mcq_ctx *c) {
   McqStatic st;
-  st.Q = c->d.num_query; st.S = c->d.num_sites; st.L = c->d.closest_n; st.Ls = c->Ls;
+  st.Q = c->d.num_query; st.S = c->d.num_sites; st.L = c->d.closest_n; st.Ls = c->Ls; st.Lg = c->Lg;
   st.N = c->d.total_num_refs; st.H = c->d.num_hla_types;
   st.G = c->G; st.aoff = c->aoff; st.toff = c->toff; st.ncodon = c->ncodon; st.nsite = c->nsite;
   st.cons_in_list = c->cons_in_list;
@@ -215,6 +215,8 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   mcq_ctx *c = new mcq_ctx();
   c->d = *dims;
   c->Ls = (dims->closest_n + 15) / 16 * 16;
+  c->Lg = 64;
+  while (c->Lg < c->Ls) c->Lg *= 2;   // 64 * NJ, NJ in {1,2,4,8,16}
   c->logBIG = log(MCQ_BIG);   // the host libm value the reference itself uses (mcmc_moves.c:223)
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
@@ -353,8 +355,14 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     aoff_h[s + 1] = aoff_h[s] + k;
     toff_h[s + 1] = toff_h[s] + 64 * k;
   }
-  for (size_t i = 0; i < (size_t)Q * L; i++)
-    REQUIRE(closest_refs[i] >= 0 && closest_refs[i] < N, "closest_refs entry out of range");
+  {
+    int lo = 0, hi = 0;   // branch-free range check (vectorises)
+    for (size_t i = 0; i < (size_t)Q * L; i++) {
+      lo = closest_refs[i] < lo ? closest_refs[i] : lo;
+      hi = closest_refs[i] > hi ? closest_refs[i] : hi;
+    }
+    REQUIRE(lo >= 0 && hi < N, "closest_refs entry out of range");
+  }
 
   if (!c->have_static) {
     c->aoff_h = aoff_h; c->toff_h = toff_h; c->ncodon_h = ncodon_h; c->cons_in_list_h = cons_in_list_h;
@@ -369,7 +377,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     ALLOC(c->cons_codon, (size_t)S);
     ALLOC(c->query_codon, (size_t)Q * S);
     ALLOC(c->hla, (size_t)Q * H);
-    ALLOC(c->G, (size_t)Q * S * c->Ls);
+    ALLOC(c->G, (size_t)Q * S * c->Lg);
     ALLOC(c->st_trip, (size_t)N * S);
     ALLOC(c->st_cons, (size_t)Q * 3 * S);
     ALLOC(c->st_closest, (size_t)Q * L);
@@ -408,7 +416,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
   {
     KScope ks(c, MCQ_K_GATHER);
-    CK(mcq_launch_gather(c->st_trip, c->st_closest, c->st_cons, c->st_slot_of, c->G, Q, S, L, c->Ls, c->stream));
+    CK(mcq_launch_gather(c->st_trip, c->st_closest, c->st_cons, c->st_slot_of, c->G, Q, S, L, c->Lg, c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   c->have_static = true;

@@ -32,7 +32,7 @@ namespace {
   } while (0)
 
 struct Scratch {
-  int S = 0, L = 0, Ls = 0;
+  int S = 0, L = 0, Ls = 0, Lg = 0;
   bool tables = false;
   cudaStream_t stream = nullptr;
   // device
@@ -68,6 +68,8 @@ struct Scratch {
     if (S_ == S && L_ == L) return;
     release();
     S = S_; L = L_; Ls = (L + 15) / 16 * 16;
+    Lg = 64;
+    while (Lg < Ls) Lg *= 2;
     DK(cudaMalloc((void **)&trip, (size_t)L * S));
     DK(cudaMalloc((void **)&cons, (size_t)3 * S));
     DK(cudaMalloc((void **)&closest, (size_t)L * sizeof(int)));
@@ -75,7 +77,7 @@ struct Scratch {
     DK(cudaMalloc((void **)&Fn, (size_t)S * sizeof(int)));
     DK(cudaMalloc((void **)&Tn, (size_t)S * sizeof(int)));
     DK(cudaMalloc((void **)&slot_of, (size_t)S * 64));
-    DK(cudaMalloc((void **)&G, (size_t)S * Ls));
+    DK(cudaMalloc((void **)&G, (size_t)S * Lg));
     DK(cudaMalloc((void **)&E, (size_t)S * 64 * sizeof(double)));
     DK(cudaMalloc((void **)&R, (size_t)S * sizeof(double)));
     DK(cudaMalloc((void **)&F, (size_t)S * Ls * sizeof(double)));
@@ -96,7 +98,7 @@ struct Scratch {
 
   McqStatic statics(int N) const {
     McqStatic st{};
-    st.Q = 1; st.S = S; st.L = L; st.Ls = Ls; st.N = N; st.H = 1;
+    st.Q = 1; st.S = S; st.L = L; st.Ls = Ls; st.Lg = Lg; st.N = N; st.H = 1;
     st.G = G; st.aoff = aoff; st.toff = aoff;   // one row of 64 entries per site
     st.query_codon = nullptr;                   // -> always row 0 of the site's block
     return st;
@@ -116,7 +118,7 @@ struct Scratch {
     DK(cudaMemcpyAsync(cons, cons_nucls, (size_t)3 * S, cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(E, h_E.data(), h_E.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(R, Rh, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, stream));
-    DK(mcq_launch_gather(trip, closest, cons, slot_of, G, 1, S, L, Ls, stream));
+    DK(mcq_launch_gather(trip, closest, cons, slot_of, G, 1, S, L, Lg, stream));
   }
 
   // one column host[L][S] (stride S) -> device column

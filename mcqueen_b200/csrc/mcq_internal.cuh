@@ -1,9 +1,10 @@
 // mcq_internal.cuh - device-side data layout and kernel launch interfaces of libmcq_b200.
 //
 // Layout in HBM (one context = one shard of Q queries on one GPU):
-//   G      u8  [Q][S][Ls]   slot of the codon that copy state r shows at site s
+//   G      u8  [Q][S][Lg]   slot of the codon that copy state r shows at site s
 //                           (0 = the site's consensus codon, 1..K_s = its other reference codons in
-//                           ascending order, 0xFF = a codon no reference shows / padding)
+//                           ascending order, 65 = a codon no reference shows / padding); Lg = 64*NJ,
+//                           bytes permuted so that a lane's 2*NJ states are contiguous
 //   F,B,T  f64 [Q][S][Ls]   forward, backward, proposal ("tmp") forward; SITE-major, state fastest
 //   Fn,Bn,Tn i32 [Q][S]     rescale counters (F_rnorm etc. of the reference)
 //   llk_cur, llk_prop f64 [Q]
@@ -26,7 +27,7 @@
 
 #define MCQ_BIG 1000000.0   // constants.c:13
 #define MCQ_BIGI 100.0      // constants.c:14
-#define MCQ_NOSLOT 0xFF
+#define MCQ_NOSLOT 65       // slot value of "a codon no reference shows" / padding: staged emission 0
 
 struct McqModel {            // device-resident parameter block (all device pointers)
   double *R;                 // [S]
@@ -40,7 +41,8 @@ struct McqModel {            // device-resident parameter block (all device poin
 
 struct McqStatic {           // device-resident static tables
   int Q, S, L, Ls, N, H;
-  const uint8_t *G;          // [Q][S][Ls]
+  int Lg;                    // bytes per G row: 64 * NJ with NJ = 1,2,4,8,16 covering Ls
+  const uint8_t *G;          // [Q][S][Lg], states permuted lane-major (see k_gather)
   const int *aoff;           // [S+1] first non-consensus slot of site s in ATAB / ncodon; K_s = aoff[s+1]-aoff[s]
   const int *toff;           // [S+1] offset of site s's block of rows in TAB
   const uint8_t *ncodon;     // [aoff[S]] codon of each non-consensus slot
@@ -102,7 +104,7 @@ struct EmisArgs {
 // launchers (mcq_kernels.cu); all asynchronous on `stream`, return cudaGetLastError()
 cudaError_t mcq_launch_tables_init();
 cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, const int8_t *cons_nucls,
-                              const uint8_t *slot_of /*[S][64]*/, uint8_t *G, int Q, int S, int L, int Ls,
+                              const uint8_t *slot_of /*[S][64]*/, uint8_t *G, int Q, int S, int L, int Lg,
                               cudaStream_t stream);
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);

@@ -64,71 +64,65 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K0: gathered codon-slot table.  Tile = 128 sites x 64 states through shared memory: a warp
-// reads 128 consecutive sites of one reference row (4 per lane), and writes 64 consecutive
-// states of two site rows (4 per lane), so both sides move whole 32-byte sectors.
+// K0: gathered codon-slot table.  One block per (query, 32 sites): reads run along a reference's
+// row (32 consecutive sites = one sector), the tile is transposed and PERMUTED in shared memory,
+// and every site row of G leaves as one contiguous run of 16-byte stores.
+//
+// Physical order inside a G row (Lg = 64*NJ bytes): the 2*NJ states a lane owns in k_forward /
+// k_backward - 64j+2l, 64j+2l+1 for j < NJ - are contiguous at byte offset l*2*NJ, so a lane
+// fetches all of them with one vector load from the staged row.
 // ------------------------------------------------------------------------------------------
-#define GT_S 128
-#define GT_R 64
+__device__ __forceinline__ int g_pos(int r, int nj) { return ((r & 63) >> 1) * (2 * nj) + 2 * (r >> 6) + (r & 1); }
+
 __global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_triplets,
                                                 const int *__restrict__ closest,
                                                 const int8_t *__restrict__ cons_nucls,
                                                 const uint8_t *__restrict__ slot_of,
-                                                uint8_t *__restrict__ G, int S, int L, int Ls) {
-  __shared__ uint8_t tile[GT_S][GT_R + 1];   // odd row stride: conflict-free transposed stores
-  const int q = blockIdx.z;
-  const int s0 = blockIdx.x * GT_S, r0 = blockIdx.y * GT_R;
+                                                uint8_t *__restrict__ G, int S, int L, int Lg) {
+  extern __shared__ __align__(16) uint8_t tile[];   // [32][Lg + 16]: row stride = 16 mod 128 -> 4-way at worst
+  const int q = blockIdx.y;
+  const int s0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // read phase: lane owns sites s0+4*lane .. +3
-  int cn[4][3];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int s = s0 + 4 * lane + i;
-#pragma unroll
-    for (int p = 0; p < 3; p++) cn[i][p] = (s < S) ? cons_nucls[(size_t)q * 3 * S + 3 * s + p] : 0;
+  const int nj = Lg >> 6, stride = Lg + 16;
+  const int s = s0 + lane;
+  int c0 = 0, c1 = 0, c2 = 0;
+  if (s < S) {
+    const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
+    c0 = cn[0]; c1 = cn[1]; c2 = cn[2];
   }
-#pragma unroll
-  for (int pass = 0; pass < GT_R / 8; pass++) {
-    const int rr = warp + 8 * pass, r = r0 + rr;
-    const int ref = (r < L) ? closest[(size_t)q * L + r] : 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int s = s0 + 4 * lane + i;
-      uint8_t slot = MCQ_NOSLOT;
-      if (s < S && r < L) {
-        const int t = ref_triplets[(size_t)ref * S + s];
-        int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
-        if (d0 == 4) d0 = cn[i][0];
-        if (d1 == 4) d1 = cn[i][1];
-        if (d2 == 4) d2 = cn[i][2];
-        slot = slot_of[s * 64 + (d0 * 16 + d1 * 4 + d2)];
-      }
-      tile[4 * lane + i][rr] = slot;
+  for (int r = warp; r < Lg; r += 8) {
+    uint8_t slot = MCQ_NOSLOT;
+    if (s < S && r < L) {
+      const int ref = closest[(size_t)q * L + r];
+      const int t = ref_triplets[(size_t)ref * S + s];
+      int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
+      if (d0 == 4) d0 = c0;
+      if (d1 == 4) d1 = c1;
+      if (d2 == 4) d2 = c2;
+      slot = slot_of[s * 64 + (d0 * 16 + d1 * 4 + d2)];
     }
+    tile[lane * stride + g_pos(r, nj)] = slot;
   }
   __syncthreads();
-  // write phase: half a warp covers the 64 states of one site row
-  const int sub = lane >> 4, l16 = lane & 15;
-#pragma unroll
-  for (int pass = 0; pass < GT_S / 16; pass++) {
-    const int ss = 2 * (warp + 8 * pass) + sub, so = s0 + ss, r = r0 + 4 * l16;
-    if (so < S && r < Ls) {   // Ls is a multiple of 16, so r..r+3 stay inside the row
-      const uchar4 v = make_uchar4(tile[ss][4 * l16], tile[ss][4 * l16 + 1], tile[ss][4 * l16 + 2], tile[ss][4 * l16 + 3]);
-      *reinterpret_cast<uchar4 *>(G + ((size_t)q * S + so) * Ls + r) = v;
-    }
+  for (int ss = warp; ss < 32; ss += 8) {
+    const int so = s0 + ss;
+    if (so >= S) break;
+    const uint4 *src = reinterpret_cast<const uint4 *>(tile + ss * stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(G + ((size_t)q * S + so) * Lg);
+    for (int i = lane; i < Lg / 16; i += 32) dst[i] = src[i];
   }
 }
 
 cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, const int8_t *cons_nucls,
-                              const uint8_t *slot_of, uint8_t *G, int Q, int S, int L, int Ls,
+                              const uint8_t *slot_of, uint8_t *G, int Q, int S, int L, int Lg,
                               cudaStream_t stream) {
-  // gridDim.z is limited to 65535: walk the queries in slabs
-  for (int q0 = 0; q0 < Q; q0 += 65535) {
+  const size_t smem = (size_t)32 * (Lg + 16);
+  for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
     int nq = Q - q0 < 65535 ? Q - q0 : 65535;
-    dim3 grid((S + GT_S - 1) / GT_S, (Ls + GT_R - 1) / GT_R, nq);
-    k_gather<<<grid, 256, 0, stream>>>(ref_triplets, closest + (size_t)q0 * L,
-                                       cons_nucls + (size_t)q0 * 3 * S, slot_of,
-                                       G + (size_t)q0 * S * Ls, S, L, Ls);
+    dim3 grid((S + 31) / 32, nq);
+    k_gather<<<grid, 256, smem, stream>>>(ref_triplets, closest + (size_t)q0 * L,
+                                          cons_nucls + (size_t)q0 * 3 * S, slot_of,
+                                          G + (size_t)q0 * S * Lg, S, L, Lg);
   }
   return cudaGetLastError();
 }
@@ -315,25 +309,47 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 #define MCQ_PF 3                 // sites staged ahead of the one being computed
 #define MCQ_RING (MCQ_PF + 1)    // ring slots per warp
-#define MCQ_ES 66                // doubles per staged emission row: slot 0 + up to 64 others, padded
+#ifndef MCQ_WPB
+#define MCQ_WPB 1                // warps (= queries) per block: small blocks balance best over the SMs
+#endif
+#define MCQ_ES 66                // doubles per staged emission row: slots 0..64 and a constant 0 at MCQ_NOSLOT
+
+// per-site lookahead state of a warp: everything stage_site needs for the NEXT site it will stage is
+// fetched one iteration early, so that no load sits between the wait and the cp.async issue
+struct SiteAhead {
+  int to;     // the query's codon at the site (row of the emission table)
+  int toff;   // start of the site's block in the table
+  int kr;     // entries per row
+};
+__device__ __forceinline__ SiteAhead look_ahead(const McqStatic &st, const uint8_t *__restrict__ qc, int t, bool valid) {
+  SiteAhead a;
+  a.to = 0; a.toff = 0; a.kr = 0;
+  if (valid) {
+    if (qc) a.to = qc[t];
+    const int a0 = st.aoff[t];
+    a.kr = st.aoff[t + 1] - a0;
+    a.toff = st.toff[t];
+  }
+  return a;
+}
 
 // Stage the rows of site t into ring slot t % MCQ_RING: one commit group per call, empty when the
-// site lies outside the range.  `to` is the query's codon at t (selects the table row).
+// site lies outside the range.
 template <int NJ>
-__device__ __forceinline__ void stage_site(uint8_t *gring, double *ering, int t, bool valid, int to, int q,
-                                           const McqStatic &st, const McqEmis &em,
+__device__ __forceinline__ void stage_site(uint8_t *gring, double *ering, int t, bool valid, const SiteAhead &sa,
+                                           int q, const McqStatic &st, const McqEmis &em,
                                            const uint8_t *__restrict__ Gq, int lane) {
   if (valid) {
-    const int slot = t % MCQ_RING, Ls = st.Ls;
-    const uint8_t *src = Gq + (size_t)t * Ls;
+    const int slot = t % MCQ_RING;
+    const uint8_t *src = Gq + (size_t)t * (64 * NJ);
     uint8_t *dst = gring + slot * (64 * NJ);
 #pragma unroll
     for (int i = 0; i < (NJ + 7) / 8; i++) {
       const int o = (lane + 32 * i) * 16;
-      if (o < Ls) cp_async16(dst + o, src + o);
+      if (o < 64 * NJ) cp_async16(dst + o, src + o);
     }
-    const int kr = st.aoff[t + 1] - st.aoff[t];
-    const double *row = em.tab + (size_t)st.toff[t] + (size_t)to * kr;
+    const int kr = sa.kr;
+    const double *row = em.tab + (size_t)sa.toff + (size_t)sa.to * kr;
     double *ed = ering + slot * MCQ_ES;
     for (int k = lane; k < kr; k += 32) cp_async8(ed + 1 + k, row + k);
     if (lane == 0 && em.ec != nullptr) cp_async8(ed, em.ec + (size_t)q * st.S + t);
@@ -341,18 +357,39 @@ __device__ __forceinline__ void stage_site(uint8_t *gring, double *ering, int t,
   cp_async_commit();
 }
 
+// the 2*NJ slot bytes a lane owns at one site: one vector load from the staged (permuted) G row
+template <int NJ>
+struct LaneSlots {
+  unsigned w[(2 * NJ + 3) / 4];
+  __device__ __forceinline__ void load(const uint8_t *gs, int lane) {
+    const uint8_t *p = gs + lane * (2 * NJ);
+    if constexpr (NJ == 1) w[0] = *reinterpret_cast<const uint16_t *>(p);
+    else if constexpr (NJ == 2) w[0] = *reinterpret_cast<const uint32_t *>(p);
+    else if constexpr (NJ == 4) { const uint2 v = *reinterpret_cast<const uint2 *>(p); w[0] = v.x; w[1] = v.y; }
+    else {
+#pragma unroll
+      for (int i = 0; i < NJ / 8; i++) {
+        const uint4 v = reinterpret_cast<const uint4 *>(p)[i];
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+      }
+    }
+  }
+  __device__ __forceinline__ unsigned first(int j) const { return (w[j >> 1] >> ((j & 1) * 16)) & 0xFFu; }
+  __device__ __forceinline__ unsigned second(int j) const { return (w[j >> 1] >> ((j & 1) * 16 + 8)) & 0xFFu; }
+};
+
 // ------------------------------------------------------------------------------------------
 // K4: forward recursion.  One warp per query; lane l holds states 64j+2l, 64j+2l+1 (j < NJ) of
-// the running column in registers.  Per site: the site's G row (Ls bytes) and emission row arrive
-// in shared memory through cp.async, staged MCQ_PF sites ahead so that no global-load latency sits
-// on the recurrence; one butterfly all-reduce (the column sum, which both decides the rescale and
-// is the next site's recombination sum); one 16-byte streaming store of F per lane per j
-// (512 contiguous bytes per warp instruction).
+// the running column in registers.  Per site: the site's G row and emission row arrive in shared
+// memory through cp.async, staged MCQ_PF sites ahead so that no global-load latency sits on the
+// recurrence; one butterfly all-reduce (the column sum, which both decides the rescale and is the
+// next site's recombination sum); one 16-byte streaming store of F per lane per j (512 contiguous
+// bytes per warp instruction).  FULL: Ls == 64*NJ, no row-bound predicates.
 // ------------------------------------------------------------------------------------------
-template <int NJ>
-__global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
-  __shared__ __align__(16) uint8_t s_g[4][MCQ_RING][64 * NJ];
-  __shared__ __align__(16) double s_e[4][MCQ_RING][MCQ_ES];
+template <int NJ, bool FULL>
+__global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
+  __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
+  __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (q >= a.st.Q) return;
@@ -362,26 +399,25 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
   }
   const int S = a.st.S, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
-  const uint8_t *__restrict__ Gq = a.st.G + qoff;
+  const uint8_t *__restrict__ Gq = a.st.G + (size_t)q * S * (64 * NJ);
   const uint8_t *__restrict__ qc = a.st.query_codon ? a.st.query_codon + (size_t)q * S : nullptr;
-  double *__restrict__ Fo = a.Fout + qoff;
+  double *__restrict__ Fo = a.Fout + qoff + 2 * lane;
   int *__restrict__ Fno = a.Fn_out + (size_t)q * S;
-  const double Nd = (double)a.st.N;
   uint8_t *gring = &s_g[wib][0][0];
   double *ering = &s_e[wib][0][0];
+  if (lane < MCQ_RING) ering[lane * MCQ_ES + MCQ_NOSLOT] = 0.0;   // the "no such codon" emission
 
-  int r0[NJ];
   bool inrow[NJ];
 #pragma unroll
-  for (int j = 0; j < NJ; j++) { r0[j] = 64 * j + 2 * lane; inrow[j] = r0[j] < Ls; }
+  for (int j = 0; j < NJ; j++) inrow[j] = FULL || (64 * j + 2 * lane < Ls);
 
-  // prologue: rows of the first MCQ_PF sites of the range; the query's codon is fetched one site
-  // further ahead than the rows it selects
+  // prologue: rows of the first MCQ_PF sites of the range
   int t = a.start;
 #pragma unroll
   for (int i = 0; i < MCQ_PF; i++, t++)
-    stage_site<NJ>(gring, ering, t, t <= a.end, (qc && t <= a.end) ? qc[t] : 0, q, a.st, a.em, Gq, lane);
-  int to_next = (qc && t <= a.end) ? qc[t] : 0;   // codon at site t = start + MCQ_PF
+    stage_site<NJ>(gring, ering, t, t <= a.end, look_ahead(a.st, qc, t, t <= a.end), q, a.st, a.em, Gq, lane);
+  SiteAhead ahead = look_ahead(a.st, qc, t, t <= a.end);   // site t = start + MCQ_PF
+  const double invN = 1.0 / (double)a.st.N;
 
   double p0[NJ], p1[NJ];   // the running column
   int s = a.start, cnt;
@@ -392,24 +428,19 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
     cp_async_wait<MCQ_PF - 1>();
     __syncwarp();
     {
-      const int to = to_next;
-      to_next = (qc && t + 1 <= a.end) ? qc[t + 1] : 0;
-      stage_site<NJ>(gring, ering, t, t <= a.end, to, q, a.st, a.em, Gq, lane);
+      const SiteAhead cur = ahead;
+      ahead = look_ahead(a.st, qc, t + 1, t + 1 <= a.end);
+      stage_site<NJ>(gring, ering, t, t <= a.end, cur, q, a.st, a.em, Gq, lane);
       t++;
     }
-    const uint8_t *gs = gring;              // ring slot 0
+    LaneSlots<NJ> g;
+    g.load(gring, lane);              // ring slot 0
     const double *es = ering;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      p0[j] = 0.0; p1[j] = 0.0;
-      if (inrow[j]) {
-        const unsigned gg = *reinterpret_cast<const uint16_t *>(gs + r0[j]);
-        const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
-        if (g0 != MCQ_NOSLOT) p0[j] = es[g0];
-        if (g1 != MCQ_NOSLOT) p1[j] = es[g1];
-        __stcs(reinterpret_cast<double2 *>(Fo + r0[j]), make_double2(p0[j], p1[j]));
-      }
+      p0[j] = es[g.first(j)]; p1[j] = es[g.second(j)];
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Fo + 64 * j), make_double2(p0[j], p1[j]));
       loc += p0[j]; loc += p1[j];
     }
     cnt = 0;
@@ -421,13 +452,13 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
     tot = warp_sum(loc);
     s = 1;
   } else {
-    const double *__restrict__ Fi = a.Fin + qoff + (size_t)(s - 1) * Ls;
+    const double *__restrict__ Fi = a.Fin + qoff + (size_t)(s - 1) * Ls + 2 * lane;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       p0[j] = 0.0; p1[j] = 0.0;
       if (inrow[j]) {
-        const double2 v = *reinterpret_cast<const double2 *>(Fi + r0[j]);
+        const double2 v = *reinterpret_cast<const double2 *>(Fi + 64 * j);
         p0[j] = v.x; p1[j] = v.y;
       }
       loc += p0[j]; loc += p1[j];
@@ -436,34 +467,35 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
     tot = warp_sum(loc);
   }
 
+  double Rnext = (s <= a.end) ? ((s == a.r_site) ? a.r_value : a.R[s]) : 0.0;
   for (; s <= a.end; ++s) {
     cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed (this lane's copies)
     __syncwarp();                  // ... and every other lane's; the slot of site s-1 is free again
     {
-      const int to = to_next;
-      to_next = (qc && t + 1 <= a.end) ? qc[t + 1] : 0;
-      stage_site<NJ>(gring, ering, t, t <= a.end, to, q, a.st, a.em, Gq, lane);
+      const SiteAhead cur = ahead;
+      ahead = look_ahead(a.st, qc, t + 1, t + 1 <= a.end);
+      stage_site<NJ>(gring, ering, t, t <= a.end, cur, q, a.st, a.em, Gq, lane);
       t++;
     }
-    const uint8_t *gs = gring + (s % MCQ_RING) * (64 * NJ);
+    LaneSlots<NJ> g;
+    g.load(gring + (s % MCQ_RING) * (64 * NJ), lane);
     const double *es = ering + (s % MCQ_RING) * MCQ_ES;
-    const double Rs = (s == a.r_site) ? a.r_value : a.R[s];
-    const double jump = tot * Rs / Nd;          // forward_backward.c:138
+    const double Rs = Rnext;
+    Rnext = (s + 1 <= a.end) ? ((s + 1 == a.r_site) ? a.r_value : a.R[s + 1]) : 0.0;
+    // forward_backward.c:138 divides by N and :141-142 adds then multiplies; here the reciprocal and
+    // a fused multiply-add keep the per-site dependency chain short (each one rounding away from
+    // the reference's sequence, far inside the tolerance - the order of the sum differs anyway)
+    const double jump = tot * Rs * invN;
     const double stay = 1 - Rs;
-    double loc = 0.0;
+    double la = 0.0, lb = 0.0;     // two partial sums: a shorter dependent chain than one
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      unsigned gg = 0xFFFFu;
-      if (inrow[j]) gg = *reinterpret_cast<const uint16_t *>(gs + r0[j]);
-      const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
-      const double e0 = (g0 != MCQ_NOSLOT) ? es[g0] : 0.0;
-      const double e1 = (g1 != MCQ_NOSLOT) ? es[g1] : 0.0;
-      double v0 = jump; v0 += stay * p0[j]; v0 *= e0;
-      double v1 = jump; v1 += stay * p1[j]; v1 *= e1;
+      const double v0 = __fma_rn(stay, p0[j], jump) * es[g.first(j)];
+      const double v1 = __fma_rn(stay, p1[j], jump) * es[g.second(j)];
       p0[j] = v0; p1[j] = v1;
-      loc += v0; loc += v1;
+      la += v0; lb += v1;
     }
-    tot = warp_sum(loc);
+    tot = warp_sum(la + lb);
     if (tot < MCQ_BIGI) {                       // forward_backward.c:163-167
       ++cnt;
 #pragma unroll
@@ -473,7 +505,7 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
     double *__restrict__ Fs = Fo + (size_t)s * Ls;
 #pragma unroll
     for (int j = 0; j < NJ; j++)
-      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + r0[j]), make_double2(p0[j], p1[j]));
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(p0[j], p1[j]));
     if (lane == 0) Fno[s] = cnt;
   }
   cp_async_wait<0>();
@@ -483,12 +515,12 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
     double dot;
     int nrm = cnt;
     if (a.llk_mode == 1) {                      // mcmc_moves.c:220-223
-      const double *__restrict__ Bc = a.B + qoff + (size_t)a.end * Ls;
+      const double *__restrict__ Bc = a.B + qoff + (size_t)a.end * Ls + 2 * lane;
       double loc = 0.0;
 #pragma unroll
       for (int j = 0; j < NJ; j++)
         if (inrow[j]) {
-          const double2 b = *reinterpret_cast<const double2 *>(Bc + r0[j]);
+          const double2 b = *reinterpret_cast<const double2 *>(Bc + 64 * j);
           loc += p0[j] * b.x; loc += p1[j] * b.y;
         }
       dot = warp_sum(loc);
@@ -500,16 +532,23 @@ __global__ void __launch_bounds__(128) k_forward(const FwdArgs a) {
   }
 }
 
-cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
-  const int nj = (a.st.Ls + 63) / 64;
-  const unsigned blocks = (unsigned)(((size_t)a.st.Q * 32 + 127) / 128);
-  if (nj <= 1) k_forward<1><<<blocks, 128, 0, stream>>>(a);
-  else if (nj <= 2) k_forward<2><<<blocks, 128, 0, stream>>>(a);
-  else if (nj <= 4) k_forward<4><<<blocks, 128, 0, stream>>>(a);
-  else if (nj <= 8) k_forward<8><<<blocks, 128, 0, stream>>>(a);
-  else if (nj <= 16) k_forward<16><<<blocks, 128, 0, stream>>>(a);
-  else return cudaErrorInvalidValue;
+template <int NJ>
+static cudaError_t launch_forward_nj(const FwdArgs &a, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((a.st.Q + MCQ_WPB - 1) / MCQ_WPB);
+  if (a.st.Ls == 64 * NJ) k_forward<NJ, true><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+  else k_forward<NJ, false><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
   return cudaGetLastError();
+}
+
+cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
+  switch (a.st.Lg / 64) {
+    case 1: return launch_forward_nj<1>(a, stream);
+    case 2: return launch_forward_nj<2>(a, stream);
+    case 4: return launch_forward_nj<4>(a, stream);
+    case 8: return launch_forward_nj<8>(a, stream);
+    case 16: return launch_forward_nj<16>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -517,37 +556,41 @@ cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
 // e = the emission at s+1, sx = sum_r b*e.  The column sum of the new column and the next sx are
 // reduced together in one butterfly.
 // ------------------------------------------------------------------------------------------
-template <int NJ>
-__global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
-  __shared__ __align__(16) uint8_t s_g[4][MCQ_RING][64 * NJ];
-  __shared__ __align__(16) double s_e[4][MCQ_RING][MCQ_ES];
+template <int NJ, bool FULL>
+__global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
+  __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
+  __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (q >= a.st.Q) return;
   if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) return;
   const int S = a.st.S, L = a.st.L, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
-  const uint8_t *__restrict__ Gq = a.st.G + qoff;
+  const uint8_t *__restrict__ Gq = a.st.G + (size_t)q * S * (64 * NJ);
   const uint8_t *__restrict__ qc = a.st.query_codon ? a.st.query_codon + (size_t)q * S : nullptr;
-  double *__restrict__ Bq = a.B + qoff;
+  double *__restrict__ Bq = a.B + qoff + 2 * lane;
   int *__restrict__ Bnq = a.Bn + (size_t)q * S;
-  const double Nd = (double)a.st.N;
   uint8_t *gring = &s_g[wib][0][0];
   double *ering = &s_e[wib][0][0];
+  if (lane < MCQ_RING) ering[lane * MCQ_ES + MCQ_NOSLOT] = 0.0;
 
-  int r0[NJ];
   bool inrow[NJ];
+  double m0[NJ], m1[NJ];   // 1 for real states, 0 for padding (r >= L): padding must not pick up `jump`
 #pragma unroll
-  for (int j = 0; j < NJ; j++) { r0[j] = 64 * j + 2 * lane; inrow[j] = r0[j] < Ls; }
+  for (int j = 0; j < NJ; j++) {
+    const int r = 64 * j + 2 * lane;
+    inrow[j] = FULL || (r < Ls);
+    m0[j] = (r < L) ? 1.0 : 0.0;
+    m1[j] = (r + 1 < L) ? 1.0 : 0.0;
+  }
 
   double b0[NJ], b1[NJ], e0[NJ], e1[NJ];
   int s = a.update, cnt;
   if (s == S - 1) {                             // forward_backward.c:197-203
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      b0[j] = (r0[j] < L) ? 1.0 : 0.0;
-      b1[j] = (r0[j] + 1 < L) ? 1.0 : 0.0;
-      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bq + (size_t)s * Ls + r0[j]), make_double2(b0[j], b1[j]));
+      b0[j] = m0[j]; b1[j] = m1[j];
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bq + (size_t)s * Ls + 64 * j), make_double2(b0[j], b1[j]));
     }
     cnt = 0;
     if (lane == 0) Bnq[s] = 0;
@@ -557,7 +600,7 @@ __global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
     for (int j = 0; j < NJ; j++) {
       b0[j] = 0.0; b1[j] = 0.0;
       if (inrow[j]) {
-        const double2 v = *reinterpret_cast<const double2 *>(Bq + (size_t)(s + 1) * Ls + r0[j]);
+        const double2 v = *reinterpret_cast<const double2 *>(Bq + (size_t)(s + 1) * Ls + 64 * j);
         b0[j] = v.x; b1[j] = v.y;
       }
     }
@@ -569,8 +612,9 @@ __global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
   int t = s + 1;
 #pragma unroll
   for (int i = 0; i < MCQ_PF; i++, t--)
-    stage_site<NJ>(gring, ering, t, t >= 0, (qc && t >= 0) ? qc[t] : 0, q, a.st, a.em, Gq, lane);
-  int to_next = (qc && t >= 0) ? qc[t] : 0;
+    stage_site<NJ>(gring, ering, t, t >= 0, look_ahead(a.st, qc, t, t >= 0), q, a.st, a.em, Gq, lane);
+  SiteAhead ahead = look_ahead(a.st, qc, t, t >= 0);
+  const double invN = 1.0 / (double)a.st.N;
 
   // emission at s+1 and sx
   double sx;
@@ -578,58 +622,52 @@ __global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
     cp_async_wait<MCQ_PF - 1>();
     __syncwarp();
     {
-      const int to = to_next;
-      to_next = (qc && t - 1 >= 0) ? qc[t - 1] : 0;
-      stage_site<NJ>(gring, ering, t, t >= 0, to, q, a.st, a.em, Gq, lane);
+      const SiteAhead cur = ahead;
+      ahead = look_ahead(a.st, qc, t - 1, t - 1 >= 0);
+      stage_site<NJ>(gring, ering, t, t >= 0, cur, q, a.st, a.em, Gq, lane);
       t--;
     }
-    const uint8_t *gs = gring + ((s + 1) % MCQ_RING) * (64 * NJ);
+    LaneSlots<NJ> g;
+    g.load(gring + ((s + 1) % MCQ_RING) * (64 * NJ), lane);
     const double *es = ering + ((s + 1) % MCQ_RING) * MCQ_ES;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      unsigned gg = 0xFFFFu;
-      if (inrow[j]) gg = *reinterpret_cast<const uint16_t *>(gs + r0[j]);
-      const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
-      e0[j] = (g0 != MCQ_NOSLOT) ? es[g0] : 0.0;
-      e1[j] = (g1 != MCQ_NOSLOT) ? es[g1] : 0.0;
+      e0[j] = es[g.first(j)]; e1[j] = es[g.second(j)];
       loc += b0[j] * e0[j]; loc += b1[j] * e1[j];
     }
     sx = warp_sum(loc);
   }
 
+  double Rnext = a.R[s + 1];
   for (; s >= 0; --s) {
     cp_async_wait<MCQ_PF - 1>();   // rows of site s
     __syncwarp();
     {
-      const int to = to_next;
-      to_next = (qc && t - 1 >= 0) ? qc[t - 1] : 0;
-      stage_site<NJ>(gring, ering, t, t >= 0, to, q, a.st, a.em, Gq, lane);
+      const SiteAhead cur = ahead;
+      ahead = look_ahead(a.st, qc, t - 1, t - 1 >= 0);
+      stage_site<NJ>(gring, ering, t, t >= 0, cur, q, a.st, a.em, Gq, lane);
       t--;
     }
-    const uint8_t *gs = gring + (s % MCQ_RING) * (64 * NJ);
+    LaneSlots<NJ> g;
+    g.load(gring + (s % MCQ_RING) * (64 * NJ), lane);
     const double *es = ering + (s % MCQ_RING) * MCQ_ES;
-    const double Rn = a.R[s + 1];
-    const double jump = sx * Rn / Nd;           // forward_backward.c:219
+    const double Rn = Rnext;
+    Rnext = a.R[s];                             // R[(s-1)+1] for the next iteration
+    const double jump = sx * Rn * invN;         // forward_backward.c:219 (reciprocal: see k_forward)
     const double stay = 1 - Rn;
-    double locv = 0.0, locy = 0.0;
+    double locv = 0.0, locy = 0.0, locv2 = 0.0, locy2 = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      unsigned gg = 0xFFFFu;
-      if (inrow[j]) gg = *reinterpret_cast<const uint16_t *>(gs + r0[j]);
-      const unsigned g0 = gg & 0xFF, g1 = gg >> 8;
-      const double n0 = (g0 != MCQ_NOSLOT) ? es[g0] : 0.0;   // emission at s, for the next step's products
-      const double n1 = (g1 != MCQ_NOSLOT) ? es[g1] : 0.0;
-      // pad states (r >= L) must stay 0: they would otherwise pick up `jump`
-      double v0 = jump; v0 += stay * b0[j] * e0[j];
-      double v1 = jump; v1 += stay * b1[j] * e1[j];
-      if (r0[j] >= L) v0 = 0.0;
-      if (r0[j] + 1 >= L) v1 = 0.0;
+      const double n0 = es[g.first(j)], n1 = es[g.second(j)];   // emission at s, for the next step's products
+      const double v0 = __fma_rn(stay * b0[j], e0[j], jump) * m0[j];
+      const double v1 = __fma_rn(stay * b1[j], e1[j], jump) * m1[j];
       b0[j] = v0; b1[j] = v1;
-      locv += v0; locv += v1;
-      locy += v0 * n0; locy += v1 * n1;
+      locv += v0; locv2 += v1;
+      locy = __fma_rn(v0, n0, locy); locy2 = __fma_rn(v1, n1, locy2);
       e0[j] = n0; e1[j] = n1;
     }
+    locv += locv2; locy += locy2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       locv += __shfl_xor_sync(0xffffffffu, locv, o);
@@ -645,22 +683,29 @@ __global__ void __launch_bounds__(128) k_backward(const BwdArgs a) {
     double *__restrict__ Bs = Bq + (size_t)s * Ls;
 #pragma unroll
     for (int j = 0; j < NJ; j++)
-      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bs + r0[j]), make_double2(b0[j], b1[j]));
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bs + 64 * j), make_double2(b0[j], b1[j]));
     if (lane == 0) Bnq[s] = cnt;
   }
   cp_async_wait<0>();
 }
 
-cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream) {
-  const int nj = (a.st.Ls + 63) / 64;
-  const unsigned blocks = (unsigned)(((size_t)a.st.Q * 32 + 127) / 128);
-  if (nj <= 1) k_backward<1><<<blocks, 128, 0, stream>>>(a);
-  else if (nj <= 2) k_backward<2><<<blocks, 128, 0, stream>>>(a);
-  else if (nj <= 4) k_backward<4><<<blocks, 128, 0, stream>>>(a);
-  else if (nj <= 8) k_backward<8><<<blocks, 128, 0, stream>>>(a);
-  else if (nj <= 16) k_backward<16><<<blocks, 128, 0, stream>>>(a);
-  else return cudaErrorInvalidValue;
+template <int NJ>
+static cudaError_t launch_backward_nj(const BwdArgs &a, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((a.st.Q + MCQ_WPB - 1) / MCQ_WPB);
+  if (a.st.Ls == 64 * NJ) k_backward<NJ, true><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+  else k_backward<NJ, false><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
   return cudaGetLastError();
+}
+
+cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream) {
+  switch (a.st.Lg / 64) {
+    case 1: return launch_backward_nj<1>(a, stream);
+    case 2: return launch_backward_nj<2>(a, stream);
+    case 4: return launch_backward_nj<4>(a, stream);
+    case 8: return launch_backward_nj<8>(a, stream);
+    case 16: return launch_backward_nj<16>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
