@@ -212,6 +212,11 @@ int mcq_host_unregister(void *ptr);
 int mcq_comm_unique_id(unsigned char id[128]);
 int mcq_ctx_attach_comm(mcq_ctx *ctx, int nranks, int rank, const unsigned char id[128]);
 
+/* Substitution class of the codon pair (c1,c2), codons numbered base-4 over T,C,A,G: 0 none or
+ * multi-step, 1 non-synonymous transition, 2 non-synonymous transversion, 3 synonymous transition,
+ * 4 synonymous transversion - the content of NS_TS / NS_TV / S_TS / S_TV (constants.c:424-688). */
+int mcq_codon_class(int c1, int c2);
+
 /* ---- batched closest-L (closest_seqs.c over all queries; fill_closest_n, dmodel.c:356-387) -- */
 /* ref_seqs: num_refs rows of num_bases ASCII bytes (row stride ref_stride), queries likewise.
  * skip_first = the -q self-reference mode (find closest_n+1, drop the first, dmodel.c:362,380-386).

@@ -69,6 +69,7 @@ SYMBOLS = {
     "mcq_host_unregister": (C.c_int, [_V]),
     "mcq_comm_unique_id": (C.c_int, [_V]),
     "mcq_ctx_attach_comm": (C.c_int, [_V, C.c_int, C.c_int, _V]),
+    "mcq_codon_class": (C.c_int, [C.c_int, C.c_int]),
     "mcq_closest_batch": (C.c_int, [C.c_int, _V, C.c_size_t, C.c_int, _V, C.c_size_t, C.c_int, C.c_int,
                                     C.c_int, C.c_int, _V]),
     "mcq_hamming_batch": (C.c_int, [C.c_int, _V, C.c_size_t, C.c_int, _V, C.c_size_t, C.c_int, C.c_int, _V]),
