@@ -73,3 +73,19 @@ def test_trace_matches_reference_dmodel(tmp_path, extra, gaps):
     assert np.array_equal(ours_log[:, 0], ref_log[:, 0])
     assert np.allclose(ours_log[:, 1], ref_log[:, 1], rtol=1e-9, atol=0)
     assert np.array_equal(ours_log[:, 2:], ref_log[:, 2:])
+
+
+def test_reference_dmodel_linked_against_the_dropin_symbols(tmp_path):
+    """The UNMODIFIED reference dmodel with forward_backward.o / closest_seqs.o replaced by
+    libmcq_b200.so (oracle/_ref/dmodel_dropin): same decisions as the all-CPU reference."""
+    dropin = os.path.join(ROOT, "oracle", "_ref", "dmodel_dropin")
+    if not (os.path.exists(dropin) and os.path.exists(cpu_libs.REF_DMODEL)):
+        pytest.skip("oracle/_ref binaries not present")
+    paths, L, _ = make_chain_inputs(str(tmp_path / "in"), "toy", Q=12, S=60)
+    args = ["-H", paths["hla"], "-l", str(L), "-n", "300", "-s", "50", paths["ref"], paths["query"]]
+    traces = []
+    for exe, name in ((cpu_libs.REF_DMODEL, "ref"), (dropin, "dropin")):
+        t = str(tmp_path / f"{name}.trace")
+        run([exe] + args + [str(tmp_path / name)], env={"MCQ_SEED": "3", "MCQ_GSL_SEED": "3", "MCQ_TRACE": t})
+        traces.append(read_trace(t))
+    assert traces[0].shape == traces[1].shape and np.array_equal(traces[0], traces[1])

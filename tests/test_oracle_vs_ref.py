@@ -93,3 +93,50 @@ def test_hamming_survey_example(libs):
     refs = np.frombuffer(b"ACGTACGNNNNNacgt", np.uint8).reshape(4, 4).copy()
     q = np.frombuffer(b"AC-T", np.uint8).copy()
     assert list(orc.hamming(refs, q)) == [0, 2, 6, 0] == list(ref.hamming(refs, q))
+
+
+def test_mu_rescale_matches_mutation_move(libs):
+    """orc_mu_rescale against the rescale loop inside the reference's mutation_move
+    (mcmc_moves.c:1082-1111), driven through the whole move with a seeded proposal."""
+    import ctypes as C
+    import math
+    orc, ref = libs
+    p = make_problem("toy")
+    st = cpu_libs.full_state(ref, p)
+    Q, S, L = p.Q, p.S, p.L
+    lib = ref.lib
+    C.c_double.in_dll(lib, "phi").value = p.phi
+    prior_c1 = (C.c_double * 64).in_dll(lib, "prior_C1")
+    for i in range(64):
+        prior_c1[i] = p.prior[i]
+    c2c, A = st["c2c"].copy(), st["A"].copy()
+    tc2c, tA = np.zeros_like(c2c), np.zeros_like(A)
+    F, tF = st["F"].copy(), np.zeros_like(st["F"])
+    Fn, tFn = st["Fn"].copy(), np.zeros_like(st["Fn"])
+    B, Bn = st["B"].copy(), st["Bn"].copy()
+    mu = C.c_double(p.mu)
+    llk = C.c_double(float(st["llk"].sum()))
+    R = p.R.copy()
+
+    def pp(a):
+        return C.byref(C.c_void_p(a.ctypes.data))
+
+    seed = 77
+    cpu_libs.srandom(seed)
+    u = cpu_libs.libc_random() / 2147483647.0
+    mu_new = p.mu * math.exp((1 * u - 0.5) / 4)
+    cpu_libs.srandom(seed)
+    holders = [C.c_void_p(a.ctypes.data) for a in (F, Fn, c2c, A, tA, tc2c, tF, tFn)]
+    lib.mutation_move(C.c_double(1.0), S, L, p.N, Q, cpu_libs.ip(p.n_site_codons), cpu_libs.cp(p.site_codons),
+                      C.byref(mu), cpu_libs.dp(R), C.byref(holders[0]), cpu_libs.dp(B), C.byref(holders[1]),
+                      cpu_libs.ip(Bn), C.byref(holders[2]), cpu_libs.cp(p.ref_codons), cpu_libs.cp(p.ref_triplets),
+                      cpu_libs.cp(p.query_codons), C.byref(holders[3]), C.byref(holders[4]), C.byref(holders[5]),
+                      C.byref(holders[6]), C.byref(llk), cpu_libs.ip(p.closest_refs), C.byref(holders[7]),
+                      3 * S, cpu_libs.cp(p.cons_query_nucls))
+    # the rescaled tables were written into the arrays that were "tmp" on entry (swapped or not)
+    want_c2c, want_A = np.zeros_like(c2c), np.zeros_like(A)
+    orc.lib.orc_mu_rescale(S, p.N, Q, cpu_libs.ip(p.n_site_codons), cpu_libs.cp(p.site_codons),
+                           cpu_libs.dp(st["c2c"]), cpu_libs.dp(st["A"]), cpu_libs.dp(want_c2c), cpu_libs.dp(want_A),
+                           cpu_libs.cp(p.query_codons), C.c_double(p.mu), C.c_double(mu_new), C.c_double(p.phi),
+                           cpu_libs.dp(p.prior))
+    assert np.array_equal(tc2c, want_c2c) and np.array_equal(tA, want_A)
