@@ -206,6 +206,47 @@ def run_ref_bench(p, threads, seconds, path=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# dmodel MCMC steps/s (second half of BASELINE.json's metric): the C driver on the GPU library next
+# to the reference dmodel on the host CPU, same files, same seeds, default move mix with annealing
+# ------------------------------------------------------------------------------------------------
+def mcmc_steps_per_s(workload, steps, ref_steps=12):
+    import re
+    import shutil
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from chain_files import make_chain_inputs
+    driver = os.path.join(ROOT, "mcqueen_b200", "host", "mcq_dmodel")
+    if not os.path.exists(driver):
+        return {"error": "mcqueen_b200/host/mcq_dmodel not built"}
+    tmp = tempfile.mkdtemp(prefix="mcq_mcmc_")
+    out = {"workload": workload, "steps": steps}
+    try:
+        paths, L, _ = make_chain_inputs(os.path.join(tmp, "in"), workload, seed=SEED)
+        base = ["-H", paths["hla"], "-l", str(L), "-s", "1000000", paths["ref"], paths["query"]]
+        for key, extra in (("gpu", []), ("gpu_sparse_esc", ["--sparse_esc"])):
+            r = subprocess.run([driver, "--seed", "1", "--gsl_seed", "1", "-n", str(steps)] + extra + base +
+                               [os.path.join(tmp, key)], capture_output=True, text=True)
+            m = re.search(r"MCMC loop: (\d+) steps in ([0-9.]+) s = ([0-9.]+) steps/s", r.stdout)
+            out[key + "_steps_per_s"] = float(m.group(3)) if m else None
+            if not m:
+                out[key + "_error"] = (r.stdout + r.stderr)[-300:]
+        ref = os.path.join(ROOT, "oracle", "_ref", "dmodel_ref")
+        if os.path.exists(ref) and ref_steps > 0:
+            env = dict(os.environ, MCQ_SEED="1", MCQ_GSL_SEED="1")
+            t = []
+            for n in (1, 1 + ref_steps):     # the difference removes the start-up (closest-L, initial F/B)
+                t0 = time.perf_counter()
+                subprocess.run([ref, "-n", str(n)] + base + [os.path.join(tmp, f"ref{n}")], capture_output=True,
+                               text=True, env=env, check=True)
+                t.append(time.perf_counter() - t0)
+            out["reference_cpu_steps_per_s"] = ref_steps / max(t[1] - t[0], 1e-9)
+            out["reference_cpu"] = f"unmodified reference dmodel, 1 core, {ref_steps} steps after start-up " \
+                                   f"({t[0]:.1f} s start-up incl. closest-L and initial F/B)"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,6 +256,8 @@ def main():
     ap.add_argument("--workload", default="C4", choices=list(synth.CONFIGS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-mcmc", action="store_true", help="skip the dmodel MCMC steps/s measurement")
+    ap.add_argument("--mcmc-steps", type=int, default=3000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -344,6 +387,8 @@ def main():
         e2e_step()
     barrier()
     e2e_parts[:] = 0
+    ctx.enable_timing(2)
+    ctx.kernel_time(api.K_GATHER, reset=True)
     ctx.timer_start()
     t_e2e = time.perf_counter()
     for _ in range(args.steps):
@@ -351,6 +396,8 @@ def main():
     ms_e2e_dev = ctx.timer_stop()
     barrier()
     t_e2e = (time.perf_counter() - t_e2e) * 1e3
+    gather_ms = ctx.kernel_time(api.K_GATHER)[0] / max(args.steps, 1)
+    ctx.enable_timing(0)
     for a in host_arrays:
         api.host_unregister(a)
     assert abs(tot - llk0) <= 1e-12 * abs(llk0)
@@ -423,7 +470,7 @@ def main():
             "e2e": {"value": total_cells / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                     "breakdown_ms": dict(zip(["upload_static", "set_params", "full_llk", "read_back"],
-                                             (e2e_parts / args.steps * 1e3).round(3).tolist())),
+                                             (e2e_parts / args.steps * 1e3).round(3).tolist()), gather_kernel=round(gather_ms, 3)),
                     "what": "mcq_ctx_upload_static + mcq_ctx_set_params + mcq_ctx_full_llk + per-query llk "
                             "read-back, all inputs from pinned host buffers every step"},
             "roofline": {"bound": "hbm", "kernel": "k_forward", "achieved": achieved, "peak": peak,
@@ -436,6 +483,9 @@ def main():
             "kernel_share": {"forward_ms_per_step": fwd_ms / max(args.steps, 1),
                              "emission_ms_per_step": emi_ms / max(args.steps, 1)},
         }
+        if world == 1 and not args.no_mcmc:
+            ctx.close()          # frees the C4 context before the driver allocates its own
+            line["mcmc"] = mcmc_steps_per_s("C2", args.mcmc_steps)
         if world == 1 and args.cpu_seconds > 0:
             ncpu = os.cpu_count() or 1
             v, desc = run_ref_bench(p, ncpu, args.cpu_seconds)

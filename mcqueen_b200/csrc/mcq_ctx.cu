@@ -123,7 +123,7 @@ struct mcq_ctx {
   // staging buffers of mcq_ctx_upload_static (kept so that a re-upload allocates nothing)
   int8_t *st_trip = nullptr, *st_cons = nullptr;
   int *st_closest = nullptr;
-  uint8_t *st_slot_of = nullptr;
+  uint8_t *st_slot_of = nullptr, *st_trip_tab = nullptr;
   std::vector<uint8_t> st_bits;
 
   ncclComm_t comm = nullptr;
@@ -202,6 +202,7 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   REQUIRE(dims->num_sites > 0 && dims->closest_n > 0 && dims->total_num_refs > 0 && dims->num_query > 0 &&
               dims->num_hla_types > 0, "dimensions must be positive");
   REQUIRE(dims->closest_n <= 1024, "closest_n > 1024 is not supported");
+  REQUIRE((double)dims->total_num_refs * dims->num_sites < 4.0e9, "total_num_refs * num_sites must stay below 4e9");
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   REQUIRE(ndev > 0, "no CUDA device: libmcq_b200 has no CPU fallback");
@@ -240,7 +241,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   void *ptrs[] = {c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
-                  c->llk_cur, c->llk_prop, c->d_sum, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of};
+                  c->llk_cur, c->llk_prop, c->d_sum, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
@@ -382,6 +383,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     ALLOC(c->st_cons, (size_t)Q * 3 * S);
     ALLOC(c->st_closest, (size_t)Q * L);
     ALLOC(c->st_slot_of, (size_t)S * 64);
+    ALLOC(c->st_trip_tab, (size_t)(S + 31) / 32 * 32 * 128);
     const size_t cells = (size_t)Q * S * c->Ls;
     ALLOC(c->F, cells); ALLOC(c->B, cells); ALLOC(c->T, cells);
     ALLOC(c->Fn, (size_t)Q * S); ALLOC(c->Bn, (size_t)Q * S); ALLOC(c->Tn, (size_t)Q * S);
@@ -416,7 +418,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
   {
     KScope ks(c, MCQ_K_GATHER);
-    CK(mcq_launch_gather(c->st_trip, c->st_closest, c->st_cons, c->st_slot_of, c->G, Q, S, L, c->Lg, c->stream));
+    CK(mcq_launch_gather(c->st_trip, c->st_closest, c->st_cons, c->st_slot_of, c->st_trip_tab, c->G, Q, S, L, c->Lg, c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   c->have_static = true;

@@ -38,7 +38,7 @@ struct Scratch {
   // device
   int8_t *trip = nullptr, *cons = nullptr;
   int *closest = nullptr, *aoff = nullptr, *Fn = nullptr, *Tn = nullptr;
-  uint8_t *slot_of = nullptr, *G = nullptr;
+  uint8_t *slot_of = nullptr, *trip_tab = nullptr, *G = nullptr;
   double *E = nullptr, *R = nullptr, *F = nullptr, *T = nullptr;
   // host staging
   std::vector<int8_t> h_trip;
@@ -46,10 +46,10 @@ struct Scratch {
   std::vector<int> h_n;
 
   void release() {
-    void *p[] = {trip, cons, closest, aoff, Fn, Tn, slot_of, G, E, R, F, T};
+    void *p[] = {trip, cons, closest, aoff, Fn, Tn, slot_of, trip_tab, G, E, R, F, T};
     for (void *x : p)
       if (x) cudaFree(x);
-    trip = cons = nullptr; closest = aoff = Fn = Tn = nullptr; slot_of = G = nullptr;
+    trip = cons = nullptr; closest = aoff = Fn = Tn = nullptr; slot_of = trip_tab = G = nullptr;
     E = R = F = T = nullptr;
   }
 
@@ -77,6 +77,7 @@ struct Scratch {
     DK(cudaMalloc((void **)&Fn, (size_t)S * sizeof(int)));
     DK(cudaMalloc((void **)&Tn, (size_t)S * sizeof(int)));
     DK(cudaMalloc((void **)&slot_of, (size_t)S * 64));
+    DK(cudaMalloc((void **)&trip_tab, (size_t)(S + 31) / 32 * 32 * 128));
     DK(cudaMalloc((void **)&G, (size_t)S * Lg));
     DK(cudaMalloc((void **)&E, (size_t)S * 64 * sizeof(double)));
     DK(cudaMalloc((void **)&R, (size_t)S * sizeof(double)));
@@ -118,7 +119,7 @@ struct Scratch {
     DK(cudaMemcpyAsync(cons, cons_nucls, (size_t)3 * S, cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(E, h_E.data(), h_E.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(R, Rh, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, stream));
-    DK(mcq_launch_gather(trip, closest, cons, slot_of, G, 1, S, L, Lg, stream));
+    DK(mcq_launch_gather(trip, closest, cons, slot_of, trip_tab, G, 1, S, L, Lg, stream));
   }
 
   // one column host[L][S] (stride S) -> device column

@@ -72,57 +72,108 @@ __device__ __forceinline__ double warp_sum(double v) {
 // k_backward - 64j+2l, 64j+2l+1 for j < NJ - are contiguous at byte offset l*2*NJ, so a lane
 // fetches all of them with one vector load from the staged row.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int g_pos(int r, int nj) { return ((r & 63) >> 1) * (2 * nj) + 2 * (r >> 6) + (r & 1); }
+// state index stored at physical byte `pos` of a G row (the inverse of the lane-major permutation)
+__device__ __forceinline__ int g_state_of(int pos, int lg2) {   // lg2 = log2(2*NJ), bytes per lane
+  return 64 * ((pos & ((1 << lg2) - 1)) >> 1) + 2 * (pos >> lg2) + (pos & 1);
+}
+
+#define MCQ_NEEDS_CONS 0xFE   // table entry of a triplet with an unknown base: resolved per query
+
+// triplet -> slot per site for triplets without unknown bases (query independent); 128 entries per
+// site, 125 = "no state" -> MCQ_NOSLOT.  Rows are padded to a multiple of 32 sites.
+__global__ void __launch_bounds__(128) k_trip_table(const uint8_t *__restrict__ slot_of, uint8_t *__restrict__ trip_tab,
+                                                    int S) {
+  const int s = blockIdx.x, t = threadIdx.x;
+  uint8_t v = MCQ_NOSLOT;
+  if (s < S && t < 125) {
+    const int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
+    v = (d0 == 4 || d1 == 4 || d2 == 4) ? MCQ_NEEDS_CONS : slot_of[(size_t)s * 64 + d0 * 16 + d1 * 4 + d2];
+  }
+  trip_tab[(size_t)s * 128 + t] = v;
+}
 
 __global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_triplets,
                                                 const int *__restrict__ closest,
                                                 const int8_t *__restrict__ cons_nucls,
                                                 const uint8_t *__restrict__ slot_of,
-                                                uint8_t *__restrict__ G, int S, int L, int Lg) {
-  extern __shared__ __align__(16) uint8_t tile[];   // [32][Lg + 16]: row stride = 16 mod 128 -> 4-way at worst
+                                                const uint8_t *__restrict__ trip_tab,
+                                                uint32_t *__restrict__ G, int S, int L, int Lg) {
+  extern __shared__ uint32_t tile[];                // [32][Lg/4 + 1] words: odd stride, conflict-free both ways
+  __shared__ __align__(16) unsigned s_off[1024];    // row offset (ref*S) of the state at each PHYSICAL position
+  __shared__ __align__(16) uint8_t s_tab[32][128];  // the block's 32 rows of trip_tab
   const int q = blockIdx.y;
   const int s0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nj = Lg >> 6, stride = Lg + 16;
+  const int words = Lg >> 2, stride = words + 1;
+  const int lg2 = 31 - __clz(Lg >> 5);              // log2(2 * NJ)
   const int s = s0 + lane;
-  int c0 = 0, c1 = 0, c2 = 0;
-  if (s < S) {
-    const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
-    c0 = cn[0]; c1 = cn[1]; c2 = cn[2];
+  for (int pos = threadIdx.x; pos < Lg; pos += 256) {
+    const int r = g_state_of(pos, lg2);
+    s_off[pos] = r < L ? (unsigned)closest[(size_t)q * L + r] * (unsigned)S : 0xFFFFFFFFu;
   }
-  for (int r = warp; r < Lg; r += 8) {
-    uint8_t slot = MCQ_NOSLOT;
-    if (s < S && r < L) {
-      const int ref = closest[(size_t)q * L + r];
-      const int t = ref_triplets[(size_t)ref * S + s];
-      int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
-      if (d0 == 4) d0 = c0;
-      if (d1 == 4) d1 = c1;
-      if (d2 == 4) d2 = c2;
-      slot = slot_of[s * 64 + (d0 * 16 + d1 * 4 + d2)];
+  reinterpret_cast<uint4 *>(&s_tab[0][0])[threadIdx.x] =
+      reinterpret_cast<const uint4 *>(trip_tab + (size_t)s0 * 128)[threadIdx.x];
+  __syncthreads();
+  const uint8_t *tab = s_tab[lane];
+  const int8_t *col = ref_triplets + (s < S ? s : 0);
+  // read phase: a thread builds 4 consecutive physical bytes of its site's row per step; the 8 loads of
+  // two steps are issued before any is used
+  for (int m0 = warp; m0 < words; m0 += 16) {
+    int t[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int m = m0 + 8 * h;
+      uint4 o = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (m < words) o = reinterpret_cast<const uint4 *>(s_off)[m];
+      t[h][0] = o.x != 0xFFFFFFFFu ? (int)col[o.x] : 125;
+      t[h][1] = o.y != 0xFFFFFFFFu ? (int)col[o.y] : 125;
+      t[h][2] = o.z != 0xFFFFFFFFu ? (int)col[o.z] : 125;
+      t[h][3] = o.w != 0xFFFFFFFFu ? (int)col[o.w] : 125;
     }
-    tile[lane * stride + g_pos(r, nj)] = slot;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int m = m0 + 8 * h;
+      if (m >= words) break;
+      uint32_t word = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        unsigned slot = tab[t[h][i]];
+        if (slot == MCQ_NEEDS_CONS) {
+          // triplet_to_codon (amino_acids.c:50-66): unknown bases take the query's local consensus
+          const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
+          const int tt = t[h][i];
+          int d0 = tt / 25, d1 = (tt / 5) % 5, d2 = tt % 5;
+          if (d0 == 4) d0 = cn[0];
+          if (d1 == 4) d1 = cn[1];
+          if (d2 == 4) d2 = cn[2];
+          slot = slot_of[(size_t)s * 64 + (d0 * 16 + d1 * 4 + d2)];
+        }
+        word |= slot << (8 * i);
+      }
+      tile[lane * stride + m] = word;
+    }
   }
   __syncthreads();
   for (int ss = warp; ss < 32; ss += 8) {
     const int so = s0 + ss;
     if (so >= S) break;
-    const uint4 *src = reinterpret_cast<const uint4 *>(tile + ss * stride);
-    uint4 *dst = reinterpret_cast<uint4 *>(G + ((size_t)q * S + so) * Lg);
-    for (int i = lane; i < Lg / 16; i += 32) dst[i] = src[i];
+    uint32_t *dst = G + ((size_t)q * S + so) * words;
+    for (int i = lane; i < words; i += 32) dst[i] = tile[ss * stride + i];
   }
 }
 
 cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, const int8_t *cons_nucls,
-                              const uint8_t *slot_of, uint8_t *G, int Q, int S, int L, int Lg,
+                              const uint8_t *slot_of, uint8_t *trip_tab, uint8_t *G, int Q, int S, int L, int Lg,
                               cudaStream_t stream) {
-  const size_t smem = (size_t)32 * (Lg + 16);
+  const int sblocks = (S + 31) / 32;
+  k_trip_table<<<sblocks * 32, 128, 0, stream>>>(slot_of, trip_tab, S);
+  const size_t smem = (size_t)32 * (Lg / 4 + 1) * sizeof(uint32_t);
   for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
     int nq = Q - q0 < 65535 ? Q - q0 : 65535;
-    dim3 grid((S + 31) / 32, nq);
+    dim3 grid(sblocks, nq);
     k_gather<<<grid, 256, smem, stream>>>(ref_triplets, closest + (size_t)q0 * L,
-                                          cons_nucls + (size_t)q0 * 3 * S, slot_of,
-                                          G + (size_t)q0 * S * Lg, S, L, Lg);
+                                          cons_nucls + (size_t)q0 * 3 * S, slot_of, trip_tab,
+                                          reinterpret_cast<uint32_t *>(G + (size_t)q0 * S * Lg), S, L, Lg);
   }
   return cudaGetLastError();
 }

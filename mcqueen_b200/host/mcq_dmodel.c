@@ -647,6 +647,8 @@ int main(int argc, char **argv)
   fclose(priors_file);
 
   const double T0 = no_anneal ? 1 : 500;
+  struct timespec ts0, ts1;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
   time_t t_start = time(NULL);
   int hours_passed = 1, sample_i = 1, chain_i;
   for(chain_i = 0; chain_i < chain_length; chain_i++, sample_i++) {
@@ -706,6 +708,12 @@ int main(int argc, char **argv)
          "window_coeff_accept: %i window_coeff_reject: %i\nmut_accept: %i mut_reject: %i\n",
          c.rec_acc, c.rec_rej, c.sel_acc, c.sel_rej, c.merge_acc, c.merge_rej, c.split_acc, c.split_rej,
          c.grow_acc, c.grow_rej, c.coeff_acc, c.coeff_rej, c.mut_acc, c.mut_rej);
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
+  {
+    double sec = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
+    int done = chain_i < chain_length ? chain_i + 1 : chain_i;
+    printf("MCMC loop: %d steps in %.6f s = %.3f steps/s\n", done, sec, done / sec);
+  }
   printf("final log-likelihood: %.10f\n", c.llk);
   printf("time taken: %.2f\n", difftime(time(NULL), t_start));
 
