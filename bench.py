@@ -79,6 +79,7 @@ def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
     ctypes.CDLL("libc.so.6").srandom(SEED & 0x7fffffff)
     closest = api.closest_batch(refs, qs, L, device=device_index)
     t2 = time.time()
+    ham_ms, sel_ms = api.closest_last_timing()
     cons_q = consensus_of_closest_torch(gen.base_codes(refs), closest, f"cuda:{device_index}")
     p = prep.build_problem(refs, qs, hla, closest, cons_q=cons_q)
     prep.random_parameters(p, seed=1)
@@ -86,6 +87,14 @@ def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
     log(f"[bench] data {t1 - t0:.1f}s  closest-L(GPU) {t2 - t1:.1f}s  prep {t3 - t2:.1f}s  "
         f"Q={p.Q} S={p.S} L={p.L} N={p.N} H={p.H}")
     p.closest_seconds = t2 - t1
+    nb = refs.shape[1]
+    p.closest_stats = {
+        "shape": f"{refs.shape[0]} refs x {qs.shape[0]} queries x {nb} nt, L={L} (BASELINE config 3 when the workload is C4)",
+        "hamming_kernel_ms": ham_ms, "select_kernels_ms": sel_ms, "wall_seconds_incl_transfers_and_tie_shuffle": t2 - t1,
+        "nt_compares_per_s": refs.shape[0] * qs.shape[0] * nb / (ham_ms * 1e-3) if ham_ms > 0 else None,
+        # one 64-bit POPC word per 64 nt per pair: B200 issues 16 POPC.32 lanes/clk/SM
+        "popc_word_ops_per_s": refs.shape[0] * qs.shape[0] * ((nb + 63) // 64) / (ham_ms * 1e-3) if ham_ms > 0 else None,
+        "queries_per_s": qs.shape[0] / (t2 - t1)}
     return p
 
 
@@ -177,7 +186,7 @@ def write_ref_problem(p, path, nq):
     return nq
 
 
-def run_ref_bench(p, threads, seconds, path=None):
+def run_ref_bench(p, threads, seconds, path=None, total_queries=None):
     """Times the reference on a bounded sample; returns (cells/s, description dict)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
     if not os.path.exists(exe):
@@ -199,7 +208,7 @@ def run_ref_bench(p, threads, seconds, path=None):
     if own:
         os.unlink(path)
     desc = dict(kind="reference", cores=threads, value=res["cells_per_s"], unit=UNIT,
-                sample=f"{nq} of {p.Q} queries x {reps} repeats ({res['seconds']:.1f} s): "
+                sample=f"{nq} of {total_queries or p.Q} queries x {reps} repeats ({res['seconds']:.1f} s): "
                        f"create_codon_to_codon_HLA + initialise_F_numerical_recipes + llk per query, "
                        f"reference objects built -O3 (oracle/Makefile), {threads} host threads over query shards")
     return res["cells_per_s"], desc
@@ -284,7 +293,7 @@ def main():
         desc = None
         per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
         for i in range(args.warmup + args.steps):
-            v, desc = run_ref_bench(p, ncpu, per_step, path)
+            v, desc = run_ref_bench(p, ncpu, per_step, path, total_queries=Qtot)
             if v is None:
                 print(json.dumps({"impl": "reference", "unavailable": desc["error"]}))
                 return 0
@@ -427,7 +436,7 @@ def main():
         ctx.propose(api.PROP_REV, w0, w1, value0=1.1)
         ctx.accept()
         extras["window_accept_ms"] = ctx.last_timing()[0]
-        extras["closest_L_seconds_setup"] = p.closest_seconds
+        extras["closest_L"] = p.closest_stats
         ctx.enable_timing(0)
 
     # ---- gather over ranks (max time)

@@ -224,6 +224,9 @@ int mcq_codon_class(int c1, int c2);
 int mcq_closest_batch(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
                       const char *query_seqs, size_t query_stride, int num_query,
                       int num_bases, int closest_n, int skip_first, int *closest_refs /*[Q][L]*/);
+/* Device time (CUDA events) of the distance kernel and of the two selection kernels in the last
+ * mcq_closest_batch / mcq_hamming_batch call of the calling thread. */
+int mcq_closest_last_timing(float *hamming_ms, float *select_ms);
 /* Hamming distances only (values as closest_seqs.c:17-48), hamming[Q][N]. */
 int mcq_hamming_batch(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
                       const char *query_seqs, size_t query_stride, int num_query,

@@ -126,6 +126,13 @@ def closest_batch(ref_seqs, query_seqs, closest_n, skip_first=False, device=0):
     return out
 
 
+def closest_last_timing():
+    """(distance kernel ms, selection kernels ms) of the last closest_batch / hamming_batch call."""
+    a, b = C.c_float(), C.c_float()
+    check(_lib.load().mcq_closest_last_timing(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 # --------------------------------------------------------------------------------------------
 # batched context
 # --------------------------------------------------------------------------------------------

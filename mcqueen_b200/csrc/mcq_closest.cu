@@ -272,6 +272,27 @@ __global__ void __launch_bounds__(512) k_select_fill(const V *__restrict__ D, in
 // ------------------------------------------------------------------------------------------
 namespace {
 
+// device times of the last batched call on this thread (mcq_closest_last_timing)
+thread_local float g_ms_hamming = 0.f, g_ms_select = 0.f;
+
+struct EventTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t st;
+  float *out;
+  EventTimer(cudaStream_t s, float *o) : st(s), out(o) {
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+  }
+  ~EventTimer() {
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *out += ms;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  }
+};
+
 struct DevBuf {
   void *p = nullptr;
   ~DevBuf() { if (p) cudaFree(p); }
@@ -330,8 +351,11 @@ int select_rows(const V *D, int Q, int N, int n, int skip_first, int L, int *clo
   CK(cudaMalloc(&dT.p, (size_t)Q * sizeof(unsigned)));
   CK(cudaMalloc(&dlt.p, (size_t)Q * sizeof(int)));
   CK(cudaMalloc(&deq.p, (size_t)Q * sizeof(int)));
-  k_select_count<V><<<Q, 512, 0, st>>>(D, N, n, dT.as<unsigned>(), dlt.as<int>(), deq.as<int>());
-  CK(cudaGetLastError());
+  {
+    EventTimer t(st, &g_ms_select);
+    k_select_count<V><<<Q, 512, 0, st>>>(D, N, n, dT.as<unsigned>(), dlt.as<int>(), deq.as<int>());
+    CK(cudaGetLastError());
+  }
   std::vector<int> n_lt(Q), n_eq(Q);
   std::vector<unsigned> Tk(Q);
   CK(cudaMemcpyAsync(n_lt.data(), dlt.p, (size_t)Q * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -350,9 +374,12 @@ int select_rows(const V *D, int Q, int N, int n, int skip_first, int L, int *clo
   CK(cudaMemcpyAsync(doff.p, off.data(), (size_t)(Q + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   const size_t smem = (size_t)cap2 * sizeof(u64);
   CK(cudaFuncSetAttribute(k_select_fill<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_select_fill<V><<<Q, 512, smem, st>>>(D, N, cap, dT.as<unsigned>(), doff.as<long long>(), dlti.as<int>(),
-                                         dltk.as<unsigned>(), dpool.as<int>());
-  CK(cudaGetLastError());
+  {
+    EventTimer t(st, &g_ms_select);
+    k_select_fill<V><<<Q, 512, smem, st>>>(D, N, cap, dT.as<unsigned>(), doff.as<long long>(), dlti.as<int>(),
+                                           dltk.as<unsigned>(), dpool.as<int>());
+    CK(cudaGetLastError());
+  }
   std::vector<int> lti((size_t)Q * cap), pool((size_t)std::max<long long>(off[Q], 1));
   std::vector<unsigned> ltk((size_t)Q * cap);
   CK(cudaMemcpyAsync(lti.data(), dlti.p, lti.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -397,12 +424,22 @@ int distances(int device, const char *ref_seqs, size_t ref_stride, int N, const 
   if (pack_to_device(ref_seqs, ref_stride, N, nbases, W, false, npad, refp, sg.s)) return 1;
   if (pack_to_device(query_seqs, query_stride, Q, nbases, W, true, 0, qryp, sg.s)) return 1;
   CK(cudaMalloc(&D.p, (size_t)Q * N * sizeof(uint16_t)));
-  if (hamming_device(refp, npad, N, qryp, Q, W, D.as<uint16_t>(), sg.s)) return 1;
+  g_ms_hamming = 0.f; g_ms_select = 0.f;
+  {
+    EventTimer t(sg.s, &g_ms_hamming);
+    if (hamming_device(refp, npad, N, qryp, Q, W, D.as<uint16_t>(), sg.s)) return 1;
+  }
   CK(cudaStreamSynchronize(sg.s));
   return 0;
 }
 
 }  // namespace
+
+extern "C" int mcq_closest_last_timing(float *hamming_ms, float *select_ms) {
+  if (hamming_ms) *hamming_ms = g_ms_hamming;
+  if (select_ms) *select_ms = g_ms_select;
+  return 0;
+}
 
 extern "C" int mcq_hamming_batch(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
                                  const char *query_seqs, size_t query_stride, int num_query,
