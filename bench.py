@@ -278,7 +278,7 @@ def main():
     config = {"workload": f"{args.workload}: synthetic {Qtot} queries x L={L} x {S} codons, N={N} refs, H={H} HLA "
                           f"types; full likelihood evaluation (emission + forward fill + llk)",
               "queries": Qtot, "sites": S, "closest_n": L, "refs": N, "hla_types": H,
-              "sharding": f"queries/{world}", "cache": "inputs+outputs per step (>20 GB at C4) exceed L2; no flush"}
+              "sharding": f"queries/{world}", "exchange": os.environ.get("MCQ_BENCH_COMM", "peer") if world > 1 else "none", "cache": "inputs+outputs per step (>20 GB at C4) exceed L2; no flush"}
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -326,7 +326,12 @@ def main():
     q0, q1 = Qtot * rank // world, Qtot * (rank + 1) // world
     p = build_shard(args.workload, q0, q1, dev)
     ctx = api.Context.from_problem(p, device=dev)
-    if world > 1 and not os.environ.get("MCQ_BENCH_NO_COMM"):
+    comm_kind = os.environ.get("MCQ_BENCH_COMM", "peer") if world > 1 else "none"
+    if comm_kind == "peer":       # shard totals exchanged by NVLink peer stores inside the reduction kernel
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_handle())
+        ctx.attach_peers(world, rank, handles)
+    elif comm_kind == "nccl":     # one ncclAllReduce of one double
         ids = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.attach_comm(world, rank, ids[0])

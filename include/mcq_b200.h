@@ -208,7 +208,14 @@ int mcq_host_register(void *ptr, size_t bytes);
 int mcq_host_unregister(void *ptr);
 
 /* ---- multi-GPU: queries are sharded over ranks, one scalar is exchanged ---------------- */
-/* 128-byte NCCL unique id, created on rank 0 and passed to the others by the launcher. */
+/* (a) NVLink peer exchange (preferred on one NVSwitch box): each rank exports a 64-byte CUDA IPC
+ * handle of its mailbox, the launcher gathers them, every rank attaches all of them; the shard totals
+ * are then exchanged by peer stores inside the reduction kernel and added in rank order.
+ * `handles` is [nranks][64], entry `rank` may be anything. At most 16 ranks. */
+int mcq_ctx_peer_handle(mcq_ctx *ctx, unsigned char handle[64]);
+int mcq_ctx_attach_peers(mcq_ctx *ctx, int nranks, int rank, const unsigned char *handles);
+/* (b) NCCL all-reduce of the one double.
+ * 128-byte NCCL unique id, created on rank 0 and passed to the others by the launcher. */
 int mcq_comm_unique_id(unsigned char id[128]);
 int mcq_ctx_attach_comm(mcq_ctx *ctx, int nranks, int rank, const unsigned char id[128]);
 

@@ -67,6 +67,8 @@ SYMBOLS = {
     "mcq_ctx_synchronize": (C.c_int, [_V]),
     "mcq_host_register": (C.c_int, [_V, C.c_size_t]),
     "mcq_host_unregister": (C.c_int, [_V]),
+    "mcq_ctx_peer_handle": (C.c_int, [_V, _V]),
+    "mcq_ctx_attach_peers": (C.c_int, [_V, C.c_int, C.c_int, _V]),
     "mcq_comm_unique_id": (C.c_int, [_V]),
     "mcq_ctx_attach_comm": (C.c_int, [_V, C.c_int, C.c_int, _V]),
     "mcq_codon_class": (C.c_int, [C.c_int, C.c_int]),

@@ -282,6 +282,16 @@ class Context:
         check(self.lib.mcq_ctx_get_params(self._h, C.byref(mu), _vp(R), _vp(om), _vp(ro), _vp(esc), _vp(rev)))
         return dict(mu=mu.value, R=R, omega=om, rate_out=ro, esc=esc, rev=rev)
 
+    def peer_handle(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        check(self.lib.mcq_ctx_peer_handle(self._h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def attach_peers(self, nranks, rank, handles):
+        """handles: list of nranks 64-byte IPC handles (one per rank, from peer_handle())."""
+        flat = (C.c_ubyte * (64 * nranks)).from_buffer_copy(b"".join(handles))
+        check(self.lib.mcq_ctx_attach_peers(self._h, nranks, rank, C.cast(flat, C.c_void_p)))
+
     def attach_comm(self, nranks, rank, unique_id: bytes):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         check(self.lib.mcq_ctx_attach_comm(self._h, nranks, rank, C.cast(buf, C.c_void_p)))

@@ -128,6 +128,17 @@ struct mcq_ctx {
 
   ncclComm_t comm = nullptr;
   int nranks = 1;
+  // NVLink peer mailboxes (mcq_ctx_attach_peers)
+  struct {
+    double *value[16];
+    unsigned long long *seq[16];
+    int nranks, rank;
+  } box{};
+  void *mailbox = nullptr;          // this rank's own mailbox allocation
+  void *peer_map[16] = {nullptr};   // IPC mappings of the peers' mailboxes
+  bool have_peers = false;
+  unsigned long long step = 0;
+  int *d_err = nullptr, *h_err = nullptr;
   double logBIG = 0.0;
 };
 
@@ -229,6 +240,10 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   ALLOC(c->m.esc, H * S); ALLOC(c->m.rev, S); ALLOC(c->m.prior, 64);
   ALLOC(c->llk_cur, Q); ALLOC(c->llk_prop, Q); ALLOC(c->d_sum, 1);
   CK(cudaMallocHost((void **)&c->h_sum, sizeof(double)));
+  CK(cudaMallocHost((void **)&c->h_err, sizeof(int)));
+  *c->h_err = 0;
+  ALLOC(c->d_err, 1);
+  CK(cudaMemset(c->d_err, 0, sizeof(int)));
   c->pending.kind = -1;
   *out = c;
   return 0;
@@ -245,6 +260,11 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
+  if (c->h_err) cudaFreeHost(c->h_err);
+  if (c->d_err) cudaFree(c->d_err);
+  for (int r = 0; r < 16; r++)
+    if (c->peer_map[r]) cudaIpcCloseMemHandle(c->peer_map[r]);
+  if (c->mailbox) cudaFree(c->mailbox);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -529,6 +549,20 @@ static int run_backward(mcq_ctx *c, int update, bool sparse, int hla) {
 
 // total over the shard (+ all ranks), brought to the host
 static int reduce_llk(mcq_ctx *c, const double *per_query, double *out) {
+  if (c->have_peers) {
+    // shard total + NVLink mailbox exchange in one kernel
+    {
+      KScope ks(c, MCQ_K_SUM);
+      c->step++;
+      CK(mcq_launch_sum_exchange(per_query, c->d.num_query, c->d_sum, &c->box, c->step, c->d_err, c->stream));
+    }
+    CK(cudaMemcpyAsync(c->h_sum, c->d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    REQUIRE(*c->h_err == 0, "peer exchange timed out: a rank did not reach the same evaluation");
+    if (out) *out = *c->h_sum;
+    return 0;
+  }
   {
     KScope ks(c, MCQ_K_SUM);
     CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->stream));
@@ -761,6 +795,51 @@ extern "C" int mcq_ctx_get_query_llk(mcq_ctx *c, int proposed, double *out) {
 // ------------------------------------------------------------------------------------------
 // multi-GPU
 // ------------------------------------------------------------------------------------------
+// ---- NVLink peer mailboxes ----------------------------------------------------------------
+// layout of one mailbox: double value[2][16]; unsigned long long seq[2][16]
+static const size_t kMailboxBytes = 2 * 16 * (sizeof(double) + sizeof(unsigned long long));
+
+extern "C" int mcq_ctx_peer_handle(mcq_ctx *c, unsigned char handle[64]) {
+  REQUIRE(c && handle, "null argument");
+  CK(cudaSetDevice(c->d.device));
+  if (!c->mailbox) {
+    CK(cudaMalloc(&c->mailbox, kMailboxBytes));
+    CK(cudaMemset(c->mailbox, 0, kMailboxBytes));
+    CK(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->mailbox));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle, &h, 64);
+  return 0;
+}
+
+extern "C" int mcq_ctx_attach_peers(mcq_ctx *c, int nranks, int rank, const unsigned char *handles) {
+  REQUIRE(c && handles, "null argument");
+  REQUIRE(nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks, "rank / nranks (at most 16 ranks on one box)");
+  REQUIRE(c->mailbox, "call mcq_ctx_peer_handle first");
+  CK(cudaSetDevice(c->d.device));
+  for (int r = 0; r < nranks; r++) {
+    char *base;
+    if (r == rank) base = (char *)c->mailbox;
+    else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + (size_t)r * 64, 64);
+      CK(cudaIpcOpenMemHandle(&c->peer_map[r], h, cudaIpcMemLazyEnablePeerAccess));
+      base = (char *)c->peer_map[r];
+    }
+    // every rank indexes a mailbox as [slot][R] with R = nranks
+    c->box.value[r] = (double *)base;
+    c->box.seq[r] = (unsigned long long *)(base + 2 * 16 * sizeof(double));
+  }
+  c->box.nranks = nranks;
+  c->box.rank = rank;
+  c->nranks = nranks;
+  c->have_peers = true;
+  c->step = 0;
+  return 0;
+}
+
 extern "C" int mcq_comm_unique_id(unsigned char id[128]) {
   if (nccl_load()) return 1;
   ncclUniqueId u;

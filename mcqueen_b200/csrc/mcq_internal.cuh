@@ -124,5 +124,8 @@ cudaError_t mcq_launch_commit_cons(const McqStatic &st, const double *ec_t, cons
                                    double *ac, int start, int end, cudaStream_t stream);
 cudaError_t mcq_launch_commit_params(const McqStatic &st, McqModel m, McqOverride ov, cudaStream_t stream);
 cudaError_t mcq_launch_sum(const double *v, int n, double *out, cudaStream_t stream);
+// `box` points at a host copy of the PeerBox struct of mcq_kernels.cu (16 value + 16 seq pointers, nranks, rank)
+cudaError_t mcq_launch_sum_exchange(const double *v, int n, double *out, const void *box, unsigned long long step,
+                                    int *err, cudaStream_t stream);
 
 #endif

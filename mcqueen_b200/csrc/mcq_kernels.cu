@@ -887,6 +887,65 @@ __global__ void __launch_bounds__(1024) k_sum(const double *__restrict__ v, int 
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// ------------------------------------------------------------------------------------------
+// K6c: the shard total followed, in the same kernel, by the cross-GPU exchange over NVLink peer
+// memory.  Every rank owns a mailbox {double value[2][R]; u64 seq[2][R]} that all peers have mapped
+// (CUDA IPC).  Lane r of warp 0 stores this rank's total and then the step number into peer r's
+// mailbox (slot = step parity, entry = this rank), waits for peer r's entry in its own mailbox, and
+// lane 0 adds the R totals in rank order - the same bits on every rank.  One step of latency over
+// NVSwitch instead of a collective launch.  A peer that never arrives trips a clock-based timeout.
+// ------------------------------------------------------------------------------------------
+struct PeerBox {
+  double *value[16];               // value[r] = peer r's mailbox values  [2][R]
+  unsigned long long *seq[16];     // seq[r]   = peer r's mailbox flags   [2][R]
+  int nranks, rank;
+};
+
+__global__ void __launch_bounds__(1024) k_sum_exchange(const double *__restrict__ v, int n, double *__restrict__ out,
+                                                       PeerBox box, unsigned long long step, int *__restrict__ err) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += v[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x >= 32) return;
+  const int R = box.nranks, me = box.rank, lane = threadIdx.x;
+  const int slot = (int)(step & 1);
+  double got = 0.0;
+  bool ok = true;
+  if (lane < R) {
+    // publish: value first, then the step number (system-scope release)
+    volatile double *pv = box.value[lane] + slot * R + me;
+    volatile unsigned long long *ps = box.seq[lane] + slot * R + me;
+    *pv = sh[0];
+    __threadfence_system();
+    *ps = step;
+    // collect peer `lane`'s entry from this rank's own mailbox
+    volatile unsigned long long *ms = box.seq[me] + slot * R + lane;
+    volatile double *mv = box.value[me] + slot * R + lane;
+    const long long t0 = clock64();
+    while (*ms != step) {
+      if (clock64() - t0 > 20000000000LL) { ok = false; break; }   // ~10 s
+    }
+    __threadfence_system();
+    got = *mv;
+  }
+  if (!__all_sync(0xffffffffu, ok)) { if (lane == 0) *err = 1; return; }
+  double total = 0.0;
+  for (int r = 0; r < R; r++) total += __shfl_sync(0xffffffffu, got, r);   // rank order on every rank
+  if (lane == 0) *out = total;
+}
+
+cudaError_t mcq_launch_sum_exchange(const double *v, int n, double *out, const void *box, unsigned long long step,
+                                    int *err, cudaStream_t stream) {
+  k_sum_exchange<<<1, 1024, 0, stream>>>(v, n, out, *static_cast<const PeerBox *>(box), step, err);
+  return cudaGetLastError();
+}
+
 cudaError_t mcq_launch_sum(const double *v, int n, double *out, cudaStream_t stream) {
   k_sum<<<1, 1024, 0, stream>>>(v, n, out);
   return cudaGetLastError();

@@ -349,7 +349,7 @@ static void move_mutation(Chain *c, double temperature)
 static int chain_length = 50000, sample_rate = 100, closest_n = 100, runtime_hours = 0;
 static const char *ref_path, *query_path, *out_dir, *hla_path, *cons_path;
 static bool separate_reference_set = true, no_hla = false, no_rev = false, no_rec = false, no_anneal = false;
-static bool opt_sample_prior = false, opt_sparse = false, runtime_set = false, states_set = false;
+static bool opt_sample_prior = false, opt_sparse = false, runtime_set = false, states_set = false, opt_nccl = false;
 static int opt_omega_prior = MCQ_PRIOR_EXPONENTIAL, opt_esc_prior = MCQ_PRIOR_LOG_NORMAL;
 static int opt_rev_prior = MCQ_PRIOR_LOG_NORMAL, opt_device = -1;
 static long opt_seed = -1, opt_gsl_seed = -1;
@@ -363,7 +363,7 @@ static void usage(void)
           "  -q self-reference mode  -i no HLA inference  -j no reversion inference  -o no recombination\n"
           "  -v/-e/-w omega prior gamma/log-normal/uniform   -g/-k/-f escape prior gamma/normal/flat\n"
           "  -a/-d/-u reversion prior gamma/normal/flat   -b sample the prior   -z no simulated annealing\n"
-          "  --seed N --gsl_seed N (default: clock)  --device D  --sparse_esc  --trace FILE\n");
+          "  --seed N --gsl_seed N (default: clock)  --device D  --sparse_esc  --trace FILE  --nccl\n");
   exit(EXIT_FAILURE);
 }
 
@@ -382,7 +382,8 @@ static void parse(int argc, char **argv)
       {"HLA_coeff_rev_uniform", no_argument, NULL, 'u'}, {"sample_prior", no_argument, NULL, 'b'},
       {"no_simulated_annealing", no_argument, NULL, 'z'}, {"seed", required_argument, NULL, 1001},
       {"gsl_seed", required_argument, NULL, 1002}, {"device", required_argument, NULL, 1003},
-      {"sparse_esc", no_argument, NULL, 1004}, {"trace", required_argument, NULL, 1005}, {NULL, 0, NULL, 0}};
+      {"sparse_esc", no_argument, NULL, 1004}, {"trace", required_argument, NULL, 1005},
+      {"nccl", no_argument, NULL, 1006}, {NULL, 0, NULL, 0}};
   int o;
   while((o = getopt_long(argc, argv, "H:n:s:t:c:l:qijovewgkfadubz", lo, NULL)) != -1) {
     switch(o) {
@@ -412,6 +413,7 @@ static void parse(int argc, char **argv)
       case 1003: opt_device = atoi(optarg); break;
       case 1004: opt_sparse = true; break;
       case 1005: trace_path = optarg; break;
+      case 1006: opt_nccl = true; break;
       default: usage();
     }
   }
@@ -427,32 +429,40 @@ static int env_int(const char *name, int dflt)
   return v ? atoi(v) : dflt;
 }
 
-/* NCCL id hand-over between the ranks of one box: rank 0 writes it to a file, the others wait for it */
-static void exchange_unique_id(int rank, unsigned char id[128])
+/* Hand-over of small blobs between the ranks of one box through files under /tmp: rank r writes
+ * <tag>_<r>, everyone polls for the files it needs.  Used for the 64-byte CUDA IPC handles of the peer
+ * mailboxes (default) or the 128-byte NCCL id (--nccl). */
+static void blob_path(char *path, size_t n, const char *tag, int r)
+{
+  snprintf(path, n, "/tmp/mcq_%s_%s_%s_%d", tag, getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0",
+           getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : "run", r);
+}
+
+static void blob_put(const char *tag, int r, const unsigned char *data, size_t len)
+{
+  char path[PATH_MAX], tmp[PATH_MAX + 8];
+  blob_path(path, sizeof(path), tag, r);
+  snprintf(tmp, sizeof(tmp), "%s.tmp", path);
+  FILE *f = fopen(tmp, "wb");
+  if(!f || fwrite(data, 1, len, f) != len) mcq_die("cannot write %s", tmp);
+  fclose(f);
+  rename(tmp, path);
+}
+
+static void blob_get(const char *tag, int r, unsigned char *data, size_t len)
 {
   char path[PATH_MAX];
-  snprintf(path, sizeof(path), "/tmp/mcq_nccl_id_%s_%s", getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0",
-           getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : "run");
-  if(rank == 0) {
-    CHECK(mcq_comm_unique_id(id));
-    char tmp[PATH_MAX + 8];
-    snprintf(tmp, sizeof(tmp), "%s.tmp", path);
-    FILE *f = fopen(tmp, "wb");
-    if(!f || fwrite(id, 1, 128, f) != 128) mcq_die("cannot write %s", tmp);
-    fclose(f);
-    rename(tmp, path);
-  } else {
-    for(int tries = 0; tries < 6000; tries++) {
-      FILE *f = fopen(path, "rb");
-      if(f) {
-        size_t n = fread(id, 1, 128, f);
-        fclose(f);
-        if(n == 128) return;
-      }
-      usleep(10000);
+  blob_path(path, sizeof(path), tag, r);
+  for(int tries = 0; tries < 12000; tries++) {
+    FILE *f = fopen(path, "rb");
+    if(f) {
+      size_t n = fread(data, 1, len, f);
+      fclose(f);
+      if(n == len) return;
     }
-    mcq_die("timed out waiting for %s", path);
+    usleep(10000);
   }
+  mcq_die("timed out waiting for %s", path);
 }
 
 int main(int argc, char **argv)
@@ -613,9 +623,18 @@ int main(int argc, char **argv)
   mcq_params prm = {c.mu, kappa, phi, prior, c.R, c.omega, rate_out, c.esc, c.rev};
   CHECK(mcq_ctx_set_params(c.ctx, &prm));
   if(opt_sparse) CHECK(mcq_ctx_set_option(c.ctx, MCQ_OPT_SPARSE_ESC, 1));
-  if(world > 1) {
+  if(world > 1 && !opt_nccl) {
+    /* shard totals are exchanged by NVLink peer stores inside the reduction kernel */
+    unsigned char *handles = malloc((size_t)64 * world);
+    CHECK(mcq_ctx_peer_handle(c.ctx, handles + (size_t)64 * rank));
+    blob_put("peer", rank, handles + (size_t)64 * rank, 64);
+    for(int r = 0; r < world; r++) if(r != rank) blob_get("peer", r, handles + (size_t)64 * r, 64);
+    CHECK(mcq_ctx_attach_peers(c.ctx, world, rank, handles));
+    free(handles);
+  } else if(world > 1) {
     unsigned char id[128];
-    exchange_unique_id(rank, id);
+    if(rank == 0) { CHECK(mcq_comm_unique_id(id)); blob_put("nccl", 0, id, 128); }
+    else blob_get("nccl", 0, id, 128);
     CHECK(mcq_ctx_attach_comm(c.ctx, world, rank, id));
   }
   if(!c.sample_prior) {

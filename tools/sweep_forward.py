@@ -31,6 +31,17 @@ def main():
         for _ in range(5):
             ctx.backward_fill()
         b_ms, b_n = ctx.kernel_time(api.K_BACKWARD, reset=True)
+        ctx.enable_timing(0)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            ctx.full_llk(True)
+        step_ms = (time.perf_counter() - t0) / 50 * 1e3
+        ctx.enable_timing(2)
+        ctx.kernel_time(api.K_EMISSION, reset=True)
+        ctx.full_llk(True)
+        e_ms = ctx.kernel_time(api.K_EMISSION)[0]
+        print(f"   step (emission+forward+sum+D2H, wall) {step_ms:.3f} ms; emission kernels {e_ms:.3f} ms")
         fb = (9 + 520 / L) * Q * S * L
         print(f"Q={Q:6d} forward {f_ms / f_n:7.3f} ms  {fb / (f_ms / f_n) / 1e6:7.0f} GB/s   "
               f"backward {b_ms / b_n:7.3f} ms {fb / (b_ms / b_n) / 1e6:7.0f} GB/s", flush=True)
