@@ -124,7 +124,6 @@ struct mcq_ctx {
   int8_t *st_trip = nullptr, *st_cons = nullptr;
   int *st_closest = nullptr;
   uint8_t *st_slot_of = nullptr, *st_trip_tab = nullptr;
-  std::vector<uint8_t> st_bits;
 
   ncclComm_t comm = nullptr;
   int nranks = 1;
@@ -376,14 +375,6 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     aoff_h[s + 1] = aoff_h[s] + k;
     toff_h[s + 1] = toff_h[s] + 64 * k;
   }
-  {
-    int lo = 0, hi = 0;   // branch-free range check (vectorises)
-    for (size_t i = 0; i < (size_t)Q * L; i++) {
-      lo = closest_refs[i] < lo ? closest_refs[i] : lo;
-      hi = closest_refs[i] > hi ? closest_refs[i] : hi;
-    }
-    REQUIRE(lo >= 0 && hi < N, "closest_refs entry out of range");
-  }
 
   if (!c->have_static) {
     c->aoff_h = aoff_h; c->toff_h = toff_h; c->ncodon_h = ncodon_h; c->cons_in_list_h = cons_in_list_h;
@@ -414,7 +405,6 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     const size_t zn[] = {c->TL, c->TL, (size_t)c->NA, (size_t)c->NA, qs, qs, qs, qs};
     for (int i = 0; i < 8; i++) CK(cudaMemsetAsync(zero[i], 0, (zn[i] ? zn[i] : 1) * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->Fn, 0, (size_t)Q * S * sizeof(int), c->stream));
-    c->st_bits.resize((size_t)Q * H);
     std::vector<int> site_of((size_t)c->NA);
     for (int s = 0; s < S; s++)
       for (int k = aoff_h[s]; k < aoff_h[s + 1]; k++) site_of[k] = s;
@@ -428,19 +418,24 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
                 cons_codon_h == c->cons_codon_h,
             "re-upload changes the per-site codon lists: create a new context");
   }
-  CK(cudaMemcpyAsync(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->query_codon, query_codons, (size_t)Q * S, cudaMemcpyHostToDevice, c->stream));
-  for (size_t i = 0; i < c->st_bits.size(); i++) c->st_bits[i] = (hla_types[i] == '1');
-  CK(cudaMemcpyAsync(c->hla, c->st_bits.data(), c->st_bits.size(), cudaMemcpyHostToDevice, c->stream));
+  // the large inputs go first (DMA from the caller's buffers); the '0'/'1' characters of hla_types are
+  // turned into 0/1 and closest_refs is range-checked on the device
   CK(cudaMemcpyAsync(c->st_trip, ref_triplets, (size_t)N * S, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->st_cons, cons_query_nucls, (size_t)Q * 3 * S, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->st_closest, closest_refs, (size_t)Q * L * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->st_cons, cons_query_nucls, (size_t)Q * 3 * S, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->query_codon, query_codons, (size_t)Q * S, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->hla, hla_types, (size_t)Q * H, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
   {
     KScope ks(c, MCQ_K_GATHER);
-    CK(mcq_launch_gather(c->st_trip, c->st_closest, c->st_cons, c->st_slot_of, c->st_trip_tab, c->G, Q, S, L, c->Lg, c->stream));
+    CK(mcq_launch_gather(c->st_trip, c->st_closest, c->st_cons, c->st_slot_of, c->st_trip_tab, c->G, c->hla, Q, S, L,
+                         c->Lg, N, H, c->d_err, c->stream));
   }
+  CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
+  REQUIRE(*c->h_err == 0, "closest_refs entry out of range");
   c->have_static = true;
   c->have_state = false;
   c->has_pending = false;

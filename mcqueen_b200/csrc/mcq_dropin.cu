@@ -37,7 +37,7 @@ struct Scratch {
   cudaStream_t stream = nullptr;
   // device
   int8_t *trip = nullptr, *cons = nullptr;
-  int *closest = nullptr, *aoff = nullptr, *Fn = nullptr, *Tn = nullptr;
+  int *closest = nullptr, *aoff = nullptr, *Fn = nullptr, *Tn = nullptr, *d_err = nullptr;
   uint8_t *slot_of = nullptr, *trip_tab = nullptr, *G = nullptr;
   double *E = nullptr, *R = nullptr, *F = nullptr, *T = nullptr;
   // host staging
@@ -74,6 +74,7 @@ struct Scratch {
     DK(cudaMalloc((void **)&cons, (size_t)3 * S));
     DK(cudaMalloc((void **)&closest, (size_t)L * sizeof(int)));
     DK(cudaMalloc((void **)&aoff, (size_t)(S + 1) * sizeof(int)));
+    if (!d_err) DK(cudaMalloc((void **)&d_err, sizeof(int)));
     DK(cudaMalloc((void **)&Fn, (size_t)S * sizeof(int)));
     DK(cudaMalloc((void **)&Tn, (size_t)S * sizeof(int)));
     DK(cudaMalloc((void **)&slot_of, (size_t)S * 64));
@@ -119,7 +120,7 @@ struct Scratch {
     DK(cudaMemcpyAsync(cons, cons_nucls, (size_t)3 * S, cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(E, h_E.data(), h_E.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(R, Rh, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, stream));
-    DK(mcq_launch_gather(trip, closest, cons, slot_of, trip_tab, G, 1, S, L, Lg, stream));
+    DK(mcq_launch_gather(trip, closest, cons, slot_of, trip_tab, G, nullptr, 1, S, L, Lg, L, 1, d_err, stream));
   }
 
   // one column host[L][S] (stride S) -> device column

@@ -80,7 +80,8 @@ __device__ __forceinline__ int g_state_of(int pos, int lg2) {   // lg2 = log2(2*
 #define MCQ_NEEDS_CONS 0xFE   // table entry of a triplet with an unknown base: resolved per query
 
 // triplet -> slot per site for triplets without unknown bases (query independent); 128 entries per
-// site, 125 = "no state" -> MCQ_NOSLOT.  Rows are padded to a multiple of 32 sites.
+// site, 125 = "no state" -> MCQ_NOSLOT.  Stored per block of 32 sites as [128 triplets][32 sites] so that
+// k_gather can keep it in shared memory with the bank depending on the lane (= site) only.
 __global__ void __launch_bounds__(128) k_trip_table(const uint8_t *__restrict__ slot_of, uint8_t *__restrict__ trip_tab,
                                                     int S) {
   const int s = blockIdx.x, t = threadIdx.x;
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(128) k_trip_table(const uint8_t *__restrict__ 
     const int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
     v = (d0 == 4 || d1 == 4 || d2 == 4) ? MCQ_NEEDS_CONS : slot_of[(size_t)s * 64 + d0 * 16 + d1 * 4 + d2];
   }
-  trip_tab[(size_t)s * 128 + t] = v;
+  trip_tab[(size_t)(s >> 5) * 4096 + t * 32 + (s & 31)] = v;
 }
 
 __global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_triplets,
@@ -97,10 +98,11 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_t
                                                 const int8_t *__restrict__ cons_nucls,
                                                 const uint8_t *__restrict__ slot_of,
                                                 const uint8_t *__restrict__ trip_tab,
-                                                uint32_t *__restrict__ G, int S, int L, int Lg) {
+                                                uint32_t *__restrict__ G, int S, int L, int Lg, int N,
+                                                int *__restrict__ err) {
   extern __shared__ uint32_t tile[];                // [32][Lg/4 + 1] words: odd stride, conflict-free both ways
   __shared__ __align__(16) unsigned s_off[1024];    // row offset (ref*S) of the state at each PHYSICAL position
-  __shared__ __align__(16) uint8_t s_tab[32][128];  // the block's 32 rows of trip_tab
+  __shared__ uint32_t s_tab[128 * 32];              // [triplet][site of the block]: bank == lane, conflict-free
   const int q = blockIdx.y;
   const int s0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,12 +111,21 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_t
   const int s = s0 + lane;
   for (int pos = threadIdx.x; pos < Lg; pos += 256) {
     const int r = g_state_of(pos, lg2);
-    s_off[pos] = r < L ? (unsigned)closest[(size_t)q * L + r] * (unsigned)S : 0xFFFFFFFFu;
+    unsigned off = 0xFFFFFFFFu;
+    if (r < L) {
+      int ref = closest[(size_t)q * L + r];
+      if ((unsigned)ref >= (unsigned)N) { ref = 0; *err = 2; }   // reported by mcq_ctx_upload_static
+      off = (unsigned)ref * (unsigned)S;
+    }
+    s_off[pos] = off;
   }
-  reinterpret_cast<uint4 *>(&s_tab[0][0])[threadIdx.x] =
-      reinterpret_cast<const uint4 *>(trip_tab + (size_t)s0 * 128)[threadIdx.x];
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    const uint32_t w4 = reinterpret_cast<const uint32_t *>(trip_tab + (size_t)blockIdx.x * 4096)[i];
+    s_tab[4 * i + 0] = w4 & 0xFF; s_tab[4 * i + 1] = (w4 >> 8) & 0xFF;
+    s_tab[4 * i + 2] = (w4 >> 16) & 0xFF; s_tab[4 * i + 3] = w4 >> 24;
+  }
   __syncthreads();
-  const uint8_t *tab = s_tab[lane];
+  const uint32_t *tab = s_tab + lane;
   const int8_t *col = ref_triplets + (s < S ? s : 0);
   // read phase: a thread builds 4 consecutive physical bytes of its site's row per step; the 8 loads of
   // two steps are issued before any is used
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_t
       uint32_t word = 0;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        unsigned slot = tab[t[h][i]];
+        unsigned slot = tab[t[h][i] * 32];
         if (slot == MCQ_NEEDS_CONS) {
           // triplet_to_codon (amino_acids.c:50-66): unknown bases take the query's local consensus
           const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
@@ -162,10 +173,20 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_t
   }
 }
 
+// '0'/'1' characters (load_data.c:125-157) -> 0/1, in place
+__global__ void __launch_bounds__(256) k_hla_bits(uint8_t *hla, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) hla[i] = (hla[i] == '1');
+}
+
 cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, const int8_t *cons_nucls,
-                              const uint8_t *slot_of, uint8_t *trip_tab, uint8_t *G, int Q, int S, int L, int Lg,
-                              cudaStream_t stream) {
+                              const uint8_t *slot_of, uint8_t *trip_tab, uint8_t *G, uint8_t *hla_chars, int Q, int S,
+                              int L, int Lg, int N, int H, int *err, cudaStream_t stream) {
   const int sblocks = (S + 31) / 32;
+  if (hla_chars != nullptr) {
+    const size_t n = (size_t)Q * H;
+    k_hla_bits<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(hla_chars, n);
+  }
   k_trip_table<<<sblocks * 32, 128, 0, stream>>>(slot_of, trip_tab, S);
   const size_t smem = (size_t)32 * (Lg / 4 + 1) * sizeof(uint32_t);
   for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
@@ -173,7 +194,7 @@ cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, co
     dim3 grid(sblocks, nq);
     k_gather<<<grid, 256, smem, stream>>>(ref_triplets, closest + (size_t)q0 * L,
                                           cons_nucls + (size_t)q0 * 3 * S, slot_of, trip_tab,
-                                          reinterpret_cast<uint32_t *>(G + (size_t)q0 * S * Lg), S, L, Lg);
+                                          reinterpret_cast<uint32_t *>(G + (size_t)q0 * S * Lg), S, L, Lg, N, err);
   }
   return cudaGetLastError();
 }

@@ -206,3 +206,11 @@ def test_errors_are_loud(api):
     with pytest.raises(api._lib.McqError):
         ctx.init_state()                           # nothing uploaded
     ctx.close()
+    p = make_problem("toy")
+    bad = p.closest_refs.copy()
+    bad[3, 5] = p.N                                # one past the panel
+    ctx = api.Context(p.S, p.L, p.N, p.Q, p.H)
+    with pytest.raises(api._lib.McqError, match="closest_refs"):
+        ctx.upload_static(p.ref_triplets, bad, p.cons_query_nucls, p.query_codons, p.hla, p.consensus_codons,
+                          p.n_site_codons, p.site_codons)
+    ctx.close()
