@@ -51,21 +51,6 @@ def make_data(name):
     return synth.make_dataset(seed=SEED, **cfg)
 
 
-def consensus_of_closest_torch(ref_codes, closest, device):
-    """Per-query majority base over its closest references (amino_acids.c:118-141) - set-up
-    plumbing done with torch on the GPU because the numpy version takes minutes at C4 size."""
-    import torch
-    rc = torch.from_numpy(ref_codes).to(device)
-    out = np.empty((closest.shape[0], ref_codes.shape[1]), np.int8)
-    step = max(1, (256 << 20) // (closest.shape[1] * ref_codes.shape[1]))
-    for i in range(0, closest.shape[0], step):
-        idx = torch.from_numpy(closest[i:i + step].astype(np.int64)).to(device)
-        g = rc[idx]
-        counts = torch.stack([(g == b).sum(1) for b in range(4)], 1)
-        out[i:i + step] = counts.argmax(1).to(torch.int8).cpu().numpy()
-    return out
-
-
 def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
     """Problem restricted to queries q0..q1-1 (references are shared by every shard)."""
     from mcqueen_b200 import api
@@ -80,7 +65,7 @@ def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
     closest = api.closest_batch(refs, qs, L, device=device_index)
     t2 = time.time()
     ham_ms, sel_ms = api.closest_last_timing()
-    cons_q = consensus_of_closest_torch(gen.base_codes(refs), closest, f"cuda:{device_index}")
+    cons_q = api.consensus_batch(refs, closest, device=device_index)
     p = prep.build_problem(refs, qs, hla, closest, cons_q=cons_q)
     prep.random_parameters(p, seed=1)
     t3 = time.time()

@@ -231,6 +231,12 @@ int mcq_codon_class(int c1, int c2);
 int mcq_closest_batch(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
                       const char *query_seqs, size_t query_stride, int num_query,
                       int num_bases, int closest_n, int skip_first, int *closest_refs /*[Q][L]*/);
+/* Per-query consensus of the closest references (generate_consensus_subset over every query,
+ * dmodel.c:664-681 / amino_acids.c:118-141): cons_codes[Q][num_bases] receives base codes 0..3
+ * (T,C,A,G), i.e. cons_query_nucls.  Reference sequences must still carry their unknown bases. */
+int mcq_consensus_batch(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
+                        const int *closest_refs, int num_query, int closest_n, int num_bases,
+                        char *cons_codes);
 /* Device time (CUDA events) of the distance kernel and of the two selection kernels in the last
  * mcq_closest_batch / mcq_hamming_batch call of the calling thread. */
 int mcq_closest_last_timing(float *hamming_ms, float *select_ms);

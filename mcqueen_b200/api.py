@@ -126,6 +126,19 @@ def closest_batch(ref_seqs, query_seqs, closest_n, skip_first=False, device=0):
     return out
 
 
+def consensus_batch(ref_seqs, closest_refs, device=0):
+    """cons_query_nucls (Q, num_bases) int8 codes 0..3: per-query majority base over its closest references
+    (dmodel.c:664-681)."""
+    lib = _lib.load()
+    ref_seqs = _chars(ref_seqs, "ref_seqs")
+    closest_refs = _req(np.ascontiguousarray(closest_refs, np.int32), np.int32, "closest_refs")
+    N, nb = ref_seqs.shape
+    Q, L = closest_refs.shape
+    out = np.zeros((Q, nb), np.int8)
+    check(lib.mcq_consensus_batch(device, _vp(ref_seqs), nb, N, _vp(closest_refs), Q, L, nb, _vp(out)))
+    return out
+
+
 def closest_last_timing():
     """(distance kernel ms, selection kernels ms) of the last closest_batch / hamming_batch call."""
     a, b = C.c_float(), C.c_float()

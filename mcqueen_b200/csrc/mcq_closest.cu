@@ -470,6 +470,62 @@ extern "C" int mcq_closest_batch(int device, const char *ref_seqs, size_t ref_st
 }
 
 // ------------------------------------------------------------------------------------------
+// per-query consensus of the closest references (generate_consensus_subset, amino_acids.c:118-141,
+// as used by dmodel.c:664-681): majority base per position over the query's L references, ties to
+// the first of T,C,A,G, 'T' when no reference has a base there.  One thread per (query, position),
+// references walked in list order (reads coalesced along the position).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_consensus(const unsigned char *__restrict__ refs, size_t stride,
+                                                   const int *__restrict__ closest, int L, int nbases,
+                                                   signed char *__restrict__ out) {
+  const int q = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nbases) return;
+  const int *cl = closest + (size_t)q * L;
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (int r = 0; r < L; r++) {
+    const unsigned char ch = refs[(size_t)cl[r] * stride + i];
+    int code = 4;
+    if ((ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z')) code = base_code(ch);
+    c0 += (code == 0); c1 += (code == 1); c2 += (code == 2); c3 += (code == 3);
+  }
+  int best = 0, cnt = c0;
+  if (c1 > cnt) { best = 1; cnt = c1; }
+  if (c2 > cnt) { best = 2; cnt = c2; }
+  if (c3 > cnt) { best = 3; cnt = c3; }
+  out[(size_t)q * nbases + i] = (signed char)best;
+}
+
+extern "C" int mcq_consensus_batch(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
+                                   const int *closest_refs, int num_query, int closest_n, int num_bases,
+                                   char *cons_codes) {
+  REQUIRE(ref_seqs && closest_refs && cons_codes, "null argument");
+  REQUIRE(num_refs > 0 && num_query > 0 && closest_n > 0 && num_bases > 0, "dimensions must be positive");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  REQUIRE(ndev > 0, "no CUDA device: libmcq_b200 has no CPU fallback");
+  REQUIRE(device >= 0 && device < ndev, "device ordinal out of range");
+  for (size_t i = 0; i < (size_t)num_query * closest_n; i++)
+    REQUIRE(closest_refs[i] >= 0 && closest_refs[i] < num_refs, "closest_refs entry out of range");
+  CK(cudaSetDevice(device));
+  DevBuf d_refs, d_cl, d_out;
+  CK(cudaMalloc(&d_refs.p, (size_t)num_refs * ref_stride));
+  CK(cudaMalloc(&d_cl.p, (size_t)num_query * closest_n * sizeof(int)));
+  CK(cudaMalloc(&d_out.p, (size_t)num_query * num_bases));
+  CK(cudaMemcpy(d_refs.p, ref_seqs, (size_t)num_refs * ref_stride, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_cl.p, closest_refs, (size_t)num_query * closest_n * sizeof(int), cudaMemcpyHostToDevice));
+  for (int q0 = 0; q0 < num_query; q0 += 65535) {
+    const int nq = std::min(65535, num_query - q0);
+    dim3 grid((unsigned)((num_bases + 255) / 256), (unsigned)nq);
+    k_consensus<<<grid, 256>>>(d_refs.as<unsigned char>(), ref_stride, d_cl.as<int>() + (size_t)q0 * closest_n, closest_n,
+                               num_bases, d_out.as<signed char>() + (size_t)q0 * num_bases);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(cons_codes, d_out.p, (size_t)num_query * num_bases, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // drop-in symbols (closest_seqs.h:4-9)
 // ------------------------------------------------------------------------------------------
 namespace {

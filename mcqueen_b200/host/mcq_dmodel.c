@@ -581,8 +581,8 @@ int main(int argc, char **argv)
   const int Q = q1 - q0;
   c.Q = Q;
   McqData d;
-  mcq_prepare(&d, ref_seqs, N, query_seqs + q0, Q, cons_seqs, ncons, hla_rows + q0, H, closest_all + (size_t)q0 * closest_n,
-              closest_n);
+  mcq_prepare(&d, device, ref_seqs, N, query_seqs + q0, Q, cons_seqs, ncons, hla_rows + q0, H,
+              closest_all + (size_t)q0 * closest_n, closest_n);
 
   printf("Reference codons: ");
   for(int s = 0; s < S; s++) {

@@ -30,8 +30,8 @@ void mcq_consensus(char *const *seqs, const int *idx, int n, int len, char *out)
   out[len] = '\0';
 }
 
-void mcq_prepare(McqData *d, char **ref_seqs, int N, char **query_seqs, int Q, char **cons_seqs, int ncons,
-                 char **hla_rows, int H, const int *closest, int L)
+void mcq_prepare(McqData *d, int device, char **ref_seqs, int N, char **query_seqs, int Q, char **cons_seqs,
+                 int ncons, char **hla_rows, int H, const int *closest, int L)
 {
   const int nb = (int)strlen(ref_seqs[0]);
   const int S = nb / 3;
@@ -48,14 +48,21 @@ void mcq_prepare(McqData *d, char **ref_seqs, int N, char **query_seqs, int Q, c
   char *consensus = malloc(nb + 1), *local = malloc(nb + 1);
   mcq_consensus(cons_seqs, NULL, ncons, nb, consensus);
 
-  /* per query: consensus of its closest references; unknown query bases take it (dmodel.c:664-681) */
-  for(int q = 0; q < Q; q++) {
-    mcq_consensus(ref_seqs, closest + (size_t)q * L, L, nb, local);
-    for(int i = 0; i < nb; i++) {
-      if(mcq_base_code((unsigned char)query_seqs[q][i]) == 4) query_seqs[q][i] = local[i];
-      d->cons_query_nucls[(size_t)q * nb + i] = (char)mcq_base_code((unsigned char)local[i]);
+  /* per query: consensus of its closest references (on the device: Q*L*nb character reads); unknown
+   * query bases take it (dmodel.c:664-681) */
+  {
+    static const char letters[4] = {'T', 'C', 'A', 'G'};
+    char *rflat = malloc((size_t)N * nb);
+    for(int r = 0; r < N; r++) memcpy(rflat + (size_t)r * nb, ref_seqs[r], nb);
+    if(mcq_consensus_batch(device, rflat, nb, N, closest, Q, L, nb, d->cons_query_nucls) != 0)
+      mcq_die("mcq_consensus_batch: %s", mcq_last_error());
+    free(rflat);
+    for(int q = 0; q < Q; q++) {
+      for(int i = 0; i < nb; i++)
+        if(mcq_base_code((unsigned char)query_seqs[q][i]) == 4)
+          query_seqs[q][i] = letters[(int)d->cons_query_nucls[(size_t)q * nb + i]];
+      memcpy(d->hla + (size_t)q * H, hla_rows[q], H);
     }
-    memcpy(d->hla + (size_t)q * H, hla_rows[q], H);
   }
   /* triplets keep unknown bases (dmodel.c:684-686); codons are taken after mapping them to the
    * global consensus (dmodel.c:693-701) */

@@ -23,8 +23,8 @@ int mcq_base_code(int ch);   /* amino_acids.c:10-17 */
 void mcq_consensus(char *const *seqs, const int *idx, int n, int len, char *out);
 /* builds everything in `d` from the sequences; fills gaps of queries/references in place the way
  * dmodel.c:664-701 does.  closest is [Q][L]. */
-void mcq_prepare(McqData *d, char **ref_seqs, int N, char **query_seqs, int Q, char **cons_seqs, int ncons,
-                 char **hla_rows, int H, const int *closest, int L);
+void mcq_prepare(McqData *d, int device, char **ref_seqs, int N, char **query_seqs, int Q, char **cons_seqs,
+                 int ncons, char **hla_rows, int H, const int *closest, int L);
 void mcq_data_free(McqData *d);
 
 #endif

@@ -96,3 +96,18 @@ def test_dropin_symbols(api):
         got = np.zeros(n, np.int32)
         api.closest_sequences(10, ham, n, got)
         assert np.array_equal(got, want)
+
+
+def test_consensus_batch_matches_host_rule(api):
+    """per-query consensus of the closest references (amino_acids.c:118-141) incl. unknown bases and ties"""
+    from mcqueen_b200 import genetics as gen, prep
+    d = _data(S=40, N=200, Q=25)
+    refs = d["ref_seqs"].copy()
+    refs[::7, 3] = ord("-"); refs[5, :] = ord("N"); refs[9, 10:20] = np.frombuffer(b"acgtacgtac", np.uint8)
+    rng = np.random.default_rng(1)
+    for L in (1, 2, 17, 199):
+        closest = np.stack([rng.choice(200, L, replace=False) for _ in range(25)]).astype(np.int32)
+        got = api.consensus_batch(refs, closest)
+        codes = gen.base_codes(refs)
+        want = np.stack([prep.majority_codes(codes[closest[q]]) for q in range(25)])
+        assert np.array_equal(got, want), L
