@@ -28,6 +28,7 @@
 
 #include "../../include/mcq_b200.h"
 #include "mcq_io.h"
+#include "mcq_json.h"
 #include "mcq_model.h"
 #include "mcq_prep.h"
 #include "mcq_rng.h"
@@ -353,13 +354,14 @@ static bool opt_sample_prior = false, opt_sparse = false, runtime_set = false, s
 static int opt_omega_prior = MCQ_PRIOR_EXPONENTIAL, opt_esc_prior = MCQ_PRIOR_LOG_NORMAL;
 static int opt_rev_prior = MCQ_PRIOR_LOG_NORMAL, opt_device = -1;
 static long opt_seed = -1, opt_gsl_seed = -1;
-static const char *trace_path = NULL;
+static const char *trace_path = NULL, *resume_path = NULL;
 
 static void usage(void)
 {
   fprintf(stderr,
           "usage: mcq_dmodel [options] <ref_seqs.fasta> <query.fasta> <outdir>\n"
           "  -H <HLA.csv>  -n <chain length>  -s <sample every>  -t <hours>  -c <consensus.fasta>  -l <closest L>\n"
+          "  -r <state.json> resume from a saved state\n"
           "  -q self-reference mode  -i no HLA inference  -j no reversion inference  -o no recombination\n"
           "  -v/-e/-w omega prior gamma/log-normal/uniform   -g/-k/-f escape prior gamma/normal/flat\n"
           "  -a/-d/-u reversion prior gamma/normal/flat   -b sample the prior   -z no simulated annealing\n"
@@ -373,6 +375,7 @@ static void parse(int argc, char **argv)
       {"HLA_inference", required_argument, NULL, 'H'}, {"chain_length", required_argument, NULL, 'n'},
       {"sample_every", required_argument, NULL, 's'}, {"runtime_hours", required_argument, NULL, 't'},
       {"consensus_fasta", required_argument, NULL, 'c'}, {"closest_n", required_argument, NULL, 'l'},
+      {"resume_json", required_argument, NULL, 'r'},
       {"separate_reference_fasta", no_argument, NULL, 'q'}, {"no_HLA_inference", no_argument, NULL, 'i'},
       {"no_rev_inference", no_argument, NULL, 'j'}, {"no_recombination_inference", no_argument, NULL, 'o'},
       {"omega_gamma", no_argument, NULL, 'v'}, {"omega_log_normal", no_argument, NULL, 'e'},
@@ -385,13 +388,14 @@ static void parse(int argc, char **argv)
       {"sparse_esc", no_argument, NULL, 1004}, {"trace", required_argument, NULL, 1005},
       {"nccl", no_argument, NULL, 1006}, {NULL, 0, NULL, 0}};
   int o;
-  while((o = getopt_long(argc, argv, "H:n:s:t:c:l:qijovewgkfadubz", lo, NULL)) != -1) {
+  while((o = getopt_long(argc, argv, "H:n:s:t:c:r:l:qijovewgkfadubz", lo, NULL)) != -1) {
     switch(o) {
       case 'H': hla_path = optarg; break;
       case 'n': chain_length = atoi(optarg); states_set = true; break;
       case 's': sample_rate = atoi(optarg); break;
       case 't': runtime_hours = atoi(optarg); runtime_set = true; break;
       case 'c': cons_path = optarg; break;
+      case 'r': resume_path = optarg; break;
       case 'l': closest_n = atoi(optarg); break;
       case 'q': separate_reference_set = false; break;
       case 'i': no_hla = true; break;
@@ -567,14 +571,21 @@ int main(int argc, char **argv)
   c.gamma_const_rev = c.gamma_const_esc;
   c.hw = malloc(sizeof(McqHlaWindows) * H);
   mcq_windows_alloc(S, H, MCQ_INIT_WINDOWS, MCQ_INIT_WINDOWS, c.hw);
-  for(int h = 0; h < H; h++) {
-    mcq_windows_randomise(c.hw[h].esc, S, MCQ_INIT_WINDOWS, log(MCQ_MU_SEL_PRIOR), MCQ_SIGMA_SEL_PRIOR);
-    mcq_windows_randomise(c.hw[h].rev, S, MCQ_INIT_WINDOWS, log(MCQ_MU_SEL_PRIOR), MCQ_SIGMA_SEL_PRIOR);
+  double resume_llk = 0;
+  if(resume_path != NULL) {
+    /* dmodel -r (dmodel.c:589-604): parameters, windows and the closest-L lists come from the saved
+     * state; the tie shuffles above have still consumed their random() draws, as in the reference */
+    mcq_load_state_json(resume_path, &resume_llk, &c.mu, c.R, c.omega, c.hw, S, H, Qall, closest_n, closest_all);
+  } else {
+    for(int h = 0; h < H; h++) {
+      mcq_windows_randomise(c.hw[h].esc, S, MCQ_INIT_WINDOWS, log(MCQ_MU_SEL_PRIOR), MCQ_SIGMA_SEL_PRIOR);
+      mcq_windows_randomise(c.hw[h].rev, S, MCQ_INIT_WINDOWS, log(MCQ_MU_SEL_PRIOR), MCQ_SIGMA_SEL_PRIOR);
+    }
+    if(hla_path == NULL || no_hla)
+      for(int h = 0; h < H; h++) for(int i = 0; i < MCQ_INIT_WINDOWS; i++) c.hw[h].esc->w[i].coeff = 1;
+    if(no_rev) for(int i = 0; i < MCQ_INIT_WINDOWS; i++) c.hw[0].rev->w[i].coeff = 1;
+    for(int h = 1; h < H; h++) for(int i = 0; i < MCQ_INIT_WINDOWS; i++) c.hw[h].rev->w[i].coeff = 1;
   }
-  if(hla_path == NULL || no_hla)
-    for(int h = 0; h < H; h++) for(int i = 0; i < MCQ_INIT_WINDOWS; i++) c.hw[h].esc->w[i].coeff = 1;
-  if(no_rev) for(int i = 0; i < MCQ_INIT_WINDOWS; i++) c.hw[0].rev->w[i].coeff = 1;
-  for(int h = 1; h < H; h++) for(int i = 0; i < MCQ_INIT_WINDOWS; i++) c.hw[h].rev->w[i].coeff = 1;
 
   /* this rank's shard of the queries */
   const int q0 = (int)((long long)Qall * rank / world), q1 = (int)((long long)Qall * (rank + 1) / world);
@@ -641,6 +652,7 @@ int main(int argc, char **argv)
     CHECK(mcq_ctx_init_state(c.ctx, &c.llk));
     printf("Total log-likelihood using initialise F: %f.\n", c.llk);
   }
+  if(resume_path != NULL) printf("Likelihood from loaded .json file: %f.\n", resume_llk);
 
   /* move weights (dmodel.c:915-962) */
   const bool esc_on = (hla_path != NULL) && !no_hla, rev_on = !no_rev;

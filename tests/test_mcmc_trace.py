@@ -89,3 +89,33 @@ def test_reference_dmodel_linked_against_the_dropin_symbols(tmp_path):
         run([exe] + args + [str(tmp_path / name)], env={"MCQ_SEED": "3", "MCQ_GSL_SEED": "3", "MCQ_TRACE": t})
         traces.append(read_trace(t))
     assert traces[0].shape == traces[1].shape and np.array_equal(traces[0], traces[1])
+
+
+def test_resume_from_saved_state_matches_reference(tmp_path):
+    """dmodel -r: a state written by this driver is read back by it AND by the reference dmodel
+    (write_json.c / load_from_json.c format); both resumed chains make the same decisions."""
+    if not os.path.exists(DRIVER):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(DRIVER)])
+    paths, L, _ = make_chain_inputs(str(tmp_path / "in"), "toy")
+    base = ["-H", paths["hla"], "-l", str(L), "-s", "50", paths["ref"], paths["query"]]
+    out = run([DRIVER, "--seed", "5", "--gsl_seed", "5", "-n", "200"] + base + [str(tmp_path / "first")])
+    state = newest(str(tmp_path / "first"), "_final_state.json")
+    saved = float(re.search(r'"llkhood": (-?[0-9]+\.[0-9]+)', open(state).read()).group(1))
+    final = float(re.search(r"final log-likelihood: (-?[0-9]+\.[0-9]+)", out).group(1))
+    assert abs(saved - final) <= 1e-9 * abs(final)
+
+    t_ours = str(tmp_path / "ours.trace")
+    o = run([DRIVER, "--seed", "9", "--gsl_seed", "9", "--trace", t_ours, "-r", state, "-n", "150"] + base +
+            [str(tmp_path / "ours")])
+    ours_init = float(re.search(r"Total log-likelihood using initialise F: (-?[0-9]+\.[0-9]+)", o).group(1))
+    # omega / R / coefficients are stored with 10 decimals: the recomputed likelihood is close to the saved one
+    assert abs(ours_init - saved) <= 1e-6 * abs(saved)
+    if not (cpu_libs.have_ref() and os.path.exists(cpu_libs.REF_DMODEL)):
+        return
+    t_ref = str(tmp_path / "ref.trace")
+    r = run([cpu_libs.REF_DMODEL, "-r", state, "-n", "150"] + base + [str(tmp_path / "ref")],
+            env={"MCQ_SEED": "9", "MCQ_GSL_SEED": "9", "MCQ_TRACE": t_ref})
+    ref_init = float(re.search(r"Total log-likelihood using initialise F: (-?[0-9]+\.[0-9]+)", r).group(1))
+    assert abs(ours_init - ref_init) <= 1e-9 * abs(ref_init)
+    a, b = read_trace(t_ours), read_trace(t_ref)
+    assert a.shape == b.shape and np.array_equal(a, b)
