@@ -48,7 +48,7 @@ def workload_dims(name):
 def make_data(name):
     cfg = workload_dims(name)
     cfg.pop("L")
-    return synth.make_dataset(seed=SEED, **cfg)
+    return synth.make_dataset(seed=SEED, self_reference=name in synth.SELF_REFERENCE, **cfg)
 
 
 def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
@@ -62,7 +62,7 @@ def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
     t1 = time.time()
     import ctypes
     ctypes.CDLL("libc.so.6").srandom(SEED & 0x7fffffff)
-    closest = api.closest_batch(refs, qs, L, device=device_index)
+    closest = api.closest_batch(refs, qs, L, skip_first=name in synth.SELF_REFERENCE, device=device_index)
     t2 = time.time()
     ham_ms, sel_ms = api.closest_last_timing()
     cons_q = api.consensus_batch(refs, closest, device=device_index)
@@ -214,7 +214,8 @@ def mcmc_steps_per_s(workload, steps, ref_steps=12):
     tmp = tempfile.mkdtemp(prefix="mcq_mcmc_")
     out = {"workload": workload, "steps": steps}
     try:
-        paths, L, _ = make_chain_inputs(os.path.join(tmp, "in"), workload, seed=SEED)
+        paths, L, _ = make_chain_inputs(os.path.join(tmp, "in"), workload, seed=SEED, query_model="dsim")
+        out["data"] = "queries drawn from the model itself (dsim recipe, mcqueen_b200/synth.py)"
         base = ["-H", paths["hla"], "-l", str(L), "-s", "1000000", paths["ref"], paths["query"]]
         for key, extra in (("gpu", []), ("gpu_sparse_esc", ["--sparse_esc"])):
             r = subprocess.run([driver, "--seed", "1", "--gsl_seed", "1", "-n", str(steps)] + extra + base +

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import genetics as gen
 
-__all__ = ["make_dataset", "CONFIGS"]
+__all__ = ["make_dataset", "CONFIGS", "dsim_rows", "dsim_queries"]
 
 # the named shapes of BASELINE.json / SURVEY.md §8
 CONFIGS = {
@@ -25,7 +25,10 @@ CONFIGS = {
     "C3": dict(S=500, N=100000, Q=10000, L=500, H=20),
     "C4": dict(S=500, N=100000, Q=10000, L=500, H=20),
     "C5": dict(S=3000, N=50000, Q=50000, L=200, H=20),
+    # one GPU's share of C5 when it is sharded 8 ways (self-reference mode: queries are references)
+    "C5s": dict(S=3000, N=50000, Q=6250, L=200, H=20),
 }
+SELF_REFERENCE = {"C5", "C5s"}   # dmodel -q: the queries are the first Q references, L+1 found, self dropped
 
 _ASCII = np.frombuffer(b"TCAG", dtype=np.uint8)
 
@@ -41,9 +44,74 @@ def _mutate(rng, codons, rate, neigh, ncount):
     return codons
 
 
+def dsim_rows(frm, cons, omega, esc_prod, rev, mu, N, kappa=gen.KAPPA, phi=gen.PHI, prior=None):
+    """The simulator's emission distribution (simulate_codon_to_codon_HLA,
+    simulate_sequences_sim.c:14-137): P(new codon = to | copied codon = frm) for every `to`.
+    All arguments broadcast against each other (frm/cons integer codons); returns (..., 64).
+    These are the rows of the likelihood's emission table read the other way round
+    (mcmc_moves.c:78-167), except that the simulator has no special case for TGG/ATG consensus."""
+    prior = gen.normalised_prior() if prior is None else np.asarray(prior, float)
+    frm, cons = np.asarray(frm, np.int64), np.asarray(cons, np.int64)
+    omega, esc_prod, rev = (np.asarray(x, float) for x in (omega, esc_prod, rev))
+    frm, cons, omega, esc_prod, rev = np.broadcast_arrays(frm, cons, omega, esc_prod, rev)
+    ns = kappa * gen.NS_TS + gen.NS_TV            # (64,64) non-synonymous single steps
+    sy = kappa * gen.S_TS + gen.S_TV              # synonymous single steps
+    om = omega[..., None]
+    step = om * ns[frm] + sy[frm]                 # (...,64): m(frm, to)
+    rate0 = kappa * gen.BETA_S[frm] + gen.BETA_V[frm] + omega * (kappa * gen.ALPHA_S[frm] + gen.ALPHA_V[frm])
+    back = (1 - phi) * prior                      # (64,)
+    to = np.arange(64)
+    is_cons_to = to == cons[..., None]
+    # copied codon is not the consensus: reversion boosts the step onto the consensus
+    m_fc = omega * ns[frm, cons] + sy[frm, cons]
+    rate_r = rate0 + (rev - 1) * m_fc
+    A_r = 1 - N / (N + rate_r * 4 * mu)
+    g_r = (phi / rate_r)[..., None]
+    rows_r = A_r[..., None] * (np.where(is_cons_to, g_r * rev[..., None] * step, g_r * step) + back)
+    rows_r = rows_r + (to == frm[..., None]) * (1 - A_r[..., None])
+    # copied codon is the consensus: escape boosts every non-synonymous step out of it
+    nsum = kappa * gen.ALPHA_S[cons] + gen.ALPHA_V[cons]
+    rate_e = rate0 + (esc_prod - 1) * omega * nsum
+    A_e = 1 - N / (N + rate_e * 4 * mu)
+    g_e = (phi / rate_e)[..., None]
+    rows_e = A_e[..., None] * (g_e * (esc_prod[..., None] * om * ns[frm] + sy[frm]) + back)
+    stay = (1 - A_e) * (1 - back[cons]) + back[cons]
+    rows_e = np.where(is_cons_to, stay[..., None], rows_e)
+    return np.where((frm == cons)[..., None], rows_e, rows_r)
+
+
+def dsim_queries(rng, ref_codons, consensus_codons, hla, omega, R, esc, rev, mu, chunk=256):
+    """Queries drawn from the model itself, as the reference's dsim does
+    (simulate_sequences_sim.c:154-300): a mosaic of references switching with probability R[s], each codon
+    drawn from the emission distribution of the copied codon given the query's HLA profile.
+    Returns (queries (Q,S) int8, copy_from (Q,S) int32)."""
+    N, S = ref_codons.shape
+    Q, H = hla.shape
+    carrier = (hla == ord("1"))
+    copy_from = np.empty((Q, S), np.int32)
+    copy_from[:, 0] = rng.integers(0, N, Q)
+    switch = rng.random((Q, S)) < R[None, :]
+    fresh = rng.integers(0, N, (Q, S))
+    for s in range(1, S):
+        copy_from[:, s] = np.where(switch[:, s], fresh[:, s], copy_from[:, s - 1])
+    out = np.empty((Q, S), np.int8)
+    sites = np.arange(S)
+    for q0 in range(0, Q, chunk):
+        q1 = min(Q, q0 + chunk)
+        frm = ref_codons[copy_from[q0:q1], sites[None, :]].astype(np.int64)
+        # product of the escape coefficients of the HLA types the query carries
+        esc_prod = np.exp(carrier[q0:q1].astype(float) @ np.log(esc))
+        rows = dsim_rows(frm, consensus_codons[None, :], omega[None, :], esc_prod, rev[None, :], mu, N)
+        cdf = np.cumsum(rows, axis=-1)
+        u = rng.random((q1 - q0, S, 1)) * cdf[..., -1:]
+        out[q0:q1] = np.minimum((u > cdf).sum(-1), 63).astype(np.int8)
+    return out, copy_from
+
+
 def make_dataset(seed=20261019, S=100, N=200, Q=50, H=4, n_clades=None,
                  clade_div=0.04, member_div=0.02, query_div=0.03, rec=0.01,
-                 ref_unknown_frac=0.0, query_gap=False, hla_site_frac=0.05, hla_boost=3.0):
+                 ref_unknown_frac=0.0, query_gap=False, hla_site_frac=0.05, hla_boost=3.0,
+                 self_reference=False, query_model="simple"):
     """Returns dict(ref_seqs (N,3S) u8 ASCII, query_seqs (Q,3S) u8 ASCII, hla (Q,H) u8 '0'/'1',
     parents (Q,S) i32 = the true copied reference per codon)."""
     rng = np.random.default_rng(seed)
@@ -91,6 +159,19 @@ def make_dataset(seed=20261019, S=100, N=200, Q=50, H=4, n_clades=None,
     rate = np.where(carrier_boost, np.minimum(1.0, query_div * hla_boost), query_div)
     _mutate(rng, queries, rate, neigh, ncount)
 
+    if query_model == "dsim":
+        # the reference's own generative recipe; parameters as SURVEY.md §8d: omega ~ LogN(0, 0.5),
+        # R = 0.01, reversion 1, escape 1 except a few (HLA, site) pairs at hla_boost; mu scaled so that a
+        # codon mutates with a few per cent probability whatever the panel size
+        codes = gen.base_codes(gen.codons_to_ascii(refs))
+        counts = np.stack([(codes == b).sum(0) for b in range(4)])
+        cons = gen.to_codons(counts.argmax(0).astype(np.int8)[None, :])[0].astype(np.int64)
+        omega = np.exp(rng.normal(0.0, 0.5, S))
+        esc = np.where(hla_sites, hla_boost, 1.0)
+        mu_gen = query_div * N / (4 * 30.0)
+        queries, parents = dsim_queries(rng, refs, cons, hla, omega, np.full(S, rec), esc, np.ones(S), mu_gen)
+    if self_reference:
+        queries = refs[:Q].copy()
     ref_seqs = gen.codons_to_ascii(refs)
     query_seqs = gen.codons_to_ascii(queries)
     if ref_unknown_frac > 0:

@@ -22,11 +22,12 @@ def write_hla_csv(path, hla):
             f.write(f"q{q}," + ",".join(chr(c) for c in row) + "\n")
 
 
-def make_chain_inputs(dirname, name="toy", seed=20261019, gaps=False, **over):
+def make_chain_inputs(dirname, name="toy", seed=20261019, gaps=False, query_model="simple", **over):
     cfg = dict(synth.CONFIGS[name])
     cfg.update(over)
     L = cfg.pop("L")
-    d = synth.make_dataset(seed=seed, ref_unknown_frac=0.03 if gaps else 0.0, query_gap=gaps, **cfg)
+    d = synth.make_dataset(seed=seed, ref_unknown_frac=0.03 if gaps else 0.0, query_gap=gaps,
+                           query_model=query_model, **cfg)
     os.makedirs(dirname, exist_ok=True)
     paths = dict(ref=os.path.join(dirname, "ref.fasta"), query=os.path.join(dirname, "query.fasta"),
                  hla=os.path.join(dirname, "query.HLA.csv"))

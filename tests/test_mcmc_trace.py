@@ -38,11 +38,12 @@ def log_rows(path):
     return np.array(rows, dtype=float)
 
 
-@pytest.mark.parametrize("extra,gaps", [([], False), (["--sparse_esc"], False), ([], True)])
-def test_trace_matches_reference_dmodel(tmp_path, extra, gaps):
+@pytest.mark.parametrize("extra,gaps,model", [([], False, "simple"), (["--sparse_esc"], False, "simple"),
+                                              ([], True, "simple"), ([], False, "dsim")])
+def test_trace_matches_reference_dmodel(tmp_path, extra, gaps, model):
     if not os.path.exists(DRIVER):
         subprocess.check_call(["make", "-s", "-C", os.path.dirname(DRIVER)])
-    paths, L, _ = make_chain_inputs(str(tmp_path / "in"), "toy", gaps=gaps)
+    paths, L, _ = make_chain_inputs(str(tmp_path / "in"), "toy", gaps=gaps, query_model=model)
     args = ["-H", paths["hla"], "-l", str(L), "-n", "1000", "-s", "50", paths["ref"], paths["query"]]
     ours_trace = str(tmp_path / "ours.trace")
     out = run([DRIVER, "--seed", "1", "--gsl_seed", "1", "--trace", ours_trace] + extra + args + [str(tmp_path / "ours")])
@@ -58,8 +59,8 @@ def test_trace_matches_reference_dmodel(tmp_path, extra, gaps):
         ref_init = float(re.search(r"Total log-likelihood using initialise F: (-?[0-9]+\.[0-9]+)", rout).group(1))
         ref_log = log_rows(newest(str(tmp_path / "ref"), "_log.txt"))
     else:
-        if gaps:
-            pytest.skip("golden trace covers the gap-free chain only")
+        if gaps or model != "simple":
+            pytest.skip("golden trace covers the gap-free chain on the simple generator only")
         g = np.load(os.path.join(GOLDEN, "toy_chain.npz"))
         ref, ref_init, ref_log = g["trace"], float(g["init_llk"]), g["log"]
 
