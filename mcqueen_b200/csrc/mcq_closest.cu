@@ -317,15 +317,22 @@ int pack_to_device(const char *seqs, size_t stride, int n, int nbases, int W, bo
 
 const int kTQ = 32, kRT = 2;
 
+template <int TQ>
+int hamming_launch(DevBuf &refp, size_t npad, int N, DevBuf &qryp, int Q, int W, uint16_t *D, cudaStream_t st) {
+  const size_t smem = (size_t)TQ * W * 3 * sizeof(u64);
+  CK(cudaFuncSetAttribute(k_hamming<TQ, kRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)(npad / (128 * kRT)), (unsigned)((Q + TQ - 1) / TQ));
+  k_hamming<TQ, kRT><<<grid, 128, smem, st>>>(refp.as<u64>(), npad, N, qryp.as<u64>(), Q, W, D);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int hamming_device(const DevBuf &refp_, size_t npad, int N, const DevBuf &qryp_, int Q, int W, uint16_t *D,
                    cudaStream_t st) {
   DevBuf &refp = const_cast<DevBuf &>(refp_), &qryp = const_cast<DevBuf &>(qryp_);
-  const size_t smem = (size_t)kTQ * W * 3 * sizeof(u64);
-  CK(cudaFuncSetAttribute(k_hamming<kTQ, kRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)(npad / (128 * kRT)), (unsigned)((Q + kTQ - 1) / kTQ));
-  k_hamming<kTQ, kRT><<<grid, 128, smem, st>>>(refp.as<u64>(), npad, N, qryp.as<u64>(), Q, W, D);
-  CK(cudaGetLastError());
-  return 0;
+  // 32 queries per block while their bit planes fit in shared memory (up to ~17 000 bases), else 8
+  if ((size_t)kTQ * W * 3 * sizeof(u64) <= 200 * 1024) return hamming_launch<kTQ>(refp, npad, N, qryp, Q, W, D, st);
+  return hamming_launch<8>(refp, npad, N, qryp, Q, W, D, st);
 }
 
 // closest_seqs.c:57-64 + util.c:24-30: forward shuffle with j = (int)((i+1) * random()/RAND_MAX)

@@ -87,6 +87,8 @@ struct mcq_ctx {
   int Ls = 0, Lg = 0, NA = 0;          // NA = number of non-consensus slots (sum_s K_s)
   size_t TL = 0;               // length of the shared emission table (64 * NA)
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // the backward refill of an accept runs beside the forward refill
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t bytes = 0;
   bool have_static = false, have_params = false, have_state = false;
 
@@ -230,6 +232,9 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   while (c->Lg < c->Ls) c->Lg *= 2;   // 64 * NJ, NJ in {1,2,4,8,16}
   c->logBIG = log(MCQ_BIG);   // the host libm value the reference itself uses (mcmc_moves.c:223)
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
   CK(cudaEventCreate(&c->evt0));
@@ -270,6 +275,10 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   cudaEventDestroy(c->evt0);
   cudaEventDestroy(c->evt1);
   for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
+  cudaStreamSynchronize(c->stream2);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -532,11 +541,18 @@ static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int star
   return 0;
 }
 
-static int run_backward(mcq_ctx *c, int update, bool sparse, int hla) {
+static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream_t stream = nullptr) {
+  if (stream == nullptr) stream = c->stream;
   BwdArgs a;
   a.st = make_static(c);
   a.em.tab = c->tab; a.em.ec = c->ec; a.R = c->m.R; a.B = c->B; a.Bn = c->Bn; a.update = update;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
+  if (stream != c->stream) {          // beside the main stream: counted, not bracketed
+    c->launches++;
+    c->k_n[MCQ_K_BACKWARD]++;
+    CK(mcq_launch_backward(a, stream));
+    return 0;
+  }
   KScope ks(c, MCQ_K_BACKWARD);
   CK(mcq_launch_backward(a, c->stream));
   return 0;
@@ -722,13 +738,22 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
       KScope ks(c, MCQ_K_COMMIT);
       CK(mcq_launch_commit_cols(st, c->T, c->Tn, c->F, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
     }
+    // F after the range and B from the range down to 0 do not depend on each other: two streams
+    const bool dual = c->timing < 2 && ov.end + 1 < S;
+    if (dual) {
+      CK(cudaEventRecord(c->ev_fork, c->stream));
+      CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      if (run_backward(c, ov.end, sparse, ov.hla, c->stream2)) return 1;
+      CK(cudaEventRecord(c->ev_join, c->stream2));
+    }
     if (ov.end + 1 < S)
       if (run_forward(c, c->tab, c->ec, ov.end + 1, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
-    if (run_backward(c, ov.end, sparse, ov.hla)) return 1;
+    if (dual) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    else if (run_backward(c, ov.end, sparse, ov.hla)) return 1;
   }
   swap_ptr(c->llk_cur, c->llk_prop);
   c->has_pending = false;
-  if (!c->timing) CK(cudaStreamSynchronize(c->stream));
+  // no host wait here: everything later is ordered behind this on the context's stream
   return 0;
 }
 

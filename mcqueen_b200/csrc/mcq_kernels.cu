@@ -189,6 +189,9 @@ cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, co
   }
   k_trip_table<<<sblocks * 32, 128, 0, stream>>>(slot_of, trip_tab, S);
   const size_t smem = (size_t)32 * (Lg / 4 + 1) * sizeof(uint32_t);
+  // static (20 KB) + dynamic shared memory passes the 48 KB default for the widest rows
+  cudaError_t e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
     int nq = Q - q0 < 65535 ? Q - q0 : 65535;
     dim3 grid(sblocks, nq);

@@ -23,7 +23,8 @@ def _data(S=100, N=300, Q=40, seed=5, **kw):
     return synth.make_dataset(seed=seed, S=S, N=N, Q=Q, H=4, ref_unknown_frac=0.1, query_gap=True, **kw)
 
 
-@pytest.mark.parametrize("S,N,Q", [(100, 300, 40), (7, 130, 33), (43, 1000, 5), (500, 257, 70)])
+@pytest.mark.parametrize("S,N,Q", [(100, 300, 40), (7, 130, 33), (43, 1000, 5), (500, 257, 70),
+                                   (7000, 40, 9)])      # 21 000 bases: the 8-queries-per-block variant
 def test_hamming_batch_bit_exact(api, S, N, Q):
     d = _data(S, N, Q)
     refs, qs = d["ref_seqs"].copy(), d["query_seqs"].copy()

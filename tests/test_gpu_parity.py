@@ -164,7 +164,13 @@ def test_dropin_symbols_match(api):
         assert np.array_equal(Bn2, Hn2) and rel(B2, H2) < RTOL_CELL
 
 
-@pytest.mark.parametrize("name,over", [("toy", {}), ("toy", dict(L=100, N=150)), ("toy", dict(L=37, S=33, Q=9))])
+@pytest.mark.parametrize("name,over", [("toy", {}), ("toy", dict(L=100, N=150)), ("toy", dict(L=37, S=33, Q=9)),
+                                       ("toy", dict(L=200, N=260, S=40, Q=6)),      # NJ = 4, ragged row
+                                       ("toy", dict(L=256, N=300, S=25, Q=5)),      # NJ = 4, full row
+                                       ("toy", dict(L=1000, N=1100, S=21, Q=4)),    # NJ = 16, ragged
+                                       ("toy", dict(L=1024, N=1100, S=12, Q=3)),    # NJ = 16, the maximum
+                                       ("toy", dict(L=1, N=50, S=30, Q=7)),         # a single copy state
+                                       ("toy", dict(L=20, N=200, S=1, Q=5))])       # a single site
 def test_shapes_and_likelihood_identity(api, name, over):
     """Ragged shapes (L not a multiple of 16 or 64, tiny S) and the F.B identity: for every site s,
     log sum_r F[r][s] B[r][s] - (Fn+Bn) log BIG is the query's log-likelihood."""
@@ -179,6 +185,13 @@ def test_shapes_and_likelihood_identity(api, name, over):
         B, Bn = ctx.matrix(api.BUF_B, q)
         per_site = np.log((F * B).sum(0)) - (Fn + Bn) * np.log(1e6)
         assert np.max(np.abs(per_site - lq[q])) < 1e-9 * abs(lq[q])
+    assert_state_matches(ctx, cpu, [0, p.Q - 1])
+    if p.S > 2:      # one window proposal + accept through the same shapes
+        mv = dict(kind=REV, start=1, end=min(p.S - 1, 9), value0=1.4)
+        want, got = cpu.propose(**mv), ctx.propose(**mv)
+        assert abs(got - want) <= RTOL_LLK * abs(want)
+        cpu.accept(); ctx.accept()
+        assert_state_matches(ctx, cpu, [0, p.Q - 1])
     ctx.close()
 
 
