@@ -96,6 +96,7 @@ struct mcq_ctx {
   uint8_t *G = nullptr, *ncodon = nullptr, *cons_in_list = nullptr, *cons_codon = nullptr;
   uint8_t *query_codon = nullptr, *hla = nullptr;
   int *aoff = nullptr, *toff = nullptr, *nsite = nullptr;
+  int2 *desc = nullptr;
   // static (host mirrors)
   std::vector<int> aoff_h, toff_h;
   std::vector<uint8_t> ncodon_h, cons_in_list_h, cons_codon_h, slot_of_h;
@@ -160,7 +161,7 @@ static McqStatic make_static(const mcq_ctx *c) {
   st.Q = c->d.num_query; st.S = c->d.num_sites; st.L = c->d.closest_n; st.Ls = c->Ls; st.Lg = c->Lg;
   st.N = c->d.total_num_refs; st.H = c->d.num_hla_types;
   st.G = c->G; st.aoff = c->aoff; st.toff = c->toff; st.ncodon = c->ncodon; st.nsite = c->nsite;
-  st.cons_in_list = c->cons_in_list;
+  st.cons_in_list = c->cons_in_list; st.desc = c->desc;
   st.cons_codon = c->cons_codon; st.query_codon = c->query_codon; st.hla = c->hla;
   return st;
 }
@@ -257,7 +258,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->d.device);
   cudaStreamSynchronize(c->stream);
-  void *ptrs[] = {c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
+  void *ptrs[] = {c->desc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
                   c->llk_cur, c->llk_prop, c->d_sum, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
@@ -420,6 +421,12 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     CK(cudaMemcpy(c->nsite, site_of.data(), site_of.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->aoff, aoff_h.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->toff, toff_h.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    {
+      std::vector<int2> desc_h(S);
+      for (int s = 0; s < S; s++) desc_h[s] = make_int2(toff_h[s], aoff_h[s + 1] - aoff_h[s]);
+      ALLOC(c->desc, (size_t)S);
+      CK(cudaMemcpy(c->desc, desc_h.data(), (size_t)S * sizeof(int2), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpy(c->ncodon, ncodon_h.data(), ncodon_h.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->cons_in_list, cons_in_list_h.data(), S, cudaMemcpyHostToDevice));
   } else {

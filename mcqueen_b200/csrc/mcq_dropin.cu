@@ -38,6 +38,7 @@ struct Scratch {
   // device
   int8_t *trip = nullptr, *cons = nullptr;
   int *closest = nullptr, *aoff = nullptr, *Fn = nullptr, *Tn = nullptr, *d_err = nullptr;
+  int2 *desc = nullptr;
   uint8_t *slot_of = nullptr, *trip_tab = nullptr, *G = nullptr;
   double *E = nullptr, *R = nullptr, *F = nullptr, *T = nullptr;
   // host staging
@@ -46,10 +47,10 @@ struct Scratch {
   std::vector<int> h_n;
 
   void release() {
-    void *p[] = {trip, cons, closest, aoff, Fn, Tn, slot_of, trip_tab, G, E, R, F, T};
+    void *p[] = {trip, cons, closest, aoff, desc, Fn, Tn, slot_of, trip_tab, G, E, R, F, T};
     for (void *x : p)
       if (x) cudaFree(x);
-    trip = cons = nullptr; closest = aoff = Fn = Tn = nullptr; slot_of = trip_tab = G = nullptr;
+    trip = cons = nullptr; closest = aoff = Fn = Tn = nullptr; desc = nullptr; slot_of = trip_tab = G = nullptr;
     E = R = F = T = nullptr;
   }
 
@@ -92,6 +93,12 @@ struct Scratch {
     for (size_t i = 0; i < so.size(); i++) so[i] = (uint8_t)((i & 63) + 1);
     for (int r = 0; r < L; r++) cl[r] = r;
     DK(cudaMemcpy(aoff, eo.data(), eo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    {
+      std::vector<int2> dh(S);
+      for (int s = 0; s < S; s++) dh[s] = make_int2(64 * s, 64);
+      DK(cudaMalloc((void **)&desc, (size_t)S * sizeof(int2)));
+      DK(cudaMemcpy(desc, dh.data(), dh.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
     DK(cudaMemcpy(slot_of, so.data(), so.size(), cudaMemcpyHostToDevice));
     DK(cudaMemcpy(closest, cl.data(), cl.size() * sizeof(int), cudaMemcpyHostToDevice));
     DK(cudaMemset(F, 0, (size_t)S * Ls * sizeof(double)));
@@ -101,7 +108,7 @@ struct Scratch {
   McqStatic statics(int N) const {
     McqStatic st{};
     st.Q = 1; st.S = S; st.L = L; st.Ls = Ls; st.Lg = Lg; st.N = N; st.H = 1;
-    st.G = G; st.aoff = aoff; st.toff = aoff;   // one row of 64 entries per site
+    st.G = G; st.aoff = aoff; st.toff = aoff; st.desc = desc;   // one row of 64 entries per site
     st.query_codon = nullptr;                   // -> always row 0 of the site's block
     return st;
   }

@@ -45,6 +45,7 @@ struct McqStatic {           // device-resident static tables
   const uint8_t *G;          // [Q][S][Lg], states permuted lane-major (see k_gather)
   const int *aoff;           // [S+1] first non-consensus slot of site s in ATAB / ncodon; K_s = aoff[s+1]-aoff[s]
   const int *toff;           // [S+1] offset of site s's block of rows in TAB
+  const int2 *desc;          // [S] {toff[s], K_s}: what a warp needs to stage site s, in one load
   const uint8_t *ncodon;     // [aoff[S]] codon of each non-consensus slot
   const int *nsite;          // [aoff[S]] site of each non-consensus slot
   const uint8_t *cons_codon; // [S]

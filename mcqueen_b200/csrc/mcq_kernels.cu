@@ -401,9 +401,9 @@ __device__ __forceinline__ SiteAhead look_ahead(const McqStatic &st, const uint8
   a.to = 0; a.toff = 0; a.kr = 0;
   if (valid) {
     if (qc) a.to = qc[t];
-    const int a0 = st.aoff[t];
-    a.kr = st.aoff[t + 1] - a0;
-    a.toff = st.toff[t];
+    const int2 d = st.desc[t];     // {offset of the site's block in the table, entries per row}
+    a.toff = d.x;
+    a.kr = d.y;
   }
   return a;
 }
@@ -423,10 +423,11 @@ __device__ __forceinline__ void stage_site(uint8_t *gring, double *ering, int t,
       const int o = (lane + 32 * i) * 16;
       if (o < 64 * NJ) cp_async16(dst + o, src + o);
     }
-    const int kr = sa.kr;
+    const int kr = sa.kr;             // at most 64 entries: two predicated copies, no loop
     const double *row = em.tab + (size_t)sa.toff + (size_t)sa.to * kr;
     double *ed = ering + slot * MCQ_ES;
-    for (int k = lane; k < kr; k += 32) cp_async8(ed + 1 + k, row + k);
+    if (lane < kr) cp_async8(ed + 1 + lane, row + lane);
+    if (lane + 32 < kr) cp_async8(ed + 33 + lane, row + 32 + lane);
     if (lane == 0 && em.ec != nullptr) cp_async8(ed, em.ec + (size_t)q * st.S + t);
   }
   cp_async_commit();
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
     // forward_backward.c:138 divides by N and :141-142 adds then multiplies; here the reciprocal and
     // a fused multiply-add keep the per-site dependency chain short (each one rounding away from
     // the reference's sequence, far inside the tolerance - the order of the sum differs anyway)
-    const double jump = tot * Rs * invN;
+    const double jump = tot * (Rs * invN);
     const double stay = 1 - Rs;
     double la = 0.0, lb = 0.0;     // two partial sums: a shorter dependent chain than one
 #pragma unroll
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
     const double *es = ering + (s % MCQ_RING) * MCQ_ES;
     const double Rn = Rnext;
     Rnext = a.R[s];                             // R[(s-1)+1] for the next iteration
-    const double jump = sx * Rn * invN;         // forward_backward.c:219 (reciprocal: see k_forward)
+    const double jump = sx * (Rn * invN);       // forward_backward.c:219 (reciprocal: see k_forward)
     const double stay = 1 - Rn;
     double locv = 0.0, locy = 0.0, locv2 = 0.0, locy2 = 0.0;
 #pragma unroll
