@@ -172,7 +172,6 @@ enum {
   MCQ_OPT_SPARSE_ESC = 1,  /* 1: an ESC proposal re-evaluates only carriers of that HLA and
                               reuses the cached per-query llk of the others (the reference
                               re-evaluates all, mcmc_moves.c:803; results agree to ~1e-13 rel) */
-  MCQ_OPT_FUSED_ACCEPT = 2 /* reserved */
 };
 int mcq_ctx_set_option(mcq_ctx *ctx, int option, int value);
 

@@ -686,7 +686,7 @@ extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_ll
     case MCQ_PROP_MU:
       {
         KScope ks(c, MCQ_K_EMISSION);
-        CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->NA, (int)c->TL, c->tab, c->atab, c->ec, c->ac,
+        CK(mcq_launch_mu_rescale(make_static(c), c->m, ov.v0, c->NA, c->tab, c->atab, c->ec, c->ac,
                                  c->tab_t, c->atab_t, c->ec_t, c->ac_t, c->stream));
         c->launches++;   // two kernels
       }

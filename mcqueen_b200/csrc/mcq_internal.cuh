@@ -115,7 +115,7 @@ cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
 // create_codon_to_codon_HLA
 cudaError_t mcq_launch_emission_table(const EmisArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_emission_cons(const EmisArgs &a, cudaStream_t stream);
-cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots, int tab_len,
+cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots,
                                   const double *tab, const double *atab, const double *ec, const double *ac,
                                   double *tab_o, double *atab_o, double *ec_o, double *ac_o, cudaStream_t stream);
 cudaError_t mcq_launch_commit_cols(const McqStatic &st, const double *T, const int *Tn, double *F, int *Fn,

@@ -356,10 +356,9 @@ __global__ void __launch_bounds__(256) k_mu_rescale_cons(const McqStatic st, con
   ac_o[idx] = an;
 }
 
-cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots, int tab_len,
+cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots,
                                   const double *tab, const double *atab, const double *ec, const double *ac,
                                   double *tab_o, double *atab_o, double *ec_o, double *ac_o, cudaStream_t stream) {
-  (void)tab_len;
   const unsigned n1 = (unsigned)nslots * 64u, n2 = (unsigned)st.Q * (unsigned)st.S;
   if (n1) k_mu_rescale_table<<<(n1 + 255) / 256, 256, 0, stream>>>(st, m, mu_new, nslots, tab, atab, tab_o, atab_o);
   k_mu_rescale_cons<<<(n2 + 255) / 256, 256, 0, stream>>>(st, m, mu_new, ec, ac, ec_o, ac_o);
