@@ -203,7 +203,7 @@ def run_ref_bench(p, threads, seconds, path=None, total_queries=None):
 # dmodel MCMC steps/s (second half of BASELINE.json's metric): the C driver on the GPU library next
 # to the reference dmodel on the host CPU, same files, same seeds, default move mix with annealing
 # ------------------------------------------------------------------------------------------------
-def mcmc_steps_per_s(workload, steps, ref_steps=12):
+def mcmc_steps_per_s(workload, steps, ref_steps=12, variants=(("gpu", []), ("gpu_sparse_esc", ["--sparse_esc"]))):
     import re
     import shutil
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -217,7 +217,7 @@ def mcmc_steps_per_s(workload, steps, ref_steps=12):
         paths, L, _ = make_chain_inputs(os.path.join(tmp, "in"), workload, seed=SEED, query_model="dsim")
         out["data"] = "queries drawn from the model itself (dsim recipe, mcqueen_b200/synth.py)"
         base = ["-H", paths["hla"], "-l", str(L), "-s", "1000000", paths["ref"], paths["query"]]
-        for key, extra in (("gpu", []), ("gpu_sparse_esc", ["--sparse_esc"])):
+        for key, extra in variants:
             r = subprocess.run([driver, "--seed", "1", "--gsl_seed", "1", "-n", str(steps)] + extra + base +
                                [os.path.join(tmp, key)], capture_output=True, text=True)
             m = re.search(r"MCMC loop: (\d+) steps in ([0-9.]+) s = ([0-9.]+) steps/s", r.stdout)
@@ -486,6 +486,8 @@ def main():
         if world == 1 and not args.no_mcmc:
             ctx.close()          # frees the C4 context before the driver allocates its own
             line["mcmc"] = mcmc_steps_per_s("C2", args.mcmc_steps)
+            # the same driver at the headline shape (no CPU side: the reference would need hours)
+            line["mcmc_c4"] = mcmc_steps_per_s(args.workload, 300, ref_steps=0, variants=(("gpu", []),))
         if world == 1 and args.cpu_seconds > 0:
             ncpu = os.cpu_count() or 1
             v, desc = run_ref_bench(p, ncpu, args.cpu_seconds)
