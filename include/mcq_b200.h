@@ -166,12 +166,20 @@ int mcq_ctx_propose(mcq_ctx *ctx, const mcq_proposal *prop, double *sum_llk);
 int mcq_ctx_accept(mcq_ctx *ctx);
 /* Drop the last proposal (nothing to undo on the device; kept for symmetry). */
 int mcq_ctx_reject(mcq_ctx *ctx);
+/* Complete every refill still owed (MCQ_OPT_LAZY_REFILL): afterwards F and B hold what the
+ * reference's would after its last accept.  mcq_ctx_get_matrix does this itself. */
+int mcq_ctx_flush(mcq_ctx *ctx);
 
 /* Options. */
 enum {
   MCQ_OPT_SPARSE_ESC = 1,  /* 1: an ESC proposal re-evaluates only carriers of that HLA and
                               reuses the cached per-query llk of the others (the reference
                               re-evaluates all, mcmc_moves.c:803; results agree to ~1e-13 rel) */
+  MCQ_OPT_LAZY_REFILL = 2, /* default 1: after an accept the refills of F behind the range and of B
+                              below it (mcmc_moves.c:266-279) are owed per query and completed by the
+                              next evaluation that needs those columns, with the parameters then
+                              current - the same values, computed when first read.  0: refill at
+                              once, the reference's schedule. */
 };
 int mcq_ctx_set_option(mcq_ctx *ctx, int option, int value);
 

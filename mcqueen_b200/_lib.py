@@ -53,6 +53,7 @@ SYMBOLS = {
     "mcq_ctx_propose": (C.c_int, [_V, C.POINTER(McqProposal), c_double_p]),
     "mcq_ctx_accept": (C.c_int, [_V]),
     "mcq_ctx_reject": (C.c_int, [_V]),
+    "mcq_ctx_flush": (C.c_int, [_V]),
     "mcq_ctx_set_option": (C.c_int, [_V, C.c_int, C.c_int]),
     "mcq_ctx_get_matrix": (C.c_int, [_V, C.c_int, C.c_int, _V, _V]),
     "mcq_ctx_get_table": (C.c_int, [_V, C.c_int, C.c_int, _V]),

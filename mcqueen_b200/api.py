@@ -22,6 +22,7 @@ DO_HLA_ESC, DO_HLA_REV, DO_HLA_BOTH, DO_ALL_HLAS = 0, 1, 2, -1   # mcmc_moves.h:
 BUF_F, BUF_B, BUF_TMP_F = 0, 1, 2
 TAB_C2C, TAB_A, TAB_TMP_C2C, TAB_TMP_A = 0, 1, 2, 3
 OPT_SPARSE_ESC = 1
+OPT_LAZY_REFILL = 2
 K_GATHER, K_EMISSION, K_FORWARD, K_BACKWARD, K_COMMIT, K_SUM = range(6)
 
 
@@ -237,6 +238,9 @@ class Context:
 
     def reject(self):
         check(self.lib.mcq_ctx_reject(self._h))
+
+    def flush(self):
+        check(self.lib.mcq_ctx_flush(self._h))
 
     def set_option(self, option, value):
         check(self.lib.mcq_ctx_set_option(self._h, option, value))

@@ -108,11 +108,15 @@ struct mcq_ctx {
   double *tab = nullptr, *atab = nullptr, *ec = nullptr, *ac = nullptr;
   double *tab_t = nullptr, *atab_t = nullptr, *ec_t = nullptr, *ac_t = nullptr;
   double *llk_cur = nullptr, *llk_prop = nullptr, *d_sum = nullptr;
+  int *fv = nullptr, *bv = nullptr;   // per query: F valid up to fv, B valid from bv (lazy refills)
   double *h_sum = nullptr;   // pinned
 
   McqOverride pending{};
   bool has_pending = false;
   int opt_sparse_esc = 0;
+  int opt_lazy = 1;          // MCQ_OPT_LAZY_REFILL
+  // host-side bounds on the per-query validity marks: every fv[q] >= fv_lo, every bv[q] <= bv_hi
+  int fv_lo = -1, bv_hi = 1 << 30;
 
   int timing = 0;            // 0 off, 1 per API call, 2 per kernel launch as well
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
@@ -244,6 +248,7 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   ALLOC(c->m.R, S); ALLOC(c->m.omega, S); ALLOC(c->m.rate_out, S * 64);
   ALLOC(c->m.esc, H * S); ALLOC(c->m.rev, S); ALLOC(c->m.prior, 64);
   ALLOC(c->llk_cur, Q); ALLOC(c->llk_prop, Q); ALLOC(c->d_sum, 1);
+  ALLOC(c->fv, Q); ALLOC(c->bv, Q);
   CK(cudaMallocHost((void **)&c->h_sum, sizeof(double)));
   CK(cudaMallocHost((void **)&c->h_err, sizeof(int)));
   *c->h_err = 0;
@@ -261,7 +266,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   void *ptrs[] = {c->desc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
-                  c->llk_cur, c->llk_prop, c->d_sum, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
+                  c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
@@ -339,6 +344,11 @@ extern "C" int mcq_ctx_last_timing(const mcq_ctx *c, float *ms, int *launches) {
 extern "C" int mcq_ctx_set_option(mcq_ctx *c, int option, int value) {
   REQUIRE(c, "null context");
   if (option == MCQ_OPT_SPARSE_ESC) { c->opt_sparse_esc = value; return 0; }
+  if (option == MCQ_OPT_LAZY_REFILL) {
+    if (!value && c->have_state && mcq_ctx_flush(c)) return 1;   // leave lazy mode with F and B complete
+    c->opt_lazy = value;
+    return 0;
+  }
   return mcq_fail(__FILE__, __LINE__, "unknown option");
 }
 
@@ -534,10 +544,12 @@ static int run_emission(mcq_ctx *c, int start, int end, int which_hla, int mode,
 
 static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int start, int end, const double *Fin, const int *Fn_in,
                        double *Fout, int *Fn_out, int llk_mode, double *llk_out, int r_site, double r_value,
-                       bool sparse, int hla) {
+                       bool sparse, int hla, bool lazy = false) {
   FwdArgs a;
   a.st = make_static(c);
   a.em.tab = tab; a.em.ec = ec; a.R = c->m.R; a.r_site = r_site; a.r_value = r_value;
+  a.em_pre.tab = c->tab; a.em_pre.ec = c->ec;
+  a.fv = lazy ? c->fv : nullptr;   // catch up F before `start` where it is stale
   a.Fin = Fin; a.Fn_in = Fn_in; a.Fout = Fout; a.Fn_out = Fn_out;
   a.start = start; a.end = end; a.llk_mode = llk_mode;
   a.B = c->B; a.Bn = c->Bn; a.llk_out = llk_out; a.llk_keep = c->llk_cur;
@@ -548,11 +560,15 @@ static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int star
   return 0;
 }
 
-static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream_t stream = nullptr) {
+// lazy: every query continues from its own bv mark down to column `bottom`; otherwise the reference's
+// update_B(update) down to column 0
+static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream_t stream = nullptr,
+                        bool lazy = false, int bottom = 0) {
   if (stream == nullptr) stream = c->stream;
   BwdArgs a;
   a.st = make_static(c);
   a.em.tab = c->tab; a.em.ec = c->ec; a.R = c->m.R; a.B = c->B; a.Bn = c->Bn; a.update = update;
+  a.bottom = bottom; a.bv = lazy ? c->bv : nullptr;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
   if (stream != c->stream) {          // beside the main stream: counted, not bracketed
     c->launches++;
@@ -603,6 +619,38 @@ static int reduce_llk(mcq_ctx *c, const double *per_query, double *out) {
     CK(cudaSetDevice((c)->d.device));                                              \
   } while (0)
 
+// validity marks of F and B (lazy refills): on the device per query, on the host as bounds
+static int set_marks(mcq_ctx *c, int f, int b, bool sparse, int hla) {
+  CK(mcq_launch_set_valid(c->fv, c->bv, c->d.num_query, c->d.num_hla_types, f, b, sparse ? c->hla : nullptr, hla, c->stream));
+  c->launches++;
+  if (f >= -1) c->fv_lo = sparse ? (c->fv_lo < f ? c->fv_lo : f) : f;
+  if (b >= 0) c->bv_hi = sparse ? (c->bv_hi > b ? c->bv_hi : b) : b;
+  return 0;
+}
+
+// Complete F (to the last site) and B (down to site 0) for every query whose refill is still owed.
+static int flush_lazy(mcq_ctx *c) {
+  const int S = c->d.num_sites;
+  if (c->fv_lo < S - 1) {
+    if (run_forward(c, c->tab, c->ec, S, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, false, 0, true)) return 1;
+    c->fv_lo = S - 1;
+  }
+  if (c->bv_hi > 0) {
+    if (run_backward(c, S - 1, false, 0, nullptr, true, 0)) return 1;
+    c->bv_hi = 0;
+  }
+  return 0;
+}
+
+extern "C" int mcq_ctx_flush(mcq_ctx *c) {
+  READY(c);
+  REQUIRE(c->have_state, "mcq_ctx_init_state has not been called");
+  CallScope scope(c);
+  if (flush_lazy(c)) return 1;
+  if (!c->timing) CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 extern "C" int mcq_ctx_emission(mcq_ctx *c, int start, int end, int which_hla, int mode) {
   READY(c);
   REQUIRE(start >= 0 && end < c->d.num_sites && start <= end, "site range");
@@ -621,6 +669,7 @@ extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
   McqOverride none{}; none.kind = -1;
   if (with_emission && run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
   if (run_forward(c, c->tab, c->ec, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (set_marks(c, S - 1, -1, false, 0)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->has_pending = false;
   return 0;
@@ -630,6 +679,7 @@ extern "C" int mcq_ctx_backward_fill(mcq_ctx *c) {
   READY(c);
   CallScope scope(c);
   if (run_backward(c, c->d.num_sites - 1, false, 0)) return 1;
+  if (set_marks(c, -2, 0, false, 0)) return 1;
   if (!c->timing) CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -642,6 +692,7 @@ extern "C" int mcq_ctx_init_state(mcq_ctx *c, double *llk) {
   if (run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
   if (run_forward(c, c->tab, c->ec, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
   if (run_backward(c, S - 1, false, 0)) return 1;
+  if (set_marks(c, S - 1, 0, false, 0)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->have_state = true;
   c->has_pending = false;
@@ -651,6 +702,47 @@ extern "C" int mcq_ctx_init_state(mcq_ctx *c, double *llk) {
 // ------------------------------------------------------------------------------------------
 // proposals
 // ------------------------------------------------------------------------------------------
+// Columns ov.start..ov.end of a proposal into T and its per-query log-likelihood (the dot with B at
+// ov.end, mcmc_moves.c:220-223) into llk_prop.  With lazy refills the columns of F before the range and
+// of B down to ov.end are completed first where an earlier accept left them owed: F inside the forward
+// kernel itself, B by a backward launch beside it on the second stream, joined by k_dot.
+static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const McqOverride &ov, int r_site,
+                      double r_value, bool sparse) {
+  const bool need_f = c->opt_lazy && c->fv_lo < ov.start - 1;
+  const bool need_b = c->opt_lazy && c->bv_hi > ov.end;
+  if (!need_b) {
+    if (run_forward(c, tab, ec, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, r_site, r_value,
+                    sparse, ov.hla, need_f)) return 1;
+    if (need_f && !sparse) c->fv_lo = ov.start - 1;
+    return 0;
+  }
+  const bool dual = c->timing < 2;
+  if (dual) {
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    if (run_backward(c, 0, sparse, ov.hla, c->stream2, true, ov.end)) return 1;
+    CK(cudaEventRecord(c->ev_join, c->stream2));
+  } else if (run_backward(c, 0, sparse, ov.hla, nullptr, true, ov.end)) return 1;
+  if (run_forward(c, tab, ec, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 0, nullptr, r_site, r_value, sparse,
+                  ov.hla, need_f)) return 1;
+  if (dual) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  DotArgs d;
+  d.st = make_static(c);
+  d.T = c->T; d.Tn = c->Tn; d.B = c->B; d.Bn = c->Bn; d.site = ov.end;
+  d.llk_out = c->llk_prop; d.llk_keep = c->llk_cur;
+  d.active = sparse ? c->hla : nullptr; d.active_hla = ov.hla;
+  d.logBIG = c->logBIG;
+  {
+    KScope ks(c, MCQ_K_SUM);
+    CK(mcq_launch_dot(d, c->stream));
+  }
+  if (!sparse) {          // every query is now valid this far; a sparse evaluation leaves the bounds alone
+    if (need_f) c->fv_lo = ov.start - 1;
+    c->bv_hi = ov.end;
+  }
+  return 0;
+}
+
 extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_llk) {
   READY(c);
   REQUIRE(p, "null proposal");
@@ -665,23 +757,21 @@ extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_ll
   switch (p->kind) {
     case MCQ_PROP_REC:
       REQUIRE(ov.start == ov.end, "REC proposal covers one site");
-      if (run_forward(c, c->tab, c->ec, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, ov.start, ov.v0, false, 0)) return 1;
+      if (eval_range(c, c->tab, c->ec, ov, ov.start, ov.v0, false)) return 1;
       break;
     case MCQ_PROP_SEL:
       REQUIRE(ov.start == ov.end, "SEL proposal covers one site");
       if (run_emission(c, ov.start, ov.end, -1, 2, ov, cur_set(c), tmp_set(c))) return 1;
-      if (run_forward(c, c->tab_t, c->ec_t, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      if (eval_range(c, c->tab_t, c->ec_t, ov, -1, 0.0, false)) return 1;
       break;
-    case MCQ_PROP_ESC: {
+    case MCQ_PROP_ESC:
       REQUIRE(ov.hla >= 0 && ov.hla < c->d.num_hla_types, "ESC proposal HLA index");
       if (run_emission(c, ov.start, ov.end, ov.hla, 0, ov, cur_set(c), tmp_set(c))) return 1;
-      const bool sparse = c->opt_sparse_esc != 0;
-      if (run_forward(c, c->tab, c->ec_t, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, sparse, ov.hla)) return 1;
+      if (eval_range(c, c->tab, c->ec_t, ov, -1, 0.0, c->opt_sparse_esc != 0)) return 1;
       break;
-    }
     case MCQ_PROP_REV:
       if (run_emission(c, ov.start, ov.end, -1, 1, ov, cur_set(c), tmp_set(c))) return 1;
-      if (run_forward(c, c->tab_t, c->ec, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      if (eval_range(c, c->tab_t, c->ec, ov, -1, 0.0, false)) return 1;
       break;
     case MCQ_PROP_MU:
       {
@@ -722,7 +812,9 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
     swap_ptr(c->F, c->T); swap_ptr(c->Fn, c->Tn); swap_ptr(c->tab, c->tab_t); swap_ptr(c->atab, c->atab_t);
     swap_ptr(c->ec, c->ec_t); swap_ptr(c->ac, c->ac_t);
     c->m.mu = ov.v0;
-    if (run_backward(c, S - 1, false, 0)) return 1;
+    if (c->opt_lazy) {
+      if (set_marks(c, S - 1, S, false, 0)) return 1;    // F complete, all of B owed
+    } else if (run_backward(c, S - 1, false, 0)) return 1;
   } else {
     const bool sparse = (ov.kind == MCQ_PROP_ESC) && c->opt_sparse_esc != 0;
     {
@@ -745,18 +837,23 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
       KScope ks(c, MCQ_K_COMMIT);
       CK(mcq_launch_commit_cols(st, c->T, c->Tn, c->F, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
     }
-    // F after the range and B from the range down to 0 do not depend on each other: two streams
-    const bool dual = c->timing < 2 && ov.end + 1 < S;
-    if (dual) {
-      CK(cudaEventRecord(c->ev_fork, c->stream));
-      CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-      if (run_backward(c, ov.end, sparse, ov.hla, c->stream2)) return 1;
-      CK(cudaEventRecord(c->ev_join, c->stream2));
+    if (c->opt_lazy) {
+      // the refills of mcmc_moves.c:266-279 are owed, not run: the next evaluation completes what it needs
+      if (set_marks(c, ov.end, ov.end, sparse, ov.hla)) return 1;
+    } else {
+      // F after the range and B from the range down to 0 do not depend on each other: two streams
+      const bool dual = c->timing < 2 && ov.end + 1 < S;
+      if (dual) {
+        CK(cudaEventRecord(c->ev_fork, c->stream));
+        CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        if (run_backward(c, ov.end, sparse, ov.hla, c->stream2)) return 1;
+        CK(cudaEventRecord(c->ev_join, c->stream2));
+      }
+      if (ov.end + 1 < S)
+        if (run_forward(c, c->tab, c->ec, ov.end + 1, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
+      if (dual) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+      else if (run_backward(c, ov.end, sparse, ov.hla)) return 1;
     }
-    if (ov.end + 1 < S)
-      if (run_forward(c, c->tab, c->ec, ov.end + 1, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
-    if (dual) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    else if (run_backward(c, ov.end, sparse, ov.hla)) return 1;
   }
   swap_ptr(c->llk_cur, c->llk_prop);
   c->has_pending = false;
@@ -774,6 +871,7 @@ extern "C" int mcq_ctx_get_matrix(mcq_ctx *c, int which, int q, double *out, int
   const int S = c->d.num_sites, L = c->d.closest_n, Ls = c->Ls;
   const double *src = which == MCQ_BUF_F ? c->F : which == MCQ_BUF_B ? c->B : c->T;
   const int *nsrc = which == MCQ_BUF_F ? c->Fn : which == MCQ_BUF_B ? c->Bn : c->Tn;
+  if (c->have_state && c->have_params && which != MCQ_BUF_TMP_F && flush_lazy(c)) return 1;
   CK(cudaStreamSynchronize(c->stream));
   if (out) {
     std::vector<double> slab((size_t)S * Ls);

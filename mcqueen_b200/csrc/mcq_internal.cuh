@@ -66,9 +66,17 @@ struct McqOverride {
   double v0, v1;
 };
 
+// F and B are kept valid LAZILY: per query, F[q][s] is current for s <= fv[q] and B[q][s] for
+// s >= bv[q].  An accepted proposal on sites c..d sets fv = bv = d for the queries it touched; the next
+// evaluation that needs F[c'-1] or B[d'] first catches the missing columns up (k_forward runs the sites
+// fv+1 .. start-1 with the current parameters before the proposal's own range; k_backward runs bv-1
+// down to the requested column).  The reference refills both matrices completely after every accept
+// (mcmc_moves.c:261-279); the values are the same, they are just computed when first needed.
 struct FwdArgs {
   McqStatic st;
   McqEmis em;                // emission rows read for sites start..end
+  McqEmis em_pre;            // current emission rows, for the catch-up sites before `start`
+  int *fv;                   // [Q] last valid column of Fin per query; nullptr = column start-1 is valid
   const double *R;
   int r_site; double r_value;     // R override at one site (-1 = none)
   const double *Fin; const int *Fn_in;
@@ -88,8 +96,21 @@ struct BwdArgs {
   McqEmis em;
   const double *R;
   double *B; int *Bn;
-  int update;                // start column (S-1 = fresh)
+  int update;                // first column to compute when bv == nullptr (S-1 = fresh start)
+  int bottom;                // last column to compute (0 = down to the first site)
+  int *bv;                   // [Q] first valid column of B per query (S = none); nullptr = use `update`
   const uint8_t *active; int active_hla;
+};
+
+struct DotArgs {             // per-query log-likelihood from a proposal column and the backward column
+  McqStatic st;
+  const double *T; const int *Tn;
+  const double *B; const int *Bn;
+  int site;
+  double *llk_out;
+  const double *llk_keep;
+  const uint8_t *active; int active_hla;
+  double logBIG;
 };
 
 struct EmisArgs {
@@ -111,6 +132,11 @@ cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, co
                               cudaStream_t stream);
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
+cudaError_t mcq_launch_dot(const DotArgs &a, cudaStream_t stream);
+// fv[q] := f, bv[q] := b for the queries selected by (active, hla) (all when active == nullptr); a
+// negative value leaves that array untouched
+cudaError_t mcq_launch_set_valid(int *fv, int *bv, int Q, int H, int f, int b, const uint8_t *active, int hla,
+                                 cudaStream_t stream);
 // the reversion part (rows of non-consensus codons) / the escape part (the consensus row) of
 // create_codon_to_codon_HLA
 cudaError_t mcq_launch_emission_table(const EmisArgs &a, cudaStream_t stream);

@@ -461,7 +461,7 @@ struct LaneSlots {
 // next site's recombination sum); one 16-byte streaming store of F per lane per j (512 contiguous
 // bytes per warp instruction).  FULL: Ls == 64*NJ, no row-bound predicates.
 // ------------------------------------------------------------------------------------------
-template <int NJ, bool FULL>
+template <int NJ, bool FULL, bool PRE>
 __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
   __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
@@ -476,8 +476,18 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   const size_t qoff = (size_t)q * S * Ls;
   const uint8_t *__restrict__ Gq = a.st.G + (size_t)q * S * (64 * NJ);
   const uint8_t *__restrict__ qc = a.st.query_codon ? a.st.query_codon + (size_t)q * S : nullptr;
-  double *__restrict__ Fo = a.Fout + qoff + 2 * lane;
-  int *__restrict__ Fno = a.Fn_out + (size_t)q * S;
+  // sites before `start` that are not valid yet are caught up first, with the current rows, into Fin
+  // (PRE: the variant launched when the host knows of owed columns; the other one carries none of this)
+  int s0 = a.start;
+  if (PRE) {
+    const int v = a.fv[q];
+    if (v < a.start - 1) s0 = v + 1;
+  }
+  const bool caught_up = PRE && s0 < a.start;
+  double *Fo = a.Fout + qoff + 2 * lane;
+  double *Fc = const_cast<double *>(a.Fin) + qoff + 2 * lane;
+  int *Fno = a.Fn_out + (size_t)q * S;
+  int *Fnc = const_cast<int *>(a.Fn_in) + (size_t)q * S;
   uint8_t *gring = &s_g[wib][0][0];
   double *ering = &s_e[wib][0][0];
   if (lane < MCQ_RING) ering[lane * MCQ_ES + MCQ_NOSLOT] = 0.0;   // the "no such codon" emission
@@ -487,15 +497,16 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   for (int j = 0; j < NJ; j++) inrow[j] = FULL || (64 * j + 2 * lane < Ls);
 
   // prologue: rows of the first MCQ_PF sites of the range
-  int t = a.start;
+  int t = s0;
 #pragma unroll
   for (int i = 0; i < MCQ_PF; i++, t++)
-    stage_site<NJ>(gring, ering, t, t <= a.end, look_ahead(a.st, qc, t, t <= a.end), q, a.st, a.em, Gq, lane);
-  SiteAhead ahead = look_ahead(a.st, qc, t, t <= a.end);   // site t = start + MCQ_PF
+    stage_site<NJ>(gring, ering, t, t <= a.end, look_ahead(a.st, qc, t, t <= a.end), q, a.st,
+                   (PRE && t < a.start) ? a.em_pre : a.em, Gq, lane);
+  SiteAhead ahead = look_ahead(a.st, qc, t, t <= a.end);   // site t = s0 + MCQ_PF
   const double invN = 1.0 / (double)a.st.N;
 
   double p0[NJ], p1[NJ];   // the running column
-  int s = a.start, cnt;
+  int s = s0, cnt;
   double tot;
 
   if (s == 0) {
@@ -505,29 +516,30 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
     {
       const SiteAhead cur = ahead;
       ahead = look_ahead(a.st, qc, t + 1, t + 1 <= a.end);
-      stage_site<NJ>(gring, ering, t, t <= a.end, cur, q, a.st, a.em, Gq, lane);
+      stage_site<NJ>(gring, ering, t, t <= a.end, cur, q, a.st, (PRE && t < a.start) ? a.em_pre : a.em, Gq, lane);
       t++;
     }
     LaneSlots<NJ> g;
     g.load(gring, lane);              // ring slot 0
     const double *es = ering;
+    double *F0 = (PRE && 0 < a.start) ? Fc : Fo;      // column 0 belongs to the catch-up when start > 0
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       p0[j] = es[g.first(j)]; p1[j] = es[g.second(j)];
-      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Fo + 64 * j), make_double2(p0[j], p1[j]));
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(F0 + 64 * j), make_double2(p0[j], p1[j]));
       loc += p0[j]; loc += p1[j];
     }
     cnt = 0;
     if (lane == 0) {
+      // update_F with start 0 zeroes both counters of column 0 (forward_backward.c:108-109)
       Fno[0] = 0;
-      // update_F with start 0 also zeroes the input counter (forward_backward.c:109)
-      if (a.Fn_in != nullptr) const_cast<int *>(a.Fn_in)[(size_t)q * S] = 0;
+      if (a.Fn_in != nullptr) Fnc[0] = 0;
     }
     tot = warp_sum(loc);
     s = 1;
   } else {
-    const double *__restrict__ Fi = a.Fin + qoff + (size_t)(s - 1) * Ls + 2 * lane;
+    const double *__restrict__ Fi = Fc + (size_t)(s - 1) * Ls;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
@@ -538,7 +550,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
       }
       loc += p0[j]; loc += p1[j];
     }
-    cnt = a.Fn_in[(size_t)q * S + s - 1];
+    cnt = Fnc[s - 1];
     tot = warp_sum(loc);
   }
 
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
     {
       const SiteAhead cur = ahead;
       ahead = look_ahead(a.st, qc, t + 1, t + 1 <= a.end);
-      stage_site<NJ>(gring, ering, t, t <= a.end, cur, q, a.st, a.em, Gq, lane);
+      stage_site<NJ>(gring, ering, t, t <= a.end, cur, q, a.st, (PRE && t < a.start) ? a.em_pre : a.em, Gq, lane);
       t++;
     }
     LaneSlots<NJ> g;
@@ -577,13 +589,15 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
       for (int j = 0; j < NJ; j++) { p0[j] *= MCQ_BIG; p1[j] *= MCQ_BIG; }
       tot *= MCQ_BIG;
     }
-    double *__restrict__ Fs = Fo + (size_t)s * Ls;
+    const bool pre = PRE && s < a.start;        // a catch-up site: it goes into the current matrix
+    double *__restrict__ Fs = (pre ? Fc : Fo) + (size_t)s * Ls;
 #pragma unroll
     for (int j = 0; j < NJ; j++)
       if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(p0[j], p1[j]));
-    if (lane == 0) Fno[s] = cnt;
+    if (lane == 0) (pre ? Fnc : Fno)[s] = cnt;
   }
   cp_async_wait<0>();
+  if (caught_up && lane == 0) a.fv[q] = a.start - 1;
 
   // K6 epilogue: the per-query log-likelihood at the last column of the range
   if (a.llk_mode != 0) {
@@ -610,8 +624,14 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
 template <int NJ>
 static cudaError_t launch_forward_nj(const FwdArgs &a, cudaStream_t stream) {
   const unsigned blocks = (unsigned)((a.st.Q + MCQ_WPB - 1) / MCQ_WPB);
-  if (a.st.Ls == 64 * NJ) k_forward<NJ, true><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
-  else k_forward<NJ, false><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+  const bool full = a.st.Ls == 64 * NJ;
+  if (a.fv != nullptr) {
+    if (full) k_forward<NJ, true, true><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+    else k_forward<NJ, false, true><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+  } else {
+    if (full) k_forward<NJ, true, false><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+    else k_forward<NJ, false, false><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -661,6 +681,12 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
 
   double b0[NJ], b1[NJ], e0[NJ], e1[NJ];
   int s = a.update, cnt;
+  const int bottom = a.bottom;
+  if (a.bv != nullptr) {
+    const int v = a.bv[q];
+    if (v <= bottom) return;                    // already valid down to the requested column
+    s = v - 1;
+  }
   if (s == S - 1) {                             // forward_backward.c:197-203
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
@@ -681,14 +707,17 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
     }
     cnt = Bnq[s + 1];
   }
-  if (s < 0) return;
+  if (s < bottom) {
+    if (a.bv != nullptr && lane == 0) a.bv[q] = bottom;
+    return;
+  }
 
-  // rows are consumed in the order s+1, s, s-1, ..., 0
+  // rows are consumed in the order s+1, s, s-1, ..., bottom
   int t = s + 1;
 #pragma unroll
   for (int i = 0; i < MCQ_PF; i++, t--)
-    stage_site<NJ>(gring, ering, t, t >= 0, look_ahead(a.st, qc, t, t >= 0), q, a.st, a.em, Gq, lane);
-  SiteAhead ahead = look_ahead(a.st, qc, t, t >= 0);
+    stage_site<NJ>(gring, ering, t, t >= bottom, look_ahead(a.st, qc, t, t >= bottom), q, a.st, a.em, Gq, lane);
+  SiteAhead ahead = look_ahead(a.st, qc, t, t >= bottom);
   const double invN = 1.0 / (double)a.st.N;
 
   // emission at s+1 and sx
@@ -698,8 +727,8 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
     __syncwarp();
     {
       const SiteAhead cur = ahead;
-      ahead = look_ahead(a.st, qc, t - 1, t - 1 >= 0);
-      stage_site<NJ>(gring, ering, t, t >= 0, cur, q, a.st, a.em, Gq, lane);
+      ahead = look_ahead(a.st, qc, t - 1, t - 1 >= bottom);
+      stage_site<NJ>(gring, ering, t, t >= bottom, cur, q, a.st, a.em, Gq, lane);
       t--;
     }
     LaneSlots<NJ> g;
@@ -715,13 +744,13 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   }
 
   double Rnext = a.R[s + 1];
-  for (; s >= 0; --s) {
+  for (; s >= bottom; --s) {
     cp_async_wait<MCQ_PF - 1>();   // rows of site s
     __syncwarp();
     {
       const SiteAhead cur = ahead;
-      ahead = look_ahead(a.st, qc, t - 1, t - 1 >= 0);
-      stage_site<NJ>(gring, ering, t, t >= 0, cur, q, a.st, a.em, Gq, lane);
+      ahead = look_ahead(a.st, qc, t - 1, t - 1 >= bottom);
+      stage_site<NJ>(gring, ering, t, t >= bottom, cur, q, a.st, a.em, Gq, lane);
       t--;
     }
     LaneSlots<NJ> g;
@@ -762,6 +791,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
     if (lane == 0) Bnq[s] = cnt;
   }
   cp_async_wait<0>();
+  if (a.bv != nullptr && lane == 0) a.bv[q] = bottom;
 }
 
 template <int NJ>
@@ -781,6 +811,52 @@ cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream) {
     case 16: return launch_backward_nj<16>(a, stream);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: per-query log-likelihood of a proposal from its last forward column and the backward column at
+// the same site (mcmc_moves.c:220-223): one warp per query.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dot(const DotArgs a) {
+  const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= a.st.Q) return;
+  if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) {
+    if (lane == 0) a.llk_out[q] = a.llk_keep[q];
+    return;
+  }
+  const int S = a.st.S, Ls = a.st.Ls;
+  const size_t col = ((size_t)q * S + a.site) * Ls;
+  const double2 *__restrict__ t = reinterpret_cast<const double2 *>(a.T + col);
+  const double2 *__restrict__ b = reinterpret_cast<const double2 *>(a.B + col);
+  double loc = 0.0;          // the same lane mapping and order as the epilogue of k_forward
+  for (int i = lane; i < Ls / 2; i += 32) {
+    const double2 x = t[i], y = b[i];
+    loc += x.x * y.x; loc += x.y * y.y;
+  }
+  const double dot = warp_sum(loc);
+  if (lane == 0)
+    a.llk_out[q] = log(dot) - (a.Tn[(size_t)q * S + a.site] + a.Bn[(size_t)q * S + a.site]) * a.logBIG;
+}
+
+cudaError_t mcq_launch_dot(const DotArgs &a, cudaStream_t stream) {
+  k_dot<<<(unsigned)(((size_t)a.st.Q * 32 + 127) / 128), 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_set_valid(int *fv, int *bv, int Q, int H, int f, int b,
+                                                   const uint8_t *__restrict__ active, int hla) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  if (active != nullptr && active[(size_t)q * H + hla] == 0) return;
+  if (f >= -1 && fv != nullptr) fv[q] = f;
+  if (b >= 0 && bv != nullptr) bv[q] = b;
+}
+
+cudaError_t mcq_launch_set_valid(int *fv, int *bv, int Q, int H, int f, int b, const uint8_t *active, int hla,
+                                 cudaStream_t stream) {
+  k_set_valid<<<(Q + 255) / 256, 256, 0, stream>>>(fv, bv, Q, H, f, b, active, hla);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -350,7 +350,8 @@ static void move_mutation(Chain *c, double temperature)
 static int chain_length = 50000, sample_rate = 100, closest_n = 100, runtime_hours = 0;
 static const char *ref_path, *query_path, *out_dir, *hla_path, *cons_path;
 static bool separate_reference_set = true, no_hla = false, no_rev = false, no_rec = false, no_anneal = false;
-static bool opt_sample_prior = false, opt_sparse = false, runtime_set = false, states_set = false, opt_nccl = false;
+static bool opt_sample_prior = false, opt_sparse = false, runtime_set = false, states_set = false, opt_nccl = false,
+            opt_eager = false;
 static int opt_omega_prior = MCQ_PRIOR_EXPONENTIAL, opt_esc_prior = MCQ_PRIOR_LOG_NORMAL;
 static int opt_rev_prior = MCQ_PRIOR_LOG_NORMAL, opt_device = -1;
 static long opt_seed = -1, opt_gsl_seed = -1;
@@ -365,7 +366,8 @@ static void usage(void)
           "  -q self-reference mode  -i no HLA inference  -j no reversion inference  -o no recombination\n"
           "  -v/-e/-w omega prior gamma/log-normal/uniform   -g/-k/-f escape prior gamma/normal/flat\n"
           "  -a/-d/-u reversion prior gamma/normal/flat   -b sample the prior   -z no simulated annealing\n"
-          "  --seed N --gsl_seed N (default: clock)  --device D  --sparse_esc  --trace FILE  --nccl\n");
+          "  --seed N --gsl_seed N (default: clock)  --device D  --sparse_esc  --trace FILE  --nccl\n"
+          "  --eager_refill  refill F and B at every accept (the reference's schedule) instead of when next read\n");
   exit(EXIT_FAILURE);
 }
 
@@ -386,7 +388,7 @@ static void parse(int argc, char **argv)
       {"no_simulated_annealing", no_argument, NULL, 'z'}, {"seed", required_argument, NULL, 1001},
       {"gsl_seed", required_argument, NULL, 1002}, {"device", required_argument, NULL, 1003},
       {"sparse_esc", no_argument, NULL, 1004}, {"trace", required_argument, NULL, 1005},
-      {"nccl", no_argument, NULL, 1006}, {NULL, 0, NULL, 0}};
+      {"nccl", no_argument, NULL, 1006}, {"eager_refill", no_argument, NULL, 1007}, {NULL, 0, NULL, 0}};
   int o;
   while((o = getopt_long(argc, argv, "H:n:s:t:c:r:l:qijovewgkfadubz", lo, NULL)) != -1) {
     switch(o) {
@@ -418,6 +420,7 @@ static void parse(int argc, char **argv)
       case 1004: opt_sparse = true; break;
       case 1005: trace_path = optarg; break;
       case 1006: opt_nccl = true; break;
+      case 1007: opt_eager = true; break;
       default: usage();
     }
   }
@@ -634,6 +637,7 @@ int main(int argc, char **argv)
   mcq_params prm = {c.mu, kappa, phi, prior, c.R, c.omega, rate_out, c.esc, c.rev};
   CHECK(mcq_ctx_set_params(c.ctx, &prm));
   if(opt_sparse) CHECK(mcq_ctx_set_option(c.ctx, MCQ_OPT_SPARSE_ESC, 1));
+  if(opt_eager) CHECK(mcq_ctx_set_option(c.ctx, MCQ_OPT_LAZY_REFILL, 0));
   if(world > 1 && !opt_nccl) {
     /* shard totals are exchanged by NVLink peer stores inside the reduction kernel */
     unsigned char *handles = malloc((size_t)64 * world);

@@ -99,14 +99,16 @@ def _moves(p, rng):
     return out
 
 
-@pytest.mark.parametrize("sparse", [0, 1])
-def test_proposals_and_accepts_track_the_oracle(api, sparse):
+@pytest.mark.parametrize("sparse,lazy", [(0, 1), (1, 1), (0, 0), (1, 0)])
+def test_proposals_and_accepts_track_the_oracle(api, sparse, lazy):
     """A scripted chain: every proposal's total matches, rejected ones leave no trace, accepted ones
-    leave the same F/B/emission state as the reference's accept path."""
+    leave the same F/B/emission state as the reference's accept path - whether the refills after an
+    accept run at once (lazy=0, the reference's schedule) or when first needed (lazy=1, the default)."""
     p = make_problem("toy", gaps=True)
     cpu = CpuState(checker(), p)
     ctx = api.Context.from_problem(p)
     ctx.set_option(api.OPT_SPARSE_ESC, sparse)
+    ctx.set_option(api.OPT_LAZY_REFILL, lazy)
     ctx.init_state()
     rng = np.random.default_rng(3)
     for rnd in range(3):
@@ -125,6 +127,42 @@ def test_proposals_and_accepts_track_the_oracle(api, sparse):
         assert np.array_equal(prm["esc"], cpu.esc) and np.array_equal(prm["rev"], cpu.rev[0])
         assert np.array_equal(prm["rate_out"], cpu.rate_out) and prm["mu"] == cpu.mu
     ctx.close()
+
+
+@pytest.mark.parametrize("sparse", [0, 1])
+def test_lazy_refills_are_bit_identical_to_eager(api, sparse):
+    """Owed refills (MCQ_OPT_LAZY_REFILL) compute the columns the reference would have computed at the
+    accept, with the same kernels' arithmetic: every proposal total, every per-query value and the final
+    F/B matrices are bit-identical to the eager schedule over a random chain with many accepts."""
+    p = make_problem("toy", gaps=True)
+    ctxs = []
+    for lazy in (0, 1):
+        c = api.Context.from_problem(p)
+        c.set_option(api.OPT_SPARSE_ESC, sparse)
+        c.set_option(api.OPT_LAZY_REFILL, lazy)
+        c.init_state()
+        ctxs.append(c)
+    eager, lz = ctxs
+    rng = np.random.default_rng(11)
+    for step in range(120):
+        mv = _moves(p, rng)[int(rng.integers(0, 9))]
+        a, b = eager.propose(**mv), lz.propose(**mv)
+        assert a == b, (step, mv, a, b)
+        assert np.array_equal(eager.query_llk(True), lz.query_llk(True)), (step, mv)
+        if rng.random() < 0.6:
+            eager.accept(); lz.accept()
+        else:
+            eager.reject(); lz.reject()
+        if step % 40 == 39:
+            for q in (0, 5, p.Q - 1):
+                for which in (api.BUF_F, api.BUF_B):
+                    (m0, n0), (m1, n1) = eager.matrix(which, q), lz.matrix(which, q)
+                    assert np.array_equal(n0, n1) and np.array_equal(m0, m1), (step, which, q)
+    lz.set_option(api.OPT_LAZY_REFILL, 0)      # leaving lazy mode completes what is owed
+    mv = dict(kind=REC, start=3, value0=0.03)
+    assert eager.propose(**mv) == lz.propose(**mv)
+    for c in ctxs:
+        c.close()
 
 
 def test_dropin_symbols_match(api):
