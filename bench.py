@@ -416,6 +416,12 @@ def main():
             return best
 
         cells = p.Q * S * L
+        # the same evaluation without writing F (mcq_ctx_llk_only): the recursion then runs at the
+        # instruction-issue / FP64 rate, 1 B of G per cell from HBM
+        t = timed(lambda: ctx.llk_only(True))
+        extras["llk_only_ms"] = t
+        extras["llk_only_cells_per_s"] = cells / t * 1e3
+        ctx.init_state()
         t = timed(ctx.backward_fill)
         extras["backward_fill_cells_per_s"] = cells / t * 1e3
         w0, w1 = S // 3, S // 3 + S // 6 - 1
@@ -487,7 +493,9 @@ def main():
             ctx.close()          # frees the C4 context before the driver allocates its own
             line["mcmc"] = mcmc_steps_per_s("C2", args.mcmc_steps)
             # the same driver at the headline shape (no CPU side: the reference would need hours)
-            line["mcmc_c4"] = mcmc_steps_per_s(args.workload, 300, ref_steps=0, variants=(("gpu", []),))
+            line["mcmc_c4"] = mcmc_steps_per_s(args.workload, 600, ref_steps=0,
+                                               variants=(("gpu", []), ("gpu_sparse_esc", ["--sparse_esc"]),
+                                                         ("gpu_eager_refill", ["--eager_refill"])))
         if world == 1 and args.cpu_seconds > 0:
             ncpu = os.cpu_count() or 1
             v, desc = run_ref_bench(p, ncpu, args.cpu_seconds)

@@ -134,6 +134,12 @@ int mcq_ctx_init_state(mcq_ctx *ctx, double *llk);
  * rebuilds the emission table first. This is the "full likelihood evaluation" of the headline
  * metric. */
 int mcq_ctx_full_llk(mcq_ctx *ctx, int with_emission, double *llk);
+/* The same value as mcq_ctx_full_llk without writing F: the forward recursion keeps each query's
+ * running column in registers and only the per-query log-likelihoods leave the SMs (what a caller
+ * needs when it evaluates parameters it will not propose moves from; mutation_move's whole-genome
+ * proposal, mcmc_moves.c:1124-1134, is evaluated this way).  with_emission != 0 rebuilds the
+ * emission table first and marks F and B as owed (see MCQ_OPT_LAZY_REFILL). */
+int mcq_ctx_llk_only(mcq_ctx *ctx, int with_emission, double *llk);
 /* update_B_numerical_recipes(update = S-1) for every query. */
 int mcq_ctx_backward_fill(mcq_ctx *ctx);
 

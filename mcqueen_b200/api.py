@@ -222,6 +222,11 @@ class Context:
         check(self.lib.mcq_ctx_full_llk(self._h, 1 if with_emission else 0, C.byref(v)))
         return v.value
 
+    def llk_only(self, with_emission=True):
+        v = C.c_double()
+        check(self.lib.mcq_ctx_llk_only(self._h, 1 if with_emission else 0, C.byref(v)))
+        return v.value
+
     def backward_fill(self):
         check(self.lib.mcq_ctx_backward_fill(self._h))
 

@@ -675,6 +675,21 @@ extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
   return 0;
 }
 
+extern "C" int mcq_ctx_llk_only(mcq_ctx *c, int with_emission, double *llk) {
+  READY(c);
+  CallScope scope(c);
+  const int S = c->d.num_sites;
+  McqOverride none{}; none.kind = -1;
+  if (with_emission) {
+    if (run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
+    if (set_marks(c, -1, S, false, 0)) return 1;     // F and B no longer match the rows: all of both owed
+  }
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, c->F, c->Fn, nullptr, nullptr, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (reduce_llk(c, c->llk_cur, llk)) return 1;
+  c->has_pending = false;
+  return 0;
+}
+
 extern "C" int mcq_ctx_backward_fill(mcq_ctx *c) {
   READY(c);
   CallScope scope(c);
@@ -780,7 +795,8 @@ extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_ll
                                  c->tab_t, c->atab_t, c->ec_t, c->ac_t, c->stream));
         c->launches++;   // two kernels
       }
-      if (run_forward(c, c->tab_t, c->ec_t, 0, S - 1, c->F, c->Fn, c->T, c->Tn, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      // the whole-genome sweep of mcmc_moves.c:1124-1134 without writing tmp_F: only an accept needs it
+      if (run_forward(c, c->tab_t, c->ec_t, 0, S - 1, c->F, c->Fn, nullptr, nullptr, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
       break;
     default:
       return mcq_fail(__FILE__, __LINE__, "unknown proposal kind");
@@ -808,6 +824,8 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
   CallScope scope(c);
   const McqStatic st = make_static(c);
   if (ov.kind == MCQ_PROP_MU) {
+    // the proposal was evaluated without writing tmp_F: the same sweep again, this time stored
+    if (run_forward(c, c->tab_t, c->ec_t, 0, S - 1, c->F, c->Fn, c->T, c->Tn, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
     // the reference swaps the roles of the tmp and current arrays (mcmc_moves.c:1166-1169)
     swap_ptr(c->F, c->T); swap_ptr(c->Fn, c->Tn); swap_ptr(c->tab, c->tab_t); swap_ptr(c->atab, c->atab_t);
     swap_ptr(c->ec, c->ec_t); swap_ptr(c->ac, c->ac_t);

@@ -459,9 +459,130 @@ struct LaneSlots {
 // memory through cp.async, staged MCQ_PF sites ahead so that no global-load latency sits on the
 // recurrence; one butterfly all-reduce (the column sum, which both decides the rescale and is the
 // next site's recombination sum); one 16-byte streaming store of F per lane per j (512 contiguous
-// bytes per warp instruction).  FULL: Ls == 64*NJ, no row-bound predicates.
+// bytes per warp instruction).
+//   FULL : Ls == 64*NJ, no row-bound predicates.
+//   PRE  : owed columns before `start` are completed first (lazy refills).
+//   STORE: false = the columns are not written at all (likelihood only: the recursion then runs at
+//          the instruction-issue / FP64 rate instead of the HBM store rate).
+// The site loop is unrolled by the ring depth, so that the ring slot of every site is a compile-time
+// constant: slot of site t = (t - sA) & 3, sA the first site of the loop.  The emission of a state is
+// one byte extract (PRMT), one scaled add (LEA) and one LDS.
 // ------------------------------------------------------------------------------------------
-template <int NJ, bool FULL, bool PRE>
+static_assert(MCQ_RING == 4, "the unrolled site loops assume a ring of four slots");
+
+__device__ __forceinline__ void cp_async16_sh(unsigned sa, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8_sh(unsigned sa, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// Stage the rows of site t into ring slot KS (a constant): one commit group per call, empty when the
+// site lies outside the range.  g_sh / e_sh: shared-window addresses of the rings, already offset by
+// this lane's 16 / 8 bytes; Gl = the query's G rows, offset by this lane's 16 bytes.
+template <int NJ, int KS>
+__device__ __forceinline__ void stage_k(unsigned g_sh, unsigned e_sh, int t, bool valid, const SiteAhead &sa,
+                                        const double *__restrict__ tab, const double *__restrict__ ecq,
+                                        const uint8_t *__restrict__ Gl, int lane) {
+  if (valid) {
+    const uint8_t *src = Gl + (size_t)t * (64 * NJ);
+#pragma unroll
+    for (int i = 0; i < (NJ + 7) / 8; i++)
+      if ((lane + 32 * i) * 16 < 64 * NJ) cp_async16_sh(g_sh + KS * (64 * NJ) + 512 * i, src + 512 * i);
+    const int kr = sa.kr;             // at most 64 entries: two predicated copies, no loop
+    const double *row = tab + (size_t)sa.toff + (size_t)sa.to * kr + lane;
+    const unsigned ed = e_sh + (KS * MCQ_ES + 1) * 8;
+    if (lane < kr) cp_async8_sh(ed, row);
+    if (lane + 32 < kr) cp_async8_sh(ed + 256, row + 32);
+    if (lane == 0 && ecq != nullptr) cp_async8_sh(ed - 8, ecq + t);
+  }
+  cp_async_commit();
+}
+
+// emission of the state whose slot is byte `b` of word w, from the staged row at `row`
+__device__ __forceinline__ double emis_at(const double *row, unsigned w, int b) {
+  const unsigned slot = __byte_perm(w, 0, 0x4440 + b);
+  return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(row) + (slot << 3));
+}
+
+// the 2*NJ slot bytes a lane owns at one site, from ring slot K of the staged G rows (gl = this lane's
+// bytes in slot 0)
+template <int NJ, int K>
+__device__ __forceinline__ void load_slots(const uint8_t *gl, unsigned (&w)[(2 * NJ + 3) / 4]) {
+  const uint8_t *p = gl + K * (64 * NJ);
+  if constexpr (NJ == 1) w[0] = *reinterpret_cast<const uint16_t *>(p);
+  else if constexpr (NJ == 2) w[0] = *reinterpret_cast<const uint32_t *>(p);
+  else if constexpr (NJ == 4) { const uint2 v = *reinterpret_cast<const uint2 *>(p); w[0] = v.x; w[1] = v.y; }
+  else {
+#pragma unroll
+    for (int i = 0; i < NJ / 8; i++) {
+      const uint4 v = reinterpret_cast<const uint4 *>(p)[i];
+      w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+  }
+}
+
+template <int NJ>
+struct FwdWarp {              // what one warp carries from site to site
+  double p0[NJ], p1[NJ];      // the running column
+  double tot, Rnext;
+  int cnt, t;                 // rescale counter; next site to stage
+  SiteAhead ahead;            // look-ahead of site t
+};
+
+// one site of the recursion, its rows in ring slot K
+template <int NJ, bool FULL, bool PRE, bool STORE, int K>
+__device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s, const uint8_t *gl, const double *ering,
+                                         unsigned g_sh, unsigned e_sh, const uint8_t *__restrict__ Gl,
+                                         const uint8_t *__restrict__ qc, const double *ecq, const double *ecq_pre,
+                                         int lane, const bool (&inrow)[NJ], double invN, double *Fo, double *Fc,
+                                         int *Fno, int *Fnc) {
+  cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed (this lane's copies)
+  __syncwarp();                  // ... and every other lane's; the slot of site s-1 is free again
+  {
+    const int t = w.t;
+    const SiteAhead cur = w.ahead;
+    w.ahead = look_ahead(a.st, qc, t + 1, t + 1 <= a.end);
+    const bool pre = PRE && t < a.start;
+    stage_k<NJ, (K + MCQ_PF) & 3>(g_sh, e_sh, t, t <= a.end, cur, pre ? a.em_pre.tab : a.em.tab, pre ? ecq_pre : ecq, Gl, lane);
+    w.t = t + 1;
+  }
+  unsigned g[(2 * NJ + 3) / 4];
+  load_slots<NJ, K>(gl, g);
+  const double *es = ering + K * MCQ_ES;
+  const double Rs = w.Rnext;
+  w.Rnext = (s + 1 <= a.end) ? ((s + 1 == a.r_site) ? a.r_value : a.R[s + 1]) : 0.0;
+  // forward_backward.c:138 divides by N and :141-142 adds then multiplies; here the reciprocal and
+  // a fused multiply-add keep the per-site dependency chain short (each one rounding away from
+  // the reference's sequence, far inside the tolerance - the order of the sum differs anyway)
+  const double jump = w.tot * (Rs * invN);
+  const double stay = 1 - Rs;
+  double la = 0.0, lb = 0.0;     // two partial sums: a shorter dependent chain than one
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const double v0 = __fma_rn(stay, w.p0[j], jump) * emis_at(es, g[j >> 1], (j & 1) * 2);
+    const double v1 = __fma_rn(stay, w.p1[j], jump) * emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+    w.p0[j] = v0; w.p1[j] = v1;
+    la += v0; lb += v1;
+  }
+  w.tot = warp_sum(la + lb);
+  if (w.tot < MCQ_BIGI) {                       // forward_backward.c:163-167
+    ++w.cnt;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { w.p0[j] *= MCQ_BIG; w.p1[j] *= MCQ_BIG; }
+    w.tot *= MCQ_BIG;
+  }
+  if (STORE) {
+    const bool pre = PRE && s < a.start;        // a catch-up site: it goes into the current matrix
+    double *__restrict__ Fs = (pre ? Fc : Fo) + (size_t)s * a.st.Ls;
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(w.p0[j], w.p1[j]));
+    if (lane == 0) (pre ? Fnc : Fno)[s] = w.cnt;
+  }
+}
+
+template <int NJ, bool FULL, bool PRE, bool STORE>
 __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
   __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
@@ -474,8 +595,10 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   }
   const int S = a.st.S, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
-  const uint8_t *__restrict__ Gq = a.st.G + (size_t)q * S * (64 * NJ);
+  const uint8_t *__restrict__ Gl = a.st.G + (size_t)q * S * (64 * NJ) + lane * 16;
   const uint8_t *__restrict__ qc = a.st.query_codon ? a.st.query_codon + (size_t)q * S : nullptr;
+  const double *ecq = a.em.ec ? a.em.ec + (size_t)q * S : nullptr;
+  const double *ecq_pre = (PRE && a.em_pre.ec) ? a.em_pre.ec + (size_t)q * S : nullptr;
   // sites before `start` that are not valid yet are caught up first, with the current rows, into Fin
   // (PRE: the variant launched when the host knows of owed columns; the other one carries none of this)
   int s0 = a.start;
@@ -484,125 +607,100 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
     if (v < a.start - 1) s0 = v + 1;
   }
   const bool caught_up = PRE && s0 < a.start;
-  double *Fo = a.Fout + qoff + 2 * lane;
+  double *Fo = STORE ? a.Fout + qoff + 2 * lane : nullptr;
   double *Fc = const_cast<double *>(a.Fin) + qoff + 2 * lane;
-  int *Fno = a.Fn_out + (size_t)q * S;
+  int *Fno = STORE ? a.Fn_out + (size_t)q * S : nullptr;
   int *Fnc = const_cast<int *>(a.Fn_in) + (size_t)q * S;
   uint8_t *gring = &s_g[wib][0][0];
   double *ering = &s_e[wib][0][0];
   if (lane < MCQ_RING) ering[lane * MCQ_ES + MCQ_NOSLOT] = 0.0;   // the "no such codon" emission
+  const unsigned g_sh = (unsigned)__cvta_generic_to_shared(gring) + lane * 16;
+  const unsigned e_sh = (unsigned)__cvta_generic_to_shared(ering) + lane * 8;
+  const uint8_t *gl = gring + lane * (2 * NJ);
 
   bool inrow[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; j++) inrow[j] = FULL || (64 * j + 2 * lane < Ls);
 
-  // prologue: rows of the first MCQ_PF sites of the range
-  int t = s0;
-#pragma unroll
-  for (int i = 0; i < MCQ_PF; i++, t++)
-    stage_site<NJ>(gring, ering, t, t <= a.end, look_ahead(a.st, qc, t, t <= a.end), q, a.st,
-                   (PRE && t < a.start) ? a.em_pre : a.em, Gq, lane);
-  SiteAhead ahead = look_ahead(a.st, qc, t, t <= a.end);   // site t = s0 + MCQ_PF
+  // prologue.  The loop starts at site sA with ring slot 0; when the range starts at site 0 the rows of
+  // site 0 (the seed column) go to slot 3, which the loop first reuses for site sA + 3.
+  const int sA = (s0 == 0) ? 1 : s0;
+  FwdWarp<NJ> w;
+  if (s0 == 0)
+    stage_k<NJ, 3>(g_sh, e_sh, 0, true, look_ahead(a.st, qc, 0, true), (PRE && 0 < a.start) ? a.em_pre.tab : a.em.tab,
+                   (PRE && 0 < a.start) ? ecq_pre : ecq, Gl, lane);
+  else cp_async_commit();
+  {
+    const bool pre0 = PRE && sA < a.start, pre1 = PRE && sA + 1 < a.start, pre2 = PRE && sA + 2 < a.start;
+    stage_k<NJ, 0>(g_sh, e_sh, sA, sA <= a.end, look_ahead(a.st, qc, sA, sA <= a.end),
+                   pre0 ? a.em_pre.tab : a.em.tab, pre0 ? ecq_pre : ecq, Gl, lane);
+    stage_k<NJ, 1>(g_sh, e_sh, sA + 1, sA + 1 <= a.end, look_ahead(a.st, qc, sA + 1, sA + 1 <= a.end),
+                   pre1 ? a.em_pre.tab : a.em.tab, pre1 ? ecq_pre : ecq, Gl, lane);
+    stage_k<NJ, 2>(g_sh, e_sh, sA + 2, sA + 2 <= a.end, look_ahead(a.st, qc, sA + 2, sA + 2 <= a.end),
+                   pre2 ? a.em_pre.tab : a.em.tab, pre2 ? ecq_pre : ecq, Gl, lane);
+  }
+  w.t = sA + MCQ_PF;
+  w.ahead = look_ahead(a.st, qc, w.t, w.t <= a.end);
   const double invN = 1.0 / (double)a.st.N;
 
-  double p0[NJ], p1[NJ];   // the running column
-  int s = s0, cnt;
-  double tot;
-
-  if (s == 0) {
+  if (s0 == 0) {
     // column 0 is the bare emission and is never rescaled (forward_backward.c:27-39,102-111)
-    cp_async_wait<MCQ_PF - 1>();
+    cp_async_wait<MCQ_PF>();
     __syncwarp();
-    {
-      const SiteAhead cur = ahead;
-      ahead = look_ahead(a.st, qc, t + 1, t + 1 <= a.end);
-      stage_site<NJ>(gring, ering, t, t <= a.end, cur, q, a.st, (PRE && t < a.start) ? a.em_pre : a.em, Gq, lane);
-      t++;
-    }
-    LaneSlots<NJ> g;
-    g.load(gring, lane);              // ring slot 0
-    const double *es = ering;
+    unsigned g[(2 * NJ + 3) / 4];
+    load_slots<NJ, 3>(gl, g);
+    const double *es = ering + 3 * MCQ_ES;
     double *F0 = (PRE && 0 < a.start) ? Fc : Fo;      // column 0 belongs to the catch-up when start > 0
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      p0[j] = es[g.first(j)]; p1[j] = es[g.second(j)];
-      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(F0 + 64 * j), make_double2(p0[j], p1[j]));
-      loc += p0[j]; loc += p1[j];
+      w.p0[j] = emis_at(es, g[j >> 1], (j & 1) * 2); w.p1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+      if (STORE && inrow[j]) __stcs(reinterpret_cast<double2 *>(F0 + 64 * j), make_double2(w.p0[j], w.p1[j]));
+      loc += w.p0[j]; loc += w.p1[j];
     }
-    cnt = 0;
-    if (lane == 0) {
+    w.cnt = 0;
+    if (STORE && lane == 0) {
       // update_F with start 0 zeroes both counters of column 0 (forward_backward.c:108-109)
       Fno[0] = 0;
       if (a.Fn_in != nullptr) Fnc[0] = 0;
     }
-    tot = warp_sum(loc);
-    s = 1;
+    w.tot = warp_sum(loc);
   } else {
-    const double *__restrict__ Fi = Fc + (size_t)(s - 1) * Ls;
+    const double *__restrict__ Fi = Fc + (size_t)(s0 - 1) * Ls;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      p0[j] = 0.0; p1[j] = 0.0;
+      w.p0[j] = 0.0; w.p1[j] = 0.0;
       if (inrow[j]) {
         const double2 v = *reinterpret_cast<const double2 *>(Fi + 64 * j);
-        p0[j] = v.x; p1[j] = v.y;
+        w.p0[j] = v.x; w.p1[j] = v.y;
       }
-      loc += p0[j]; loc += p1[j];
+      loc += w.p0[j]; loc += w.p1[j];
     }
-    cnt = Fnc[s - 1];
-    tot = warp_sum(loc);
+    w.cnt = Fnc[s0 - 1];
+    w.tot = warp_sum(loc);
   }
 
-  double Rnext = (s <= a.end) ? ((s == a.r_site) ? a.r_value : a.R[s]) : 0.0;
-  for (; s <= a.end; ++s) {
-    cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed (this lane's copies)
-    __syncwarp();                  // ... and every other lane's; the slot of site s-1 is free again
-    {
-      const SiteAhead cur = ahead;
-      ahead = look_ahead(a.st, qc, t + 1, t + 1 <= a.end);
-      stage_site<NJ>(gring, ering, t, t <= a.end, cur, q, a.st, (PRE && t < a.start) ? a.em_pre : a.em, Gq, lane);
-      t++;
-    }
-    LaneSlots<NJ> g;
-    g.load(gring + (s % MCQ_RING) * (64 * NJ), lane);
-    const double *es = ering + (s % MCQ_RING) * MCQ_ES;
-    const double Rs = Rnext;
-    Rnext = (s + 1 <= a.end) ? ((s + 1 == a.r_site) ? a.r_value : a.R[s + 1]) : 0.0;
-    // forward_backward.c:138 divides by N and :141-142 adds then multiplies; here the reciprocal and
-    // a fused multiply-add keep the per-site dependency chain short (each one rounding away from
-    // the reference's sequence, far inside the tolerance - the order of the sum differs anyway)
-    const double jump = tot * (Rs * invN);
-    const double stay = 1 - Rs;
-    double la = 0.0, lb = 0.0;     // two partial sums: a shorter dependent chain than one
-#pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      const double v0 = __fma_rn(stay, p0[j], jump) * es[g.first(j)];
-      const double v1 = __fma_rn(stay, p1[j], jump) * es[g.second(j)];
-      p0[j] = v0; p1[j] = v1;
-      la += v0; lb += v1;
-    }
-    tot = warp_sum(la + lb);
-    if (tot < MCQ_BIGI) {                       // forward_backward.c:163-167
-      ++cnt;
-#pragma unroll
-      for (int j = 0; j < NJ; j++) { p0[j] *= MCQ_BIG; p1[j] *= MCQ_BIG; }
-      tot *= MCQ_BIG;
-    }
-    const bool pre = PRE && s < a.start;        // a catch-up site: it goes into the current matrix
-    double *__restrict__ Fs = (pre ? Fc : Fo) + (size_t)s * Ls;
-#pragma unroll
-    for (int j = 0; j < NJ; j++)
-      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(p0[j], p1[j]));
-    if (lane == 0) (pre ? Fnc : Fno)[s] = cnt;
+  w.Rnext = (sA <= a.end) ? ((sA == a.r_site) ? a.r_value : a.R[sA]) : 0.0;
+#define MCQ_FWD_SITE(K, SITE) \
+  fwd_site<NJ, FULL, PRE, STORE, K>(a, w, SITE, gl, ering, g_sh, e_sh, Gl, qc, ecq, ecq_pre, lane, inrow, invN, Fo, Fc, Fno, Fnc)
+  for (int s = sA; s <= a.end; s += 4) {
+    MCQ_FWD_SITE(0, s);
+    if (s + 1 > a.end) break;
+    MCQ_FWD_SITE(1, s + 1);
+    if (s + 2 > a.end) break;
+    MCQ_FWD_SITE(2, s + 2);
+    if (s + 3 > a.end) break;
+    MCQ_FWD_SITE(3, s + 3);
   }
+#undef MCQ_FWD_SITE
   cp_async_wait<0>();
   if (caught_up && lane == 0) a.fv[q] = a.start - 1;
 
   // K6 epilogue: the per-query log-likelihood at the last column of the range
   if (a.llk_mode != 0) {
     double dot;
-    int nrm = cnt;
+    int nrm = w.cnt;
     if (a.llk_mode == 1) {                      // mcmc_moves.c:220-223
       const double *__restrict__ Bc = a.B + qoff + (size_t)a.end * Ls + 2 * lane;
       double loc = 0.0;
@@ -610,38 +708,49 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
       for (int j = 0; j < NJ; j++)
         if (inrow[j]) {
           const double2 b = *reinterpret_cast<const double2 *>(Bc + 64 * j);
-          loc += p0[j] * b.x; loc += p1[j] * b.y;
+          loc += w.p0[j] * b.x; loc += w.p1[j] * b.y;
         }
       dot = warp_sum(loc);
       nrm += a.Bn[(size_t)q * S + a.end];
     } else {                                    // dmodel.c:899-901, mcmc_moves.c:1129-1134
-      dot = tot;
+      dot = w.tot;
     }
     if (lane == 0) a.llk_out[q] = log(dot) - nrm * a.logBIG;
   }
 }
 
-template <int NJ>
+template <int NJ, bool STORE>
 static cudaError_t launch_forward_nj(const FwdArgs &a, cudaStream_t stream) {
   const unsigned blocks = (unsigned)((a.st.Q + MCQ_WPB - 1) / MCQ_WPB);
   const bool full = a.st.Ls == 64 * NJ;
   if (a.fv != nullptr) {
-    if (full) k_forward<NJ, true, true><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
-    else k_forward<NJ, false, true><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+    if (full) k_forward<NJ, true, true, STORE><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+    else k_forward<NJ, false, true, STORE><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
   } else {
-    if (full) k_forward<NJ, true, false><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
-    else k_forward<NJ, false, false><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+    if (full) k_forward<NJ, true, false, STORE><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+    else k_forward<NJ, false, false, STORE><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
   }
   return cudaGetLastError();
 }
 
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
+  if (a.Fout == nullptr) {          // likelihood only: no column is written
+    if (a.fv != nullptr || a.start != 0) return cudaErrorInvalidValue;
+    switch (a.st.Lg / 64) {
+      case 1: return launch_forward_nj<1, false>(a, stream);
+      case 2: return launch_forward_nj<2, false>(a, stream);
+      case 4: return launch_forward_nj<4, false>(a, stream);
+      case 8: return launch_forward_nj<8, false>(a, stream);
+      case 16: return launch_forward_nj<16, false>(a, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (a.st.Lg / 64) {
-    case 1: return launch_forward_nj<1>(a, stream);
-    case 2: return launch_forward_nj<2>(a, stream);
-    case 4: return launch_forward_nj<4>(a, stream);
-    case 8: return launch_forward_nj<8>(a, stream);
-    case 16: return launch_forward_nj<16>(a, stream);
+    case 1: return launch_forward_nj<1, true>(a, stream);
+    case 2: return launch_forward_nj<2, true>(a, stream);
+    case 4: return launch_forward_nj<4, true>(a, stream);
+    case 8: return launch_forward_nj<8, true>(a, stream);
+    case 16: return launch_forward_nj<16, true>(a, stream);
     default: return cudaErrorInvalidValue;
   }
 }

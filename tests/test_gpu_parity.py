@@ -165,6 +165,35 @@ def test_lazy_refills_are_bit_identical_to_eager(api, sparse):
         c.close()
 
 
+@pytest.mark.parametrize("over", [{}, dict(L=37, S=33, Q=9), dict(L=200, N=260, S=40, Q=6), dict(L=1000, N=1100, S=21, Q=4),
+                                  dict(L=20, N=200, S=1, Q=5), dict(L=500, N=600, S=7, Q=3)])
+def test_llk_only_equals_the_stored_sweep(api, over):
+    """mcq_ctx_llk_only runs the same recursion without writing F: bit-identical per-query values, F and
+    B untouched when the rows did not change, owed (and then recomputed correctly) when they did."""
+    p = make_problem("toy", **over)
+    cpu = CpuState(checker(), p)
+    ctx = api.Context.from_problem(p)
+    llk = ctx.init_state()
+    per_query = ctx.query_llk().copy()
+    assert ctx.llk_only(with_emission=False) == llk
+    assert np.array_equal(ctx.query_llk(), per_query)
+    assert abs(llk - cpu.llk) <= RTOL_LLK * abs(cpu.llk)
+    assert_state_matches(ctx, cpu, [0, p.Q - 1])
+    # new parameters: llk_only(with_emission) evaluates them; F and B follow when next read
+    p2 = make_problem("toy", param_seed=5, **over)
+    cpu2 = CpuState(checker(), p2)
+    ctx.set_params(mu=p2.mu, kappa=p2.kappa, phi=p2.phi, R=p2.R, omega=p2.omega,
+                   rate_out=p2.rate_out_of_codons(p2.omega), esc=p2.esc, rev=p2.rev[0])
+    got = ctx.llk_only()
+    assert abs(got - cpu2.llk) <= RTOL_LLK * abs(cpu2.llk)
+    assert_state_matches(ctx, cpu2, [0, p.Q - 1])
+    if p.S > 12:
+        mv = dict(kind=ESC, start=3, end=11, hla=1, value0=1.7)
+        want, got = cpu2.propose(**mv), ctx.propose(**mv)
+        assert abs(got - want) <= RTOL_LLK * abs(want)
+    ctx.close()
+
+
 def test_dropin_symbols_match(api):
     p = make_problem("toy", gaps=True)
     chk = checker()
