@@ -477,25 +477,33 @@ __device__ __forceinline__ void cp_async8_sh(unsigned sa, const void *gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 
-// Stage the rows of site t into ring slot KS (a constant): one commit group per call, empty when the
-// site lies outside the range.  g_sh / e_sh: shared-window addresses of the rings, already offset by
-// this lane's 16 / 8 bytes; Gl = the query's G rows, offset by this lane's 16 bytes.
+// predicated forms: straight-line code, no branch around the copy
+__device__ __forceinline__ void cp_async16_if(unsigned sa, const void *gmem, bool p) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n"
+               ::"r"(sa), "l"(gmem), "r"((int)p) : "memory");
+}
+__device__ __forceinline__ void cp_async8_if(unsigned sa, const void *gmem, bool p) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}\n"
+               ::"r"(sa), "l"(gmem), "r"((int)p) : "memory");
+}
+
+// Stage the rows of one site into ring slot KS (a constant): one commit group per call, empty when the
+// site lies outside the range (then sa.kr == 0 as well).  g_sh / e_sh: shared-window addresses of the
+// rings, already offset by this lane's 16 / 8 bytes; gsrc = the site's G row, tabl = the emission table,
+// both offset by this lane's share; ecp = the query's consensus-row value of the site (lane 0 copies it).
 template <int NJ, int KS>
-__device__ __forceinline__ void stage_k(unsigned g_sh, unsigned e_sh, int t, bool valid, const SiteAhead &sa,
-                                        const double *__restrict__ tab, const double *__restrict__ ecq,
-                                        const uint8_t *__restrict__ Gl, int lane) {
-  if (valid) {
-    const uint8_t *src = Gl + (size_t)t * (64 * NJ);
+__device__ __forceinline__ void stage_k(unsigned g_sh, unsigned e_sh, bool valid, const SiteAhead &sa,
+                                        const double *__restrict__ tabl, const double *__restrict__ ecp, bool has_ec,
+                                        const uint8_t *__restrict__ gsrc, int lane) {
 #pragma unroll
-    for (int i = 0; i < (NJ + 7) / 8; i++)
-      if ((lane + 32 * i) * 16 < 64 * NJ) cp_async16_sh(g_sh + KS * (64 * NJ) + 512 * i, src + 512 * i);
-    const int kr = sa.kr;             // at most 64 entries: two predicated copies, no loop
-    const double *row = tab + (size_t)sa.toff + (size_t)sa.to * kr + lane;
-    const unsigned ed = e_sh + (KS * MCQ_ES + 1) * 8;
-    if (lane < kr) cp_async8_sh(ed, row);
-    if (lane + 32 < kr) cp_async8_sh(ed + 256, row + 32);
-    if (lane == 0 && ecq != nullptr) cp_async8_sh(ed - 8, ecq + t);
-  }
+  for (int i = 0; i < (NJ + 7) / 8; i++)
+    cp_async16_if(g_sh + KS * (64 * NJ) + 512 * i, gsrc + 512 * i, valid && (lane + 32 * i) * 16 < 64 * NJ);
+  const int kr = sa.kr;             // at most 64 entries: two predicated copies, no loop
+  const double *row = tabl + (sa.toff + sa.to * kr);
+  const unsigned ed = e_sh + (KS * MCQ_ES + 1) * 8;
+  cp_async8_if(ed, row, lane < kr);
+  cp_async8_if(ed + 256, row + 32, lane + 32 < kr);
+  cp_async8_if(ed - 8, ecp, valid && has_ec && lane == 0);
   cp_async_commit();
 }
 
@@ -528,30 +536,59 @@ struct FwdWarp {              // what one warp carries from site to site
   double tot, Rnext;
   int cnt, t;                 // rescale counter; next site to stage
   SiteAhead ahead;            // look-ahead of site t
+  // running pointers (advanced once per site, no per-site index arithmetic)
+  const uint8_t *gsrc;        // G row of site t (this lane's 16 bytes)
+  const uint8_t *qcp;         // the query's codon at site t + 1
+  const int2 *descp;          // descriptor of site t + 1
+  const double *Rp;           // R of the site after the one being computed
+  double *Fs;                 // output column of the site being computed (this lane's states)
+  int *Fnp;                   // its rescale counter
 };
+
+// the look-ahead of the site after w.t, through the running pointers
+template <int NJ>
+__device__ __forceinline__ SiteAhead next_ahead(FwdWarp<NJ> &w, bool has_qc, bool valid) {
+  SiteAhead a;
+  a.to = 0; a.toff = 0; a.kr = 0;
+  if (valid) {
+    if (has_qc) a.to = *w.qcp;
+    const int2 d = *w.descp;
+    a.toff = d.x; a.kr = d.y;
+  }
+  w.qcp++; w.descp++;
+  return a;
+}
 
 // one site of the recursion, its rows in ring slot K
 template <int NJ, bool FULL, bool PRE, bool STORE, int K>
 __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s, const uint8_t *gl, const double *ering,
-                                         unsigned g_sh, unsigned e_sh, const uint8_t *__restrict__ Gl,
-                                         const uint8_t *__restrict__ qc, const double *ecq, const double *ecq_pre,
-                                         int lane, const bool (&inrow)[NJ], double invN, double *Fo, double *Fc,
-                                         int *Fno, int *Fnc) {
+                                         unsigned g_sh, unsigned e_sh, bool has_qc, const double *tabl,
+                                         const double *tabl_pre, const double *ecq, const double *ecq_pre,
+                                         int lane, const bool (&inrow)[NJ], double invN, ptrdiff_t pre_delta,
+                                         int *Fnc) {
   cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed (this lane's copies)
   __syncwarp();                  // ... and every other lane's; the slot of site s-1 is free again
   {
     const int t = w.t;
     const SiteAhead cur = w.ahead;
-    w.ahead = look_ahead(a.st, qc, t + 1, t + 1 <= a.end);
+    w.ahead = next_ahead(w, has_qc, t + 1 <= a.end);
     const bool pre = PRE && t < a.start;
-    stage_k<NJ, (K + MCQ_PF) & 3>(g_sh, e_sh, t, t <= a.end, cur, pre ? a.em_pre.tab : a.em.tab, pre ? ecq_pre : ecq, Gl, lane);
+    const double *eq = pre ? ecq_pre : ecq;
+    stage_k<NJ, (K + MCQ_PF) & 3>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.gsrc, lane);
+    w.gsrc += 64 * NJ;
     w.t = t + 1;
   }
   unsigned g[(2 * NJ + 3) / 4];
   load_slots<NJ, K>(gl, g);
   const double *es = ering + K * MCQ_ES;
   const double Rs = w.Rnext;
-  w.Rnext = (s + 1 <= a.end) ? ((s + 1 == a.r_site) ? a.r_value : a.R[s + 1]) : 0.0;
+  {
+    double rn = 0.0;
+    if (s + 1 <= a.end) rn = *w.Rp;
+    if (s + 1 == a.r_site) rn = a.r_value;
+    w.Rnext = rn;
+    w.Rp++;
+  }
   // forward_backward.c:138 divides by N and :141-142 adds then multiplies; here the reciprocal and
   // a fused multiply-add keep the per-site dependency chain short (each one rounding away from
   // the reference's sequence, far inside the tolerance - the order of the sum differs anyway)
@@ -573,12 +610,18 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
     w.tot *= MCQ_BIG;
   }
   if (STORE) {
-    const bool pre = PRE && s < a.start;        // a catch-up site: it goes into the current matrix
-    double *__restrict__ Fs = (pre ? Fc : Fo) + (size_t)s * a.st.Ls;
+    // a catch-up site goes into the current matrix: the same offset, pre_delta doubles away
+    const bool pre = PRE && s < a.start;
+    double *__restrict__ Fs = pre ? w.Fs + pre_delta : w.Fs;
 #pragma unroll
     for (int j = 0; j < NJ; j++)
       if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(w.p0[j], w.p1[j]));
-    if (lane == 0) (pre ? Fnc : Fno)[s] = w.cnt;
+    if (lane == 0) {
+      if (pre) Fnc[s] = w.cnt;
+      else *w.Fnp = w.cnt;
+    }
+    w.Fs += a.st.Ls;
+    w.Fnp++;
   }
 }
 
@@ -596,9 +639,11 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   const int S = a.st.S, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
   const uint8_t *__restrict__ Gl = a.st.G + (size_t)q * S * (64 * NJ) + lane * 16;
-  const uint8_t *__restrict__ qc = a.st.query_codon ? a.st.query_codon + (size_t)q * S : nullptr;
+  const bool has_qc = a.st.query_codon != nullptr;
+  const uint8_t *__restrict__ qc = has_qc ? a.st.query_codon + (size_t)q * S : nullptr;
   const double *ecq = a.em.ec ? a.em.ec + (size_t)q * S : nullptr;
   const double *ecq_pre = (PRE && a.em_pre.ec) ? a.em_pre.ec + (size_t)q * S : nullptr;
+  const double *tabl = a.em.tab + lane, *tabl_pre = PRE ? a.em_pre.tab + lane : nullptr;
   // sites before `start` that are not valid yet are caught up first, with the current rows, into Fin
   // (PRE: the variant launched when the host knows of owed columns; the other one carries none of this)
   int s0 = a.start;
@@ -626,21 +671,30 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   // site 0 (the seed column) go to slot 3, which the loop first reuses for site sA + 3.
   const int sA = (s0 == 0) ? 1 : s0;
   FwdWarp<NJ> w;
-  if (s0 == 0)
-    stage_k<NJ, 3>(g_sh, e_sh, 0, true, look_ahead(a.st, qc, 0, true), (PRE && 0 < a.start) ? a.em_pre.tab : a.em.tab,
-                   (PRE && 0 < a.start) ? ecq_pre : ecq, Gl, lane);
-  else cp_async_commit();
   {
-    const bool pre0 = PRE && sA < a.start, pre1 = PRE && sA + 1 < a.start, pre2 = PRE && sA + 2 < a.start;
-    stage_k<NJ, 0>(g_sh, e_sh, sA, sA <= a.end, look_ahead(a.st, qc, sA, sA <= a.end),
-                   pre0 ? a.em_pre.tab : a.em.tab, pre0 ? ecq_pre : ecq, Gl, lane);
-    stage_k<NJ, 1>(g_sh, e_sh, sA + 1, sA + 1 <= a.end, look_ahead(a.st, qc, sA + 1, sA + 1 <= a.end),
-                   pre1 ? a.em_pre.tab : a.em.tab, pre1 ? ecq_pre : ecq, Gl, lane);
-    stage_k<NJ, 2>(g_sh, e_sh, sA + 2, sA + 2 <= a.end, look_ahead(a.st, qc, sA + 2, sA + 2 <= a.end),
-                   pre2 ? a.em_pre.tab : a.em.tab, pre2 ? ecq_pre : ecq, Gl, lane);
+    const bool pre = PRE && 0 < a.start;
+    const double *eq = pre ? ecq_pre : ecq;
+    stage_k<NJ, 3>(g_sh, e_sh, s0 == 0, look_ahead(a.st, qc, 0, s0 == 0), pre ? tabl_pre : tabl, eq, eq != nullptr, Gl, lane);
   }
+#define MCQ_FWD_PROLOGUE(K)                                                                                  \
+  {                                                                                                          \
+    const int tt = sA + K;                                                                                   \
+    const bool pre = PRE && tt < a.start;                                                                    \
+    const double *eq = pre ? ecq_pre : ecq;                                                                  \
+    stage_k<NJ, K>(g_sh, e_sh, tt <= a.end, look_ahead(a.st, qc, tt, tt <= a.end), pre ? tabl_pre : tabl,    \
+                   eq + tt, eq != nullptr, Gl + (size_t)tt * (64 * NJ), lane);                               \
+  }
+  MCQ_FWD_PROLOGUE(0) MCQ_FWD_PROLOGUE(1) MCQ_FWD_PROLOGUE(2)
+#undef MCQ_FWD_PROLOGUE
   w.t = sA + MCQ_PF;
   w.ahead = look_ahead(a.st, qc, w.t, w.t <= a.end);
+  w.gsrc = Gl + (size_t)w.t * (64 * NJ);
+  w.qcp = qc + w.t + 1;
+  w.descp = a.st.desc + w.t + 1;
+  w.Rp = a.R + sA + 1;
+  w.Fs = STORE ? Fo + (size_t)sA * Ls : nullptr;
+  w.Fnp = STORE ? Fno + sA : nullptr;
+  const ptrdiff_t pre_delta = (PRE && STORE) ? (Fc - Fo) : 0;
   const double invN = 1.0 / (double)a.st.N;
 
   if (s0 == 0) {
@@ -682,8 +736,9 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   }
 
   w.Rnext = (sA <= a.end) ? ((sA == a.r_site) ? a.r_value : a.R[sA]) : 0.0;
-#define MCQ_FWD_SITE(K, SITE) \
-  fwd_site<NJ, FULL, PRE, STORE, K>(a, w, SITE, gl, ering, g_sh, e_sh, Gl, qc, ecq, ecq_pre, lane, inrow, invN, Fo, Fc, Fno, Fnc)
+#define MCQ_FWD_SITE(K, SITE)                                                                                     \
+  fwd_site<NJ, FULL, PRE, STORE, K>(a, w, SITE, gl, ering, g_sh, e_sh, has_qc, tabl, tabl_pre, ecq, ecq_pre, lane, \
+                                    inrow, invN, pre_delta, Fnc)
   for (int s = sA; s <= a.end; s += 4) {
     MCQ_FWD_SITE(0, s);
     if (s + 1 > a.end) break;
@@ -758,8 +813,99 @@ cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 // K5: backward recursion, same mapping and staging, descending sites.  b = B[.][s+1] (as stored),
 // e = the emission at s+1, sx = sum_r b*e.  The column sum of the new column and the next sx are
-// reduced together in one butterfly.
+// reduced together in one butterfly.  Ring slot of site t = (tA - t) & 3, tA the first site whose rows
+// are consumed (the column above the first one computed).
 // ------------------------------------------------------------------------------------------
+template <int NJ>
+struct BwdWarp {
+  double b0[NJ], b1[NJ], e0[NJ], e1[NJ];
+  double sx, Rnext;
+  int cnt, t;
+  SiteAhead ahead;
+  const uint8_t *gsrc;        // G row of site t (this lane's 16 bytes)
+  const uint8_t *qcp;         // the query's codon at site t - 1
+  const int2 *descp;          // descriptor of site t - 1
+  const double *ecp;          // consensus-row value of site t (unused when the rows carry none)
+  const double *Rp;           // R[s] of the site being computed (= R[(s-1)+1], read for the next one)
+  double *Bs;                 // output column of the site being computed
+  int *Bnp;
+};
+
+template <int NJ>
+__device__ __forceinline__ SiteAhead prev_ahead(BwdWarp<NJ> &w, bool has_qc, bool valid) {
+  SiteAhead a;
+  a.to = 0; a.toff = 0; a.kr = 0;
+  if (valid) {
+    if (has_qc) a.to = *w.qcp;
+    const int2 d = *w.descp;
+    a.toff = d.x; a.kr = d.y;
+  }
+  w.qcp--; w.descp--;
+  return a;
+}
+
+template <int NJ, int K>
+__device__ __forceinline__ void bwd_stage(const BwdArgs &a, BwdWarp<NJ> &w, unsigned g_sh, unsigned e_sh, bool has_qc,
+                                          const double *tabl, int bottom, int lane) {
+  const int t = w.t;
+  const SiteAhead cur = w.ahead;
+  w.ahead = prev_ahead(w, has_qc, t - 1 >= bottom);
+  stage_k<NJ, (K + MCQ_PF) & 3>(g_sh, e_sh, t >= bottom, cur, tabl, w.ecp, a.em.ec != nullptr, w.gsrc, lane);
+  w.gsrc -= 64 * NJ;
+  w.ecp--;
+  w.t = t - 1;
+}
+
+// one site of the recursion: computes column s from column s+1; the rows of site s are in ring slot K
+template <int NJ, bool FULL, int K>
+__device__ __forceinline__ void bwd_site(const BwdArgs &a, BwdWarp<NJ> &w, const uint8_t *gl, const double *ering,
+                                         unsigned g_sh, unsigned e_sh, bool has_qc, const double *tabl, int bottom,
+                                         int lane, const bool (&inrow)[NJ], const double (&m0)[NJ],
+                                         const double (&m1)[NJ], double invN) {
+  cp_async_wait<MCQ_PF - 1>();   // rows of site s
+  __syncwarp();
+  bwd_stage<NJ, K>(a, w, g_sh, e_sh, has_qc, tabl, bottom, lane);
+  unsigned g[(2 * NJ + 3) / 4];
+  load_slots<NJ, K>(gl, g);
+  const double *es = ering + K * MCQ_ES;
+  const double Rn = w.Rnext;
+  w.Rnext = *w.Rp;                              // R[(s-1)+1] for the next site
+  w.Rp--;
+  const double jump = w.sx * (Rn * invN);       // forward_backward.c:219 (reciprocal: see k_forward)
+  const double stay = 1 - Rn;
+  double locv = 0.0, locy = 0.0, locv2 = 0.0, locy2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    // emission at s, for the next step's products
+    const double n0 = emis_at(es, g[j >> 1], (j & 1) * 2), n1 = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+    const double v0 = __fma_rn(stay * w.b0[j], w.e0[j], jump) * m0[j];
+    const double v1 = __fma_rn(stay * w.b1[j], w.e1[j], jump) * m1[j];
+    w.b0[j] = v0; w.b1[j] = v1;
+    locv += v0; locv2 += v1;
+    locy = __fma_rn(v0, n0, locy); locy2 = __fma_rn(v1, n1, locy2);
+    w.e0[j] = n0; w.e1[j] = n1;
+  }
+  locv += locv2; locy += locy2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    locv += __shfl_xor_sync(0xffffffffu, locv, o);
+    locy += __shfl_xor_sync(0xffffffffu, locy, o);
+  }
+  w.sx = locy;
+  if (locv < MCQ_BIGI) {                        // forward_backward.c:236-242
+    ++w.cnt;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { w.b0[j] *= MCQ_BIG; w.b1[j] *= MCQ_BIG; }
+    w.sx *= MCQ_BIG;
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; j++)
+    if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(w.Bs + 64 * j), make_double2(w.b0[j], w.b1[j]));
+  if (lane == 0) *w.Bnp = w.cnt;
+  w.Bs -= a.st.Ls;
+  w.Bnp--;
+}
+
 template <int NJ, bool FULL>
 __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
@@ -770,13 +916,19 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) return;
   const int S = a.st.S, L = a.st.L, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
-  const uint8_t *__restrict__ Gq = a.st.G + (size_t)q * S * (64 * NJ);
-  const uint8_t *__restrict__ qc = a.st.query_codon ? a.st.query_codon + (size_t)q * S : nullptr;
+  const uint8_t *__restrict__ Gl = a.st.G + (size_t)q * S * (64 * NJ) + lane * 16;
+  const bool has_qc = a.st.query_codon != nullptr;
+  const uint8_t *__restrict__ qc = has_qc ? a.st.query_codon + (size_t)q * S : nullptr;
+  const double *ecq = a.em.ec ? a.em.ec + (size_t)q * S : nullptr;
+  const double *tabl = a.em.tab + lane;
   double *__restrict__ Bq = a.B + qoff + 2 * lane;
   int *__restrict__ Bnq = a.Bn + (size_t)q * S;
   uint8_t *gring = &s_g[wib][0][0];
   double *ering = &s_e[wib][0][0];
   if (lane < MCQ_RING) ering[lane * MCQ_ES + MCQ_NOSLOT] = 0.0;
+  const unsigned g_sh = (unsigned)__cvta_generic_to_shared(gring) + lane * 16;
+  const unsigned e_sh = (unsigned)__cvta_generic_to_shared(ering) + lane * 8;
+  const uint8_t *gl = gring + lane * (2 * NJ);
 
   bool inrow[NJ];
   double m0[NJ], m1[NJ];   // 1 for real states, 0 for padding (r >= L): padding must not pick up `jump`
@@ -788,8 +940,8 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
     m1[j] = (r + 1 < L) ? 1.0 : 0.0;
   }
 
-  double b0[NJ], b1[NJ], e0[NJ], e1[NJ];
-  int s = a.update, cnt;
+  BwdWarp<NJ> w;
+  int s = a.update;
   const int bottom = a.bottom;
   if (a.bv != nullptr) {
     const int v = a.bv[q];
@@ -799,106 +951,79 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   if (s == S - 1) {                             // forward_backward.c:197-203
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      b0[j] = m0[j]; b1[j] = m1[j];
-      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bq + (size_t)s * Ls + 64 * j), make_double2(b0[j], b1[j]));
+      w.b0[j] = m0[j]; w.b1[j] = m1[j];
+      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bq + (size_t)s * Ls + 64 * j), make_double2(w.b0[j], w.b1[j]));
     }
-    cnt = 0;
+    w.cnt = 0;
     if (lane == 0) Bnq[s] = 0;
     s--;
   } else {
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      b0[j] = 0.0; b1[j] = 0.0;
+      w.b0[j] = 0.0; w.b1[j] = 0.0;
       if (inrow[j]) {
         const double2 v = *reinterpret_cast<const double2 *>(Bq + (size_t)(s + 1) * Ls + 64 * j);
-        b0[j] = v.x; b1[j] = v.y;
+        w.b0[j] = v.x; w.b1[j] = v.y;
       }
     }
-    cnt = Bnq[s + 1];
+    w.cnt = Bnq[s + 1];
   }
   if (s < bottom) {
     if (a.bv != nullptr && lane == 0) a.bv[q] = bottom;
     return;
   }
 
-  // rows are consumed in the order s+1, s, s-1, ..., bottom
-  int t = s + 1;
-#pragma unroll
-  for (int i = 0; i < MCQ_PF; i++, t--)
-    stage_site<NJ>(gring, ering, t, t >= bottom, look_ahead(a.st, qc, t, t >= bottom), q, a.st, a.em, Gq, lane);
-  SiteAhead ahead = look_ahead(a.st, qc, t, t >= bottom);
+  // rows are consumed in the order tA = s+1, s, s-1, ..., bottom; slot of site t = (tA - t) & 3
+  const int tA = s + 1;
+#define MCQ_BWD_PROLOGUE(K)                                                                                  \
+  {                                                                                                          \
+    const int tt = tA - K;                                                                                   \
+    stage_k<NJ, K>(g_sh, e_sh, tt >= bottom, look_ahead(a.st, qc, tt, tt >= bottom), tabl, ecq + tt,        \
+                   ecq != nullptr, Gl + (ptrdiff_t)tt * (64 * NJ), lane);                                    \
+  }
+  MCQ_BWD_PROLOGUE(0) MCQ_BWD_PROLOGUE(1) MCQ_BWD_PROLOGUE(2)
+#undef MCQ_BWD_PROLOGUE
+  w.t = tA - MCQ_PF;
+  w.ahead = look_ahead(a.st, qc, w.t, w.t >= bottom);
+  w.gsrc = Gl + (ptrdiff_t)w.t * (64 * NJ);
+  w.qcp = qc + (w.t - 1);
+  w.descp = a.st.desc + (w.t - 1);
+  w.ecp = ecq + w.t;
+  w.Rp = a.R + s;
+  w.Bs = Bq + (size_t)s * Ls;
+  w.Bnp = Bnq + s;
   const double invN = 1.0 / (double)a.st.N;
 
   // emission at s+1 and sx
-  double sx;
   {
     cp_async_wait<MCQ_PF - 1>();
     __syncwarp();
-    {
-      const SiteAhead cur = ahead;
-      ahead = look_ahead(a.st, qc, t - 1, t - 1 >= bottom);
-      stage_site<NJ>(gring, ering, t, t >= bottom, cur, q, a.st, a.em, Gq, lane);
-      t--;
-    }
-    LaneSlots<NJ> g;
-    g.load(gring + ((s + 1) % MCQ_RING) * (64 * NJ), lane);
-    const double *es = ering + ((s + 1) % MCQ_RING) * MCQ_ES;
+    bwd_stage<NJ, 0>(a, w, g_sh, e_sh, has_qc, tabl, bottom, lane);
+    unsigned g[(2 * NJ + 3) / 4];
+    load_slots<NJ, 0>(gl, g);
+    const double *es = ering;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
-      e0[j] = es[g.first(j)]; e1[j] = es[g.second(j)];
-      loc += b0[j] * e0[j]; loc += b1[j] * e1[j];
+      w.e0[j] = emis_at(es, g[j >> 1], (j & 1) * 2); w.e1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+      loc += w.b0[j] * w.e0[j]; loc += w.b1[j] * w.e1[j];
     }
-    sx = warp_sum(loc);
+    w.sx = warp_sum(loc);
   }
 
-  double Rnext = a.R[s + 1];
-  for (; s >= bottom; --s) {
-    cp_async_wait<MCQ_PF - 1>();   // rows of site s
-    __syncwarp();
-    {
-      const SiteAhead cur = ahead;
-      ahead = look_ahead(a.st, qc, t - 1, t - 1 >= bottom);
-      stage_site<NJ>(gring, ering, t, t >= bottom, cur, q, a.st, a.em, Gq, lane);
-      t--;
-    }
-    LaneSlots<NJ> g;
-    g.load(gring + (s % MCQ_RING) * (64 * NJ), lane);
-    const double *es = ering + (s % MCQ_RING) * MCQ_ES;
-    const double Rn = Rnext;
-    Rnext = a.R[s];                             // R[(s-1)+1] for the next iteration
-    const double jump = sx * (Rn * invN);       // forward_backward.c:219 (reciprocal: see k_forward)
-    const double stay = 1 - Rn;
-    double locv = 0.0, locy = 0.0, locv2 = 0.0, locy2 = 0.0;
-#pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      const double n0 = es[g.first(j)], n1 = es[g.second(j)];   // emission at s, for the next step's products
-      const double v0 = __fma_rn(stay * b0[j], e0[j], jump) * m0[j];
-      const double v1 = __fma_rn(stay * b1[j], e1[j], jump) * m1[j];
-      b0[j] = v0; b1[j] = v1;
-      locv += v0; locv2 += v1;
-      locy = __fma_rn(v0, n0, locy); locy2 = __fma_rn(v1, n1, locy2);
-      e0[j] = n0; e1[j] = n1;
-    }
-    locv += locv2; locy += locy2;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      locv += __shfl_xor_sync(0xffffffffu, locv, o);
-      locy += __shfl_xor_sync(0xffffffffu, locy, o);
-    }
-    sx = locy;
-    if (locv < MCQ_BIGI) {                      // forward_backward.c:236-242
-      ++cnt;
-#pragma unroll
-      for (int j = 0; j < NJ; j++) { b0[j] *= MCQ_BIG; b1[j] *= MCQ_BIG; }
-      sx *= MCQ_BIG;
-    }
-    double *__restrict__ Bs = Bq + (size_t)s * Ls;
-#pragma unroll
-    for (int j = 0; j < NJ; j++)
-      if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bs + 64 * j), make_double2(b0[j], b1[j]));
-    if (lane == 0) Bnq[s] = cnt;
+  w.Rnext = a.R[s + 1];
+#define MCQ_BWD_SITE(K) \
+  bwd_site<NJ, FULL, K>(a, w, gl, ering, g_sh, e_sh, has_qc, tabl, bottom, lane, inrow, m0, m1, invN)
+  for (; s >= bottom; s -= 4) {
+    MCQ_BWD_SITE(1);
+    if (s - 1 < bottom) break;
+    MCQ_BWD_SITE(2);
+    if (s - 2 < bottom) break;
+    MCQ_BWD_SITE(3);
+    if (s - 3 < bottom) break;
+    MCQ_BWD_SITE(0);
   }
+#undef MCQ_BWD_SITE
   cp_async_wait<0>();
   if (a.bv != nullptr && lane == 0) a.bv[q] = bottom;
 }
