@@ -102,8 +102,11 @@ struct mcq_ctx {
   std::vector<uint8_t> ncodon_h, cons_in_list_h, cons_codon_h, slot_of_h;
 
   McqModel m{};
+  // F and T are the two forward column buffers (buffer 0 / buffer 1); sel[q][s] names the one that holds
+  // the current column, the other one receives proposals (an accept flips selectors, nothing is copied)
   double *F = nullptr, *B = nullptr, *T = nullptr;
   int *Fn = nullptr, *Bn = nullptr, *Tn = nullptr;
+  uint8_t *sel = nullptr;
   // emission rows: shared table + per-query consensus values, current and proposal ("tmp") sets
   double *tab = nullptr, *atab = nullptr, *ec = nullptr, *ac = nullptr;
   double *tab_t = nullptr, *atab_t = nullptr, *ec_t = nullptr, *ac_t = nullptr;
@@ -266,7 +269,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   void *ptrs[] = {c->desc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
-                  c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
+                  c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->sel, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
@@ -418,6 +421,8 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     const size_t cells = (size_t)Q * S * c->Ls;
     ALLOC(c->F, cells); ALLOC(c->B, cells); ALLOC(c->T, cells);
     ALLOC(c->Fn, (size_t)Q * S); ALLOC(c->Bn, (size_t)Q * S); ALLOC(c->Tn, (size_t)Q * S);
+    ALLOC(c->sel, (size_t)Q * S);
+    CK(cudaMemsetAsync(c->sel, 0, (size_t)Q * S, c->stream));
     ALLOC(c->tab, c->TL); ALLOC(c->tab_t, c->TL); ALLOC(c->atab, (size_t)c->NA); ALLOC(c->atab_t, (size_t)c->NA);
     const size_t qs = (size_t)Q * S;
     ALLOC(c->ec, qs); ALLOC(c->ac, qs); ALLOC(c->ec_t, qs); ALLOC(c->ac_t, qs);
@@ -542,15 +547,23 @@ static int run_emission(mcq_ctx *c, int start, int end, int which_hla, int mode,
   return 0;
 }
 
-static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int start, int end, const double *Fin, const int *Fn_in,
-                       double *Fout, int *Fn_out, int llk_mode, double *llk_out, int r_site, double r_value,
-                       bool sparse, int hla, bool lazy = false) {
+// where the columns of a forward run go
+enum FwdMode {
+  FWD_IN_PLACE,   // into the buffer holding the current column (the full sweep, refills): counters into Fn
+  FWD_PROPOSAL,   // into the other buffer (tmp_F of the reference): counters into Tn
+  FWD_NO_STORE    // nowhere: likelihood only
+};
+
+static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int start, int end, FwdMode mode, int llk_mode,
+                       double *llk_out, int r_site, double r_value, bool sparse, int hla, bool lazy = false) {
   FwdArgs a;
   a.st = make_static(c);
   a.em.tab = tab; a.em.ec = ec; a.R = c->m.R; a.r_site = r_site; a.r_value = r_value;
   a.em_pre.tab = c->tab; a.em_pre.ec = c->ec;
   a.fv = lazy ? c->fv : nullptr;   // catch up F before `start` where it is stale
-  a.Fin = Fin; a.Fn_in = Fn_in; a.Fout = Fout; a.Fn_out = Fn_out;
+  a.Fin = c->F; a.Fn_in = c->Fn; a.Fout = c->T; a.sel = c->sel;
+  a.Fn_out = (mode == FWD_PROPOSAL) ? c->Tn : c->Fn;
+  a.in_place = mode == FWD_IN_PLACE; a.no_store = mode == FWD_NO_STORE;
   a.start = start; a.end = end; a.llk_mode = llk_mode;
   a.B = c->B; a.Bn = c->Bn; a.llk_out = llk_out; a.llk_keep = c->llk_cur;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
@@ -632,7 +645,7 @@ static int set_marks(mcq_ctx *c, int f, int b, bool sparse, int hla) {
 static int flush_lazy(mcq_ctx *c) {
   const int S = c->d.num_sites;
   if (c->fv_lo < S - 1) {
-    if (run_forward(c, c->tab, c->ec, S, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, false, 0, true)) return 1;
+    if (run_forward(c, c->tab, c->ec, S, S - 1, FWD_IN_PLACE, 0, nullptr, -1, 0.0, false, 0, true)) return 1;
     c->fv_lo = S - 1;
   }
   if (c->bv_hi > 0) {
@@ -668,7 +681,7 @@ extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
   const int S = c->d.num_sites;
   McqOverride none{}; none.kind = -1;
   if (with_emission && run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
-  if (run_forward(c, c->tab, c->ec, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_IN_PLACE, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
   if (set_marks(c, S - 1, -1, false, 0)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->has_pending = false;
@@ -684,7 +697,7 @@ extern "C" int mcq_ctx_llk_only(mcq_ctx *c, int with_emission, double *llk) {
     if (run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
     if (set_marks(c, -1, S, false, 0)) return 1;     // F and B no longer match the rows: all of both owed
   }
-  if (run_forward(c, c->tab, c->ec, 0, S - 1, c->F, c->Fn, nullptr, nullptr, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_NO_STORE, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->has_pending = false;
   return 0;
@@ -705,7 +718,7 @@ extern "C" int mcq_ctx_init_state(mcq_ctx *c, double *llk) {
   const int S = c->d.num_sites;
   McqOverride none{}; none.kind = -1;
   if (run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
-  if (run_forward(c, c->tab, c->ec, 0, S - 1, c->F, c->Fn, c->F, c->Fn, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_IN_PLACE, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
   if (run_backward(c, S - 1, false, 0)) return 1;
   if (set_marks(c, S - 1, 0, false, 0)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
@@ -726,8 +739,8 @@ static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const Mcq
   const bool need_f = c->opt_lazy && c->fv_lo < ov.start - 1;
   const bool need_b = c->opt_lazy && c->bv_hi > ov.end;
   if (!need_b) {
-    if (run_forward(c, tab, ec, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 1, c->llk_prop, r_site, r_value,
-                    sparse, ov.hla, need_f)) return 1;
+    if (run_forward(c, tab, ec, ov.start, ov.end, FWD_PROPOSAL, 1, c->llk_prop, r_site, r_value, sparse, ov.hla,
+                    need_f)) return 1;
     if (need_f && !sparse) c->fv_lo = ov.start - 1;
     return 0;
   }
@@ -738,12 +751,12 @@ static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const Mcq
     if (run_backward(c, 0, sparse, ov.hla, c->stream2, true, ov.end)) return 1;
     CK(cudaEventRecord(c->ev_join, c->stream2));
   } else if (run_backward(c, 0, sparse, ov.hla, nullptr, true, ov.end)) return 1;
-  if (run_forward(c, tab, ec, ov.start, ov.end, c->F, c->Fn, c->T, c->Tn, 0, nullptr, r_site, r_value, sparse,
-                  ov.hla, need_f)) return 1;
+  if (run_forward(c, tab, ec, ov.start, ov.end, FWD_PROPOSAL, 0, nullptr, r_site, r_value, sparse, ov.hla, need_f))
+    return 1;
   if (dual) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   DotArgs d;
   d.st = make_static(c);
-  d.T = c->T; d.Tn = c->Tn; d.B = c->B; d.Bn = c->Bn; d.site = ov.end;
+  d.T = c->T; d.Tn = c->Tn; d.F = c->F; d.sel = c->sel; d.B = c->B; d.Bn = c->Bn; d.site = ov.end;
   d.llk_out = c->llk_prop; d.llk_keep = c->llk_cur;
   d.active = sparse ? c->hla : nullptr; d.active_hla = ov.hla;
   d.logBIG = c->logBIG;
@@ -796,7 +809,7 @@ extern "C" int mcq_ctx_propose(mcq_ctx *c, const mcq_proposal *p, double *sum_ll
         c->launches++;   // two kernels
       }
       // the whole-genome sweep of mcmc_moves.c:1124-1134 without writing tmp_F: only an accept needs it
-      if (run_forward(c, c->tab_t, c->ec_t, 0, S - 1, c->F, c->Fn, nullptr, nullptr, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
+      if (run_forward(c, c->tab_t, c->ec_t, 0, S - 1, FWD_NO_STORE, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
       break;
     default:
       return mcq_fail(__FILE__, __LINE__, "unknown proposal kind");
@@ -824,10 +837,11 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
   CallScope scope(c);
   const McqStatic st = make_static(c);
   if (ov.kind == MCQ_PROP_MU) {
-    // the proposal was evaluated without writing tmp_F: the same sweep again, this time stored
-    if (run_forward(c, c->tab_t, c->ec_t, 0, S - 1, c->F, c->Fn, c->T, c->Tn, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
-    // the reference swaps the roles of the tmp and current arrays (mcmc_moves.c:1166-1169)
-    swap_ptr(c->F, c->T); swap_ptr(c->Fn, c->Tn); swap_ptr(c->tab, c->tab_t); swap_ptr(c->atab, c->atab_t);
+    // the proposal was evaluated without writing tmp_F: the same sweep again, this time stored - straight
+    // into the current columns, with the proposal's rows, which then become the current ones (the
+    // reference swaps the roles of the tmp and current arrays, mcmc_moves.c:1166-1169)
+    if (run_forward(c, c->tab_t, c->ec_t, 0, S - 1, FWD_IN_PLACE, 2, c->llk_prop, -1, 0.0, false, 0)) return 1;
+    swap_ptr(c->tab, c->tab_t); swap_ptr(c->atab, c->atab_t);
     swap_ptr(c->ec, c->ec_t); swap_ptr(c->ac, c->ac_t);
     c->m.mu = ov.v0;
     if (c->opt_lazy) {
@@ -853,7 +867,7 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
     }
     {
       KScope ks(c, MCQ_K_COMMIT);
-      CK(mcq_launch_commit_cols(st, c->T, c->Tn, c->F, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
+      CK(mcq_launch_commit_cols(st, c->sel, c->Tn, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
     }
     if (c->opt_lazy) {
       // the refills of mcmc_moves.c:266-279 are owed, not run: the next evaluation completes what it needs
@@ -868,7 +882,7 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
         CK(cudaEventRecord(c->ev_join, c->stream2));
       }
       if (ov.end + 1 < S)
-        if (run_forward(c, c->tab, c->ec, ov.end + 1, S - 1, c->F, c->Fn, c->F, c->Fn, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
+        if (run_forward(c, c->tab, c->ec, ov.end + 1, S - 1, FWD_IN_PLACE, 0, nullptr, -1, 0.0, sparse, ov.hla)) return 1;
       if (dual) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
       else if (run_backward(c, ov.end, sparse, ov.hla)) return 1;
     }
@@ -887,15 +901,22 @@ extern "C" int mcq_ctx_get_matrix(mcq_ctx *c, int which, int q, double *out, int
   REQUIRE(q >= 0 && q < c->d.num_query, "query index");
   CK(cudaSetDevice(c->d.device));
   const int S = c->d.num_sites, L = c->d.closest_n, Ls = c->Ls;
-  const double *src = which == MCQ_BUF_F ? c->F : which == MCQ_BUF_B ? c->B : c->T;
   const int *nsrc = which == MCQ_BUF_F ? c->Fn : which == MCQ_BUF_B ? c->Bn : c->Tn;
   if (c->have_state && c->have_params && which != MCQ_BUF_TMP_F && flush_lazy(c)) return 1;
   CK(cudaStreamSynchronize(c->stream));
   if (out) {
-    std::vector<double> slab((size_t)S * Ls);
-    CK(cudaMemcpy(slab.data(), src + (size_t)q * S * Ls, slab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<double> slab((size_t)S * Ls), slab1;
+    std::vector<uint8_t> sel(S, 0);
+    if (which == MCQ_BUF_B) CK(cudaMemcpy(slab.data(), c->B + (size_t)q * S * Ls, slab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    else {   // column by column from the buffer the selector names (the other one for tmp_F)
+      slab1.resize(slab.size());
+      CK(cudaMemcpy(slab.data(), c->F + (size_t)q * S * Ls, slab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(slab1.data(), c->T + (size_t)q * S * Ls, slab.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(sel.data(), c->sel + (size_t)q * S, S, cudaMemcpyDeviceToHost));
+      if (which == MCQ_BUF_TMP_F) for (auto &b : sel) b ^= 1;
+    }
     for (int r = 0; r < L; r++)
-      for (int s = 0; s < S; s++) out[(size_t)r * S + s] = slab[(size_t)s * Ls + r];
+      for (int s = 0; s < S; s++) out[(size_t)r * S + s] = (sel[s] ? slab1 : slab)[(size_t)s * Ls + r];
   }
   if (rnorm) CK(cudaMemcpy(rnorm, nsrc + (size_t)q * S, S * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;

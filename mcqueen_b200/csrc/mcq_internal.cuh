@@ -79,8 +79,15 @@ struct FwdArgs {
   int *fv;                   // [Q] last valid column of Fin per query; nullptr = column start-1 is valid
   const double *R;
   int r_site; double r_value;     // R override at one site (-1 = none)
+  // Two column buffers: Fin = buffer 0, Fout = buffer 1.  sel[q][s] (0/1, or nullptr = always 0) names the
+  // buffer that holds the CURRENT column s of query q.  Column start-1 is read from the current buffer;
+  // catch-up sites and in_place runs write the current buffer, anything else (a proposal) writes the other
+  // one - so an accept only flips selectors (k_commit_cols) instead of copying columns.
   const double *Fin; const int *Fn_in;
   double *Fout; int *Fn_out;
+  const uint8_t *sel;
+  int in_place;              // 1: sites start..end go where the current column is (refills, the full sweep)
+  int no_store;              // 1: likelihood only, no column is written (start must be 0)
   int start, end;
   int llk_mode;              // 0 none, 1 dot with B at `end`, 2 plain column sum at `end`
   const double *B; const int *Bn;
@@ -104,7 +111,9 @@ struct BwdArgs {
 
 struct DotArgs {             // per-query log-likelihood from a proposal column and the backward column
   McqStatic st;
-  const double *T; const int *Tn;
+  const double *T; const int *Tn;   // buffer 1 / proposal counters
+  const double *F;                  // buffer 0
+  const uint8_t *sel;               // [Q][S] which buffer holds the current column (nullptr: buffer 0)
   const double *B; const int *Bn;
   int site;
   double *llk_out;
@@ -144,9 +153,8 @@ cudaError_t mcq_launch_emission_cons(const EmisArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots,
                                   const double *tab, const double *atab, const double *ec, const double *ac,
                                   double *tab_o, double *atab_o, double *ec_o, double *ac_o, cudaStream_t stream);
-cudaError_t mcq_launch_commit_cols(const McqStatic &st, const double *T, const int *Tn, double *F, int *Fn,
-                                   int start, int end, const uint8_t *active, int active_hla,
-                                   cudaStream_t stream);
+cudaError_t mcq_launch_commit_cols(const McqStatic &st, uint8_t *sel, const int *Tn, int *Fn, int start, int end,
+                                   const uint8_t *active, int active_hla, cudaStream_t stream);
 cudaError_t mcq_launch_copy(const double *src, double *dst, size_t n, cudaStream_t stream);
 cudaError_t mcq_launch_commit_cons(const McqStatic &st, const double *ec_t, const double *ac_t, double *ec,
                                    double *ac, int start, int end, cudaStream_t stream);

@@ -541,8 +541,10 @@ struct FwdWarp {              // what one warp carries from site to site
   const uint8_t *qcp;         // the query's codon at site t + 1
   const int2 *descp;          // descriptor of site t + 1
   const double *Rp;           // R of the site after the one being computed
-  double *Fs;                 // output column of the site being computed (this lane's states)
-  int *Fnp;                   // its rescale counter
+  double *Fs;                 // column of the site being computed in buffer 0 (this lane's states)
+  int *Fnp;                   // its rescale counter (output array)
+  const uint8_t *selp;        // column selector of the site after the next one
+  unsigned selnext;           // column selector of the next site
 };
 
 // the look-ahead of the site after w.t, through the running pointers
@@ -564,8 +566,8 @@ template <int NJ, bool FULL, bool PRE, bool STORE, int K>
 __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s, const uint8_t *gl, const double *ering,
                                          unsigned g_sh, unsigned e_sh, bool has_qc, const double *tabl,
                                          const double *tabl_pre, const double *ecq, const double *ecq_pre,
-                                         int lane, const bool (&inrow)[NJ], double invN, ptrdiff_t pre_delta,
-                                         int *Fnc) {
+                                         int lane, const bool (&inrow)[NJ], double invN, ptrdiff_t delta,
+                                         bool has_sel, int *Fnc) {
   cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed (this lane's copies)
   __syncwarp();                  // ... and every other lane's; the slot of site s-1 is free again
   {
@@ -610,9 +612,16 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
     w.tot *= MCQ_BIG;
   }
   if (STORE) {
-    // a catch-up site goes into the current matrix: the same offset, pre_delta doubles away
+    // the column goes into the buffer that holds the current one (a catch-up site, an in-place refill)
+    // or into the other one (a proposal): the same offset, `delta` doubles away
     const bool pre = PRE && s < a.start;
-    double *__restrict__ Fs = pre ? w.Fs + pre_delta : w.Fs;
+    const unsigned cur1 = w.selnext;
+    if (has_sel) {
+      if (s + 1 <= a.end) w.selnext = *w.selp;
+      w.selp++;
+    }
+    const bool into1 = (cur1 != 0) != (!a.in_place && !pre);
+    double *__restrict__ Fs = into1 ? w.Fs + delta : w.Fs;
 #pragma unroll
     for (int j = 0; j < NJ; j++)
       if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(w.p0[j], w.p1[j]));
@@ -652,8 +661,11 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
     if (v < a.start - 1) s0 = v + 1;
   }
   const bool caught_up = PRE && s0 < a.start;
-  double *Fo = STORE ? a.Fout + qoff + 2 * lane : nullptr;
-  double *Fc = const_cast<double *>(a.Fin) + qoff + 2 * lane;
+  // buffer 0 = Fin, buffer 1 = Fout; sel[q][s] says which one holds the current column s (none: buffer 0)
+  double *X0 = const_cast<double *>(a.Fin) + qoff + 2 * lane;
+  const ptrdiff_t delta = STORE ? (a.Fout - a.Fin) : 0;
+  const bool has_sel = a.sel != nullptr;
+  const uint8_t *selq = has_sel ? a.sel + (size_t)q * S : nullptr;
   int *Fno = STORE ? a.Fn_out + (size_t)q * S : nullptr;
   int *Fnc = const_cast<int *>(a.Fn_in) + (size_t)q * S;
   uint8_t *gring = &s_g[wib][0][0];
@@ -692,9 +704,10 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   w.qcp = qc + w.t + 1;
   w.descp = a.st.desc + w.t + 1;
   w.Rp = a.R + sA + 1;
-  w.Fs = STORE ? Fo + (size_t)sA * Ls : nullptr;
+  w.Fs = X0 + (size_t)sA * Ls;
   w.Fnp = STORE ? Fno + sA : nullptr;
-  const ptrdiff_t pre_delta = (PRE && STORE) ? (Fc - Fo) : 0;
+  w.selnext = (has_sel && sA <= a.end) ? selq[sA] : 0u;
+  w.selp = selq + sA + 1;
   const double invN = 1.0 / (double)a.st.N;
 
   if (s0 == 0) {
@@ -704,7 +717,9 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
     unsigned g[(2 * NJ + 3) / 4];
     load_slots<NJ, 3>(gl, g);
     const double *es = ering + 3 * MCQ_ES;
-    double *F0 = (PRE && 0 < a.start) ? Fc : Fo;      // column 0 belongs to the catch-up when start > 0
+    // column 0 belongs to the catch-up when start > 0
+    const bool into1 = ((has_sel ? selq[0] : 0) != 0) != (!a.in_place && !(PRE && 0 < a.start));
+    double *F0 = into1 ? X0 + delta : X0;
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
@@ -720,7 +735,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
     }
     w.tot = warp_sum(loc);
   } else {
-    const double *__restrict__ Fi = Fc + (size_t)(s0 - 1) * Ls;
+    const double *__restrict__ Fi = X0 + (size_t)(s0 - 1) * Ls + ((has_sel && selq[s0 - 1]) ? (a.Fout - a.Fin) : 0);
     double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
@@ -738,7 +753,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   w.Rnext = (sA <= a.end) ? ((sA == a.r_site) ? a.r_value : a.R[sA]) : 0.0;
 #define MCQ_FWD_SITE(K, SITE)                                                                                     \
   fwd_site<NJ, FULL, PRE, STORE, K>(a, w, SITE, gl, ering, g_sh, e_sh, has_qc, tabl, tabl_pre, ecq, ecq_pre, lane, \
-                                    inrow, invN, pre_delta, Fnc)
+                                    inrow, invN, delta, has_sel, Fnc)
   for (int s = sA; s <= a.end; s += 4) {
     MCQ_FWD_SITE(0, s);
     if (s + 1 > a.end) break;
@@ -789,7 +804,7 @@ static cudaError_t launch_forward_nj(const FwdArgs &a, cudaStream_t stream) {
 }
 
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
-  if (a.Fout == nullptr) {          // likelihood only: no column is written
+  if (a.no_store) {                 // likelihood only: no column is written
     if (a.fv != nullptr || a.start != 0) return cudaErrorInvalidValue;
     switch (a.st.Lg / 64) {
       case 1: return launch_forward_nj<1, false>(a, stream);
@@ -1061,7 +1076,9 @@ __global__ void __launch_bounds__(128) k_dot(const DotArgs a) {
   }
   const int S = a.st.S, Ls = a.st.Ls;
   const size_t col = ((size_t)q * S + a.site) * Ls;
-  const double2 *__restrict__ t = reinterpret_cast<const double2 *>(a.T + col);
+  // the proposal's column is in the buffer that does NOT hold the current one
+  const double *Tq = (a.sel != nullptr && a.sel[(size_t)q * S + a.site] != 0) ? a.F : a.T;
+  const double2 *__restrict__ t = reinterpret_cast<const double2 *>(Tq + col);
   const double2 *__restrict__ b = reinterpret_cast<const double2 *>(a.B + col);
   double loc = 0.0;          // the same lane mapping and order as the epilogue of k_forward
   for (int i = lane; i < Ls / 2; i += 32) {
@@ -1096,40 +1113,28 @@ cudaError_t mcq_launch_set_valid(int *fv, int *bv, int Q, int H, int f, int b, c
 // ------------------------------------------------------------------------------------------
 // K7: accept-commit copies
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_commit_cols(const McqStatic st, const double *__restrict__ T,
-                                                     const int *__restrict__ Tn, double *__restrict__ F,
-                                                     int *__restrict__ Fn, int start, int end,
+// The proposal's columns start..end become current: their selectors flip (the proposal was written into
+// the buffer that did not hold the current column, so nothing is copied) and the rescale counters follow.
+__global__ void __launch_bounds__(256) k_commit_cols(const McqStatic st, uint8_t *__restrict__ sel,
+                                                     const int *__restrict__ Tn, int *__restrict__ Fn, int start, int W,
                                                      const uint8_t *__restrict__ active, int active_hla) {
-  const int q = blockIdx.y;
-  if (active != nullptr && active[(size_t)q * st.H + active_hla] == 0) return;
-  const int W = end - start + 1;
-  const size_t base = ((size_t)q * st.S + start) * st.Ls;
-  const size_t n2 = (size_t)W * st.Ls / 2;
-  const double2 *__restrict__ src = reinterpret_cast<const double2 *>(T + base);
-  double2 *__restrict__ dst = reinterpret_cast<double2 *>(F + base);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = src[i];
-  if (blockIdx.x == 0)
-    for (int s = start + threadIdx.x; s <= end; s += blockDim.x)
-      Fn[(size_t)q * st.S + s] = Tn[(size_t)q * st.S + s];
+  const unsigned n = (unsigned)st.Q * (unsigned)W;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned q = i / W;
+    if (active != nullptr && active[(size_t)q * st.H + active_hla] == 0) continue;
+    const size_t o = (size_t)q * st.S + start + (i % W);
+    sel[o] ^= 1;
+    Fn[o] = Tn[o];
+  }
 }
 
-cudaError_t mcq_launch_commit_cols(const McqStatic &st, const double *T, const int *Tn, double *F, int *Fn,
-                                   int start, int end, const uint8_t *active, int active_hla,
-                                   cudaStream_t stream) {
-  const size_t n2 = (size_t)(end - start + 1) * st.Ls / 2;
-  unsigned bx = (unsigned)((n2 + 255) / 256);
-  if (bx > 64) bx = 64;
-  if (bx < 1) bx = 1;
-  for (int q0 = 0; q0 < st.Q; q0 += 65535) {
-    McqStatic s2 = st;
-    int nq = st.Q - q0 < 65535 ? st.Q - q0 : 65535;
-    dim3 grid(bx, nq);
-    s2.Q = nq;
-    k_commit_cols<<<grid, 256, 0, stream>>>(s2, T + (size_t)q0 * st.S * st.Ls, Tn + (size_t)q0 * st.S,
-                                            F + (size_t)q0 * st.S * st.Ls, Fn + (size_t)q0 * st.S, start, end,
-                                            active ? active + (size_t)q0 * st.H : nullptr, active_hla);
-  }
+cudaError_t mcq_launch_commit_cols(const McqStatic &st, uint8_t *sel, const int *Tn, int *Fn, int start, int end,
+                                   const uint8_t *active, int active_hla, cudaStream_t stream) {
+  const int W = end - start + 1;
+  const unsigned n = (unsigned)st.Q * (unsigned)W;
+  unsigned blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_commit_cols<<<blocks, 256, 0, stream>>>(st, sel, Tn, Fn, start, W, active, active_hla);
   return cudaGetLastError();
 }
 

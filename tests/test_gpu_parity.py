@@ -129,6 +129,28 @@ def test_proposals_and_accepts_track_the_oracle(api, sparse, lazy):
     ctx.close()
 
 
+def test_proposal_columns_and_selector_flip(api):
+    """A proposal's columns land in the buffer that does not hold the current ones (tmp_F of the
+    reference, mcmc_moves.c:805) and an accept makes them current by flipping selectors: tmp_F after the
+    proposal, F after the accept and after a second, overlapping accept all match the CPU chain."""
+    p = make_problem("toy", gaps=True)
+    cpu = CpuState(checker(), p)
+    ctx = api.Context.from_problem(p)
+    ctx.init_state()
+    for mv in (dict(kind=REV, start=10, end=30, value0=1.3), dict(kind=ESC, start=20, end=45, hla=2, value0=0.6),
+               dict(kind=REC, start=25, value0=0.04), dict(kind=REV, start=0, end=p.S - 1, value0=0.9)):
+        want, got = cpu.propose(**mv), ctx.propose(**mv)
+        assert abs(got - want) <= RTOL_LLK * abs(want)
+        end = mv.get("end", mv["start"])
+        for q in (0, 11, p.Q - 1):
+            T, Tn = ctx.matrix(api.BUF_TMP_F, q)
+            sl = slice(mv["start"], end + 1)
+            assert np.array_equal(Tn[sl], cpu.tFn[q][sl]) and rel(T[:, sl], cpu.tF[q][:, sl]) < RTOL_CELL
+        cpu.accept(); ctx.accept()
+        assert_state_matches(ctx, cpu, [0, 11, p.Q - 1])
+    ctx.close()
+
+
 @pytest.mark.parametrize("sparse", [0, 1])
 def test_lazy_refills_are_bit_identical_to_eager(api, sparse):
     """Owed refills (MCQ_OPT_LAZY_REFILL) compute the columns the reference would have computed at the
