@@ -131,7 +131,7 @@ struct mcq_ctx {
   int k_n[MCQ_K_CLASSES] = {0};
 
   // staging buffers of mcq_ctx_upload_static (kept so that a re-upload allocates nothing)
-  int8_t *st_trip = nullptr, *st_cons = nullptr;
+  int8_t *st_trip = nullptr, *st_trip_pad = nullptr, *st_cons = nullptr;
   int *st_closest = nullptr;
   uint8_t *st_slot_of = nullptr, *st_trip_tab = nullptr;
 
@@ -269,7 +269,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   void *ptrs[] = {c->desc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
-                  c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->sel, c->st_trip, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
+                  c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->sel, c->st_trip, c->st_trip_pad, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
@@ -414,6 +414,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     ALLOC(c->hla, (size_t)Q * H);
     ALLOC(c->G, (size_t)Q * S * c->Lg);
     ALLOC(c->st_trip, (size_t)N * S);
+    ALLOC(c->st_trip_pad, (size_t)N * ((S + 31) / 32 * 32));
     ALLOC(c->st_cons, (size_t)Q * 3 * S);
     ALLOC(c->st_closest, (size_t)Q * L);
     ALLOC(c->st_slot_of, (size_t)S * 64);
@@ -461,7 +462,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
   {
     KScope ks(c, MCQ_K_GATHER);
-    CK(mcq_launch_gather(c->st_trip, c->st_closest, c->st_cons, c->st_slot_of, c->st_trip_tab, c->G, c->hla, Q, S, L,
+    CK(mcq_launch_gather(c->st_trip, c->st_trip_pad, c->st_closest, c->st_cons, c->st_slot_of, c->st_trip_tab, c->G, c->hla, Q, S, L,
                          c->Lg, N, H, c->d_err, c->stream));
   }
   CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

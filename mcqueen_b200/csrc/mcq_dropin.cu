@@ -36,7 +36,7 @@ struct Scratch {
   bool tables = false;
   cudaStream_t stream = nullptr;
   // device
-  int8_t *trip = nullptr, *cons = nullptr;
+  int8_t *trip = nullptr, *trip_pad = nullptr, *cons = nullptr;
   int *closest = nullptr, *aoff = nullptr, *Fn = nullptr, *Tn = nullptr, *d_err = nullptr;
   int2 *desc = nullptr;
   uint8_t *slot_of = nullptr, *trip_tab = nullptr, *G = nullptr;
@@ -47,10 +47,10 @@ struct Scratch {
   std::vector<int> h_n;
 
   void release() {
-    void *p[] = {trip, cons, closest, aoff, desc, Fn, Tn, slot_of, trip_tab, G, E, R, F, T};
+    void *p[] = {trip, trip_pad, cons, closest, aoff, desc, Fn, Tn, slot_of, trip_tab, G, E, R, F, T};
     for (void *x : p)
       if (x) cudaFree(x);
-    trip = cons = nullptr; closest = aoff = Fn = Tn = nullptr; desc = nullptr; slot_of = trip_tab = G = nullptr;
+    trip = trip_pad = cons = nullptr; closest = aoff = Fn = Tn = nullptr; desc = nullptr; slot_of = trip_tab = G = nullptr;
     E = R = F = T = nullptr;
   }
 
@@ -72,6 +72,7 @@ struct Scratch {
     Lg = 64;
     while (Lg < Ls) Lg *= 2;
     DK(cudaMalloc((void **)&trip, (size_t)L * S));
+    DK(cudaMalloc((void **)&trip_pad, (size_t)L * ((S + 31) / 32 * 32)));
     DK(cudaMalloc((void **)&cons, (size_t)3 * S));
     DK(cudaMalloc((void **)&closest, (size_t)L * sizeof(int)));
     DK(cudaMalloc((void **)&aoff, (size_t)(S + 1) * sizeof(int)));
@@ -127,7 +128,7 @@ struct Scratch {
     DK(cudaMemcpyAsync(cons, cons_nucls, (size_t)3 * S, cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(E, h_E.data(), h_E.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(R, Rh, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, stream));
-    DK(mcq_launch_gather(trip, closest, cons, slot_of, trip_tab, G, nullptr, 1, S, L, Lg, L, 1, d_err, stream));
+    DK(mcq_launch_gather(trip, trip_pad, closest, cons, slot_of, trip_tab, G, nullptr, 1, S, L, Lg, L, 1, d_err, stream));
   }
 
   // one column host[L][S] (stride S) -> device column

@@ -134,7 +134,8 @@ struct EmisArgs {
 
 // launchers (mcq_kernels.cu); all asynchronous on `stream`, return cudaGetLastError()
 cudaError_t mcq_launch_tables_init();
-cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, const int8_t *cons_nucls,
+cudaError_t mcq_launch_gather(const int8_t *ref_triplets, int8_t *trip_pad /*[N][ceil32(S)] scratch*/,
+                              const int *closest, const int8_t *cons_nucls,
                               const uint8_t *slot_of /*[S][64]*/, uint8_t *trip_tab /*[ceil32(S)][128] scratch*/,
                               uint8_t *G, uint8_t *hla_chars /*[Q][H] '0'/'1' -> 0/1 in place, or null*/, int Q, int S,
                               int L, int Lg, int N, int H, int *err /*device flag: 2 = closest out of range*/,

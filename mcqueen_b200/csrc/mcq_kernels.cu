@@ -80,8 +80,9 @@ __device__ __forceinline__ int g_state_of(int pos, int lg2) {   // lg2 = log2(2*
 #define MCQ_NEEDS_CONS 0xFE   // table entry of a triplet with an unknown base: resolved per query
 
 // triplet -> slot per site for triplets without unknown bases (query independent); 128 entries per
-// site, 125 = "no state" -> MCQ_NOSLOT.  Stored per block of 32 sites as [128 triplets][32 sites] so that
-// k_gather can keep it in shared memory with the bank depending on the lane (= site) only.
+// site, 125..127 = "no state" -> MCQ_NOSLOT.  Stored [site][128]: k_gather keeps the 32 sites of its
+// block in shared memory; the lanes of a warp look up the same site with different triplets, which land
+// in different banks (125 triplets = 32 words) or broadcast.
 __global__ void __launch_bounds__(128) k_trip_table(const uint8_t *__restrict__ slot_of, uint8_t *__restrict__ trip_tab,
                                                     int S) {
   const int s = blockIdx.x, t = threadIdx.x;
@@ -90,86 +91,98 @@ __global__ void __launch_bounds__(128) k_trip_table(const uint8_t *__restrict__ 
     const int d0 = t / 25, d1 = (t / 5) % 5, d2 = t % 5;
     v = (d0 == 4 || d1 == 4 || d2 == 4) ? MCQ_NEEDS_CONS : slot_of[(size_t)s * 64 + d0 * 16 + d1 * 4 + d2];
   }
-  trip_tab[(size_t)(s >> 5) * 4096 + t * 32 + (s & 31)] = v;
+  trip_tab[(size_t)s * 128 + t] = v;
 }
 
-__global__ void __launch_bounds__(256) k_gather(const int8_t *__restrict__ ref_triplets,
-                                                const int *__restrict__ closest,
-                                                const int8_t *__restrict__ cons_nucls,
-                                                const uint8_t *__restrict__ slot_of,
-                                                const uint8_t *__restrict__ trip_tab,
-                                                uint32_t *__restrict__ G, int S, int L, int Lg, int N,
-                                                int *__restrict__ err) {
-  extern __shared__ uint32_t tile[];                // [32][Lg/4 + 1] words: odd stride, conflict-free both ways
-  __shared__ __align__(16) unsigned s_off[1024];    // row offset (ref*S) of the state at each PHYSICAL position
-  __shared__ uint32_t s_tab[128 * 32];              // [triplet][site of the block]: bank == lane, conflict-free
+// ref_triplets[N][S] -> rows of pitch Sp (a multiple of 32, padded with "no state"): every run of 32
+// sites of a reference is then one aligned 32-byte sector that a thread fetches with two 16-byte loads
+__global__ void __launch_bounds__(256) k_pad_rows(const int8_t *__restrict__ src, uint32_t *__restrict__ dst, int N, int S,
+                                                  int Sp) {
+  const size_t wpr = (size_t)(Sp >> 2), n = (size_t)N * wpr;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / wpr;
+    const int c0 = (int)(i - row * wpr) * 4;
+    const int8_t *p = src + row * S + c0;
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) w |= (uint32_t)(uint8_t)(c0 + b < S ? p[b] : 125) << (8 * b);
+    dst[i] = w;
+  }
+}
+
+// One block per (query, 32 sites).  A thread owns FOUR consecutive physical positions of the G rows (= four
+// copy states): it fetches the 32 triplets each of its references shows at the block's sites (one aligned
+// sector per reference, two 16-byte loads), turns each into the site's slot through the table in shared
+// memory and stores one 32-bit word per site - a warp writes 128 contiguous bytes of a G row per store.
+__global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ trip_pad, int Sp,
+                                                   const int *__restrict__ closest,
+                                                   const int8_t *__restrict__ cons_nucls,
+                                                   const uint8_t *__restrict__ slot_of,
+                                                   const uint8_t *__restrict__ trip_tab,
+                                                   uint8_t *__restrict__ G, int S, int L, int Lg, int N,
+                                                   int *__restrict__ err) {
+  __shared__ __align__(16) uint8_t s_tab[32 * 128]; // [site of the block][triplet]
   const int q = blockIdx.y;
   const int s0 = blockIdx.x * 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int words = Lg >> 2, stride = words + 1;
   const int lg2 = 31 - __clz(Lg >> 5);              // log2(2 * NJ)
-  const int s = s0 + lane;
-  for (int pos = threadIdx.x; pos < Lg; pos += 256) {
-    const int r = g_state_of(pos, lg2);
-    unsigned off = 0xFFFFFFFFu;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    reinterpret_cast<uint4 *>(s_tab)[i] = reinterpret_cast<const uint4 *>(trip_tab + (size_t)s0 * 128)[i];
+  __syncthreads();
+  const int pos = 4 * threadIdx.x;
+  if (pos >= Lg) return;
+  // the four references; padding states (r >= L) read row 0 and are overwritten with MCQ_NOSLOT below
+  unsigned w[4][8];
+  unsigned padmask = 0;                             // byte k = 0xFF when position pos + k is padding
+  size_t roff[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int r = g_state_of(pos + k, lg2);
+    int ref = 0;
     if (r < L) {
-      int ref = closest[(size_t)q * L + r];
+      ref = closest[(size_t)q * L + r];
       if ((unsigned)ref >= (unsigned)N) { ref = 0; *err = 2; }   // reported by mcq_ctx_upload_static
-      off = (unsigned)ref * (unsigned)S;
-    }
-    s_off[pos] = off;
+    } else padmask |= 0xFFu << (8 * k);
+    roff[k] = (size_t)ref * Sp + s0;
+    const uint4 *src = reinterpret_cast<const uint4 *>(trip_pad + roff[k]);
+    const uint4 a = src[0], b = src[1];
+    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+    w[k][4] = b.x; w[k][5] = b.y; w[k][6] = b.z; w[k][7] = b.w;
   }
-  for (int i = threadIdx.x; i < 1024; i += 256) {
-    const uint32_t w4 = reinterpret_cast<const uint32_t *>(trip_tab + (size_t)blockIdx.x * 4096)[i];
-    s_tab[4 * i + 0] = w4 & 0xFF; s_tab[4 * i + 1] = (w4 >> 8) & 0xFF;
-    s_tab[4 * i + 2] = (w4 >> 16) & 0xFF; s_tab[4 * i + 3] = w4 >> 24;
+  const unsigned padfill = padmask & (MCQ_NOSLOT * 0x01010101u);
+  uint8_t *dst = G + ((size_t)q * S + s0) * Lg + pos;
+  const int nrow = min(32, S - s0);
+  unsigned worst = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const uint8_t *tb = s_tab + i * 128;
+    const unsigned b0 = tb[__byte_perm(w[0][i >> 2], 0, 0x4440 + (i & 3))];
+    const unsigned b1 = tb[__byte_perm(w[1][i >> 2], 0, 0x4440 + (i & 3))];
+    const unsigned b2 = tb[__byte_perm(w[2][i >> 2], 0, 0x4440 + (i & 3))];
+    const unsigned b3 = tb[__byte_perm(w[3][i >> 2], 0, 0x4440 + (i & 3))];
+    unsigned word = __byte_perm(b0 | (b1 << 8), b2 | (b3 << 8), 0x5410);
+    word = (word & ~padmask) | padfill;
+    worst |= word;
+    if (i < nrow) *reinterpret_cast<unsigned *>(dst + (size_t)i * Lg) = word;
   }
-  __syncthreads();
-  const uint32_t *tab = s_tab + lane;
-  const int8_t *col = ref_triplets + (s < S ? s : 0);
-  // read phase: a thread builds 4 consecutive physical bytes of its site's row per step; the 8 loads of
-  // two steps are issued before any is used
-  for (int m0 = warp; m0 < words; m0 += 16) {
-    int t[2][4];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int m = m0 + 8 * h;
-      uint4 o = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-      if (m < words) o = reinterpret_cast<const uint4 *>(s_off)[m];
-      t[h][0] = o.x != 0xFFFFFFFFu ? (int)col[o.x] : 125;
-      t[h][1] = o.y != 0xFFFFFFFFu ? (int)col[o.y] : 125;
-      t[h][2] = o.z != 0xFFFFFFFFu ? (int)col[o.z] : 125;
-      t[h][3] = o.w != 0xFFFFFFFFu ? (int)col[o.w] : 125;
-    }
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int m = m0 + 8 * h;
-      if (m >= words) break;
-      uint32_t word = 0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        unsigned slot = tab[t[h][i] * 32];
-        if (slot == MCQ_NEEDS_CONS) {
-          // triplet_to_codon (amino_acids.c:50-66): unknown bases take the query's local consensus
-          const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
-          const int tt = t[h][i];
-          int d0 = tt / 25, d1 = (tt / 5) % 5, d2 = tt % 5;
-          if (d0 == 4) d0 = cn[0];
-          if (d1 == 4) d1 = cn[1];
-          if (d2 == 4) d2 = cn[2];
-          slot = slot_of[(size_t)s * 64 + (d0 * 16 + d1 * 4 + d2)];
-        }
-        word |= slot << (8 * i);
+  // every real slot value is below 0x80, MCQ_NEEDS_CONS is not: bit 7 of the OR says whether any occurred
+  if (worst & 0x80808080u) {
+    // triplet_to_codon (amino_acids.c:50-66): unknown bases take the query's local consensus
+#pragma unroll 1
+    for (int i = 0; i < nrow; i++) {
+      const int s = s0 + i;
+#pragma unroll 1
+      for (int k = 0; k < 4; k++) {
+        if ((padmask >> (8 * k)) & 1) continue;
+        const unsigned tt = (uint8_t)trip_pad[roff[k] + i];
+        if (s_tab[i * 128 + tt] != MCQ_NEEDS_CONS) continue;
+        const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
+        int d0 = tt / 25, d1 = (tt / 5) % 5, d2 = tt % 5;
+        if (d0 == 4) d0 = cn[0];
+        if (d1 == 4) d1 = cn[1];
+        if (d2 == 4) d2 = cn[2];
+        dst[(size_t)i * Lg + k] = slot_of[(size_t)s * 64 + (d0 * 16 + d1 * 4 + d2)];
       }
-      tile[lane * stride + m] = word;
     }
-  }
-  __syncthreads();
-  for (int ss = warp; ss < 32; ss += 8) {
-    const int so = s0 + ss;
-    if (so >= S) break;
-    uint32_t *dst = G + ((size_t)q * S + so) * words;
-    for (int i = lane; i < words; i += 32) dst[i] = tile[ss * stride + i];
   }
 }
 
@@ -179,25 +192,27 @@ __global__ void __launch_bounds__(256) k_hla_bits(uint8_t *hla, size_t n) {
   if (i < n) hla[i] = (hla[i] == '1');
 }
 
-cudaError_t mcq_launch_gather(const int8_t *ref_triplets, const int *closest, const int8_t *cons_nucls,
+cudaError_t mcq_launch_gather(const int8_t *ref_triplets, int8_t *trip_pad, const int *closest, const int8_t *cons_nucls,
                               const uint8_t *slot_of, uint8_t *trip_tab, uint8_t *G, uint8_t *hla_chars, int Q, int S,
                               int L, int Lg, int N, int H, int *err, cudaStream_t stream) {
-  const int sblocks = (S + 31) / 32;
+  const int sblocks = (S + 31) / 32, Sp = sblocks * 32;
   if (hla_chars != nullptr) {
     const size_t n = (size_t)Q * H;
     k_hla_bits<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(hla_chars, n);
   }
   k_trip_table<<<sblocks * 32, 128, 0, stream>>>(slot_of, trip_tab, S);
-  const size_t smem = (size_t)32 * (Lg / 4 + 1) * sizeof(uint32_t);
-  // static (20 KB) + dynamic shared memory passes the 48 KB default for the widest rows
-  cudaError_t e = cudaFuncSetAttribute(k_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  {
+    const size_t words = (size_t)N * (Sp / 4);
+    unsigned blocks = (unsigned)((words + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_pad_rows<<<blocks, 256, 0, stream>>>(ref_triplets, reinterpret_cast<uint32_t *>(trip_pad), N, S, Sp);
+  }
+  const int threads = Lg / 4 < 32 ? 32 : Lg / 4;
   for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
     int nq = Q - q0 < 65535 ? Q - q0 : 65535;
     dim3 grid(sblocks, nq);
-    k_gather<<<grid, 256, smem, stream>>>(ref_triplets, closest + (size_t)q0 * L,
-                                          cons_nucls + (size_t)q0 * 3 * S, slot_of, trip_tab,
-                                          reinterpret_cast<uint32_t *>(G + (size_t)q0 * S * Lg), S, L, Lg, N, err);
+    k_gather<<<grid, threads, 0, stream>>>(trip_pad, Sp, closest + (size_t)q0 * L, cons_nucls + (size_t)q0 * 3 * S,
+                                              slot_of, trip_tab, G + (size_t)q0 * S * Lg, S, L, Lg, N, err);
   }
   return cudaGetLastError();
 }
