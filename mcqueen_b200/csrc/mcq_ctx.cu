@@ -113,6 +113,8 @@ struct mcq_ctx {
   double *llk_cur = nullptr, *llk_prop = nullptr, *d_sum = nullptr;
   int *fv = nullptr, *bv = nullptr;   // per query: F valid up to fv, B valid from bv (lazy refills)
   double *h_sum = nullptr;   // pinned
+  McqHostSlot *h_slot = nullptr, *d_slot = nullptr;   // host-mapped result slot and its device view
+  unsigned long long eval_seq = 0;
 
   McqOverride pending{};
   bool has_pending = false;
@@ -255,6 +257,9 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   CK(cudaMallocHost((void **)&c->h_sum, sizeof(double)));
   CK(cudaMallocHost((void **)&c->h_err, sizeof(int)));
   *c->h_err = 0;
+  CK(cudaHostAlloc((void **)&c->h_slot, sizeof(McqHostSlot), cudaHostAllocMapped));
+  memset(c->h_slot, 0, sizeof(McqHostSlot));
+  CK(cudaHostGetDevicePointer((void **)&c->d_slot, c->h_slot, 0));
   ALLOC(c->d_err, 1);
   CK(cudaMemset(c->d_err, 0, sizeof(int)));
   c->pending.kind = -1;
@@ -274,6 +279,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
     if (p) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
   if (c->h_err) cudaFreeHost(c->h_err);
+  if (c->h_slot) cudaFreeHost(c->h_slot);
   if (c->d_err) cudaFree(c->d_err);
   for (int r = 0; r < 16; r++)
     if (c->peer_map[r]) cudaIpcCloseMemHandle(c->peer_map[r]);
@@ -595,33 +601,54 @@ static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream
   return 0;
 }
 
+// Wait for the reduction kernel to publish evaluation `want` in the host-mapped slot.  The stream is
+// queried now and then so that a failed launch cannot leave the host spinning.
+static int wait_slot(mcq_ctx *c, unsigned long long want) {
+  volatile unsigned long long *seq = &c->h_slot->seq;
+  for (unsigned spins = 1; *seq != want; spins++) {
+    __builtin_ia32_pause();
+    if ((spins & 0x3FFF) == 0) {
+      const cudaError_t e = cudaStreamQuery(c->stream);
+      if (e == cudaSuccess) {
+        if (*seq == want) break;
+        return mcq_fail(__FILE__, __LINE__, "the reduction kernel finished without publishing its result");
+      }
+      if (e != cudaErrorNotReady) return mcq_fail(__FILE__, __LINE__, cudaGetErrorString(e));
+    }
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  return 0;
+}
+
 // total over the shard (+ all ranks), brought to the host
 static int reduce_llk(mcq_ctx *c, const double *per_query, double *out) {
+  const unsigned long long want = ++c->eval_seq;
   if (c->have_peers) {
     // shard total + NVLink mailbox exchange in one kernel
     {
       KScope ks(c, MCQ_K_SUM);
       c->step++;
-      CK(mcq_launch_sum_exchange(per_query, c->d.num_query, c->d_sum, &c->box, c->step, c->d_err, c->stream));
+      CK(mcq_launch_sum_exchange(per_query, c->d.num_query, c->d_sum, &c->box, c->step, c->d_err, c->d_slot, want, c->stream));
     }
-    CK(cudaMemcpyAsync(c->h_sum, c->d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    REQUIRE(*c->h_err == 0, "peer exchange timed out: a rank did not reach the same evaluation");
-    if (out) *out = *c->h_sum;
+    if (wait_slot(c, want)) return 1;
+    REQUIRE(c->h_slot->err == 0, "peer exchange timed out: a rank did not reach the same evaluation");
+    if (out) *out = c->h_slot->value;
     return 0;
   }
   {
     KScope ks(c, MCQ_K_SUM);
-    CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->stream));
+    CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->comm ? nullptr : c->d_slot, want, c->stream));
   }
   if (c->comm) {
     int r = g_nccl.AllReduce(c->d_sum, c->d_sum, 1, kNcclDouble, kNcclSum, c->comm, c->stream);
     if (r != 0) return mcq_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce failed");
+    CK(cudaMemcpyAsync(c->h_sum, c->d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (out) *out = *c->h_sum;
+    return 0;
   }
-  CK(cudaMemcpyAsync(c->h_sum, c->d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  if (out) *out = *c->h_sum;
+  if (wait_slot(c, want)) return 1;
+  if (out) *out = c->h_slot->value;
   return 0;
 }
 

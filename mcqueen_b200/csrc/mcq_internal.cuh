@@ -160,9 +160,17 @@ cudaError_t mcq_launch_copy(const double *src, double *dst, size_t n, cudaStream
 cudaError_t mcq_launch_commit_cons(const McqStatic &st, const double *ec_t, const double *ac_t, double *ec,
                                    double *ac, int start, int end, cudaStream_t stream);
 cudaError_t mcq_launch_commit_params(const McqStatic &st, McqModel m, McqOverride ov, cudaStream_t stream);
-cudaError_t mcq_launch_sum(const double *v, int n, double *out, cudaStream_t stream);
+// host-mapped (pinned) result slot: the reduction kernel writes the total, then the evaluation number
+struct McqHostSlot {
+  double value;
+  unsigned long long seq;
+  int err;
+};
+// hs: device view of the slot (nullptr = none), seq: the number to publish
+cudaError_t mcq_launch_sum(const double *v, int n, double *out, McqHostSlot *hs, unsigned long long seq,
+                           cudaStream_t stream);
 // `box` points at a host copy of the PeerBox struct of mcq_kernels.cu (16 value + 16 seq pointers, nranks, rank)
 cudaError_t mcq_launch_sum_exchange(const double *v, int n, double *out, const void *box, unsigned long long step,
-                                    int *err, cudaStream_t stream);
+                                    int *err, McqHostSlot *hs, unsigned long long seq, cudaStream_t stream);
 
 #endif

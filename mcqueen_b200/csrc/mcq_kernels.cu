@@ -1228,7 +1228,17 @@ cudaError_t mcq_launch_commit_params(const McqStatic &st, McqModel m, McqOverrid
 // K6b: total over queries.  One block; thread t adds elements t, t+1024, ... in ascending order,
 // then a fixed tree - the result does not depend on scheduling.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_sum(const double *__restrict__ v, int n, double *__restrict__ out) {
+// the total also goes straight to a host-mapped slot, followed by the evaluation number: the host spins on
+// the number instead of paying for a copy and a stream synchronisation
+__device__ __forceinline__ void publish_to_host(McqHostSlot *hs, double total, unsigned long long seq) {
+  if (hs == nullptr) return;
+  *reinterpret_cast<volatile double *>(&hs->value) = total;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long *>(&hs->seq) = seq;
+}
+
+__global__ void __launch_bounds__(1024) k_sum(const double *__restrict__ v, int n, double *__restrict__ out,
+                                              McqHostSlot *hs, unsigned long long seq) {
   __shared__ double sh[1024];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += 1024) acc += v[i];
@@ -1238,7 +1248,10 @@ __global__ void __launch_bounds__(1024) k_sum(const double *__restrict__ v, int 
     if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = sh[0];
+  if (threadIdx.x == 0) {
+    *out = sh[0];
+    publish_to_host(hs, sh[0], seq);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1256,7 +1269,8 @@ struct PeerBox {
 };
 
 __global__ void __launch_bounds__(1024) k_sum_exchange(const double *__restrict__ v, int n, double *__restrict__ out,
-                                                       PeerBox box, unsigned long long step, int *__restrict__ err) {
+                                                       PeerBox box, unsigned long long step, int *__restrict__ err,
+                                                       McqHostSlot *hs, unsigned long long seq) {
   __shared__ double sh[1024];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += 1024) acc += v[i];
@@ -1288,19 +1302,30 @@ __global__ void __launch_bounds__(1024) k_sum_exchange(const double *__restrict_
     __threadfence_system();
     got = *mv;
   }
-  if (!__all_sync(0xffffffffu, ok)) { if (lane == 0) *err = 1; return; }
+  if (!__all_sync(0xffffffffu, ok)) {
+    if (lane == 0) {
+      *err = 1;
+      if (hs != nullptr) { *reinterpret_cast<volatile int *>(&hs->err) = 1; __threadfence_system(); }
+      publish_to_host(hs, 0.0, seq);
+    }
+    return;
+  }
   double total = 0.0;
   for (int r = 0; r < R; r++) total += __shfl_sync(0xffffffffu, got, r);   // rank order on every rank
-  if (lane == 0) *out = total;
+  if (lane == 0) {
+    *out = total;
+    publish_to_host(hs, total, seq);
+  }
 }
 
 cudaError_t mcq_launch_sum_exchange(const double *v, int n, double *out, const void *box, unsigned long long step,
-                                    int *err, cudaStream_t stream) {
-  k_sum_exchange<<<1, 1024, 0, stream>>>(v, n, out, *static_cast<const PeerBox *>(box), step, err);
+                                    int *err, McqHostSlot *hs, unsigned long long seq, cudaStream_t stream) {
+  k_sum_exchange<<<1, 1024, 0, stream>>>(v, n, out, *static_cast<const PeerBox *>(box), step, err, hs, seq);
   return cudaGetLastError();
 }
 
-cudaError_t mcq_launch_sum(const double *v, int n, double *out, cudaStream_t stream) {
-  k_sum<<<1, 1024, 0, stream>>>(v, n, out);
+cudaError_t mcq_launch_sum(const double *v, int n, double *out, McqHostSlot *hs, unsigned long long seq,
+                           cudaStream_t stream) {
+  k_sum<<<1, 1024, 0, stream>>>(v, n, out, hs, seq);
   return cudaGetLastError();
 }
