@@ -97,6 +97,7 @@ struct mcq_ctx {
   uint8_t *query_codon = nullptr, *hla = nullptr;
   int *aoff = nullptr, *toff = nullptr, *nsite = nullptr;
   int2 *desc = nullptr;
+  uint32_t *rowdesc = nullptr;
   // static (host mirrors)
   std::vector<int> aoff_h, toff_h;
   std::vector<uint8_t> ncodon_h, cons_in_list_h, cons_codon_h, slot_of_h;
@@ -170,7 +171,7 @@ static McqStatic make_static(const mcq_ctx *c) {
   st.Q = c->d.num_query; st.S = c->d.num_sites; st.L = c->d.closest_n; st.Ls = c->Ls; st.Lg = c->Lg;
   st.N = c->d.total_num_refs; st.H = c->d.num_hla_types;
   st.G = c->G; st.aoff = c->aoff; st.toff = c->toff; st.ncodon = c->ncodon; st.nsite = c->nsite;
-  st.cons_in_list = c->cons_in_list; st.desc = c->desc;
+  st.cons_in_list = c->cons_in_list; st.desc = c->desc; st.rowdesc = c->rowdesc;
   st.cons_codon = c->cons_codon; st.query_codon = c->query_codon; st.hla = c->hla;
   return st;
 }
@@ -271,7 +272,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->d.device);
   cudaStreamSynchronize(c->stream);
-  void *ptrs[] = {c->desc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
+  void *ptrs[] = {c->desc, c->rowdesc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
                   c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->sel, c->st_trip, c->st_trip_pad, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
@@ -410,6 +411,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     c->cons_codon_h = cons_codon_h; c->slot_of_h = slot_of;
     c->NA = aoff_h[S];
     c->TL = (size_t)toff_h[S];
+    REQUIRE(c->TL <= 0x1FFFFFFu, "emission table too large for the packed row descriptors (sum of 64*K_s must stay below 2^25)");
     ALLOC(c->aoff, (size_t)S + 1);
     ALLOC(c->toff, (size_t)S + 1);
     ALLOC(c->ncodon, (size_t)c->NA);
@@ -417,6 +419,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     ALLOC(c->cons_in_list, (size_t)S);
     ALLOC(c->cons_codon, (size_t)S);
     ALLOC(c->query_codon, (size_t)Q * S);
+    ALLOC(c->rowdesc, (size_t)Q * S);
     ALLOC(c->hla, (size_t)Q * H);
     ALLOC(c->G, (size_t)Q * S * c->Lg);
     ALLOC(c->st_trip, (size_t)N * S);
@@ -471,6 +474,8 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     CK(mcq_launch_gather(c->st_trip, c->st_trip_pad, c->st_closest, c->st_cons, c->st_slot_of, c->st_trip_tab, c->G, c->hla, Q, S, L,
                          c->Lg, N, H, c->d_err, c->stream));
   }
+  CK(mcq_launch_rowdesc(make_static(c), c->rowdesc, c->stream));
+  c->launches++;
   CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   REQUIRE(*c->h_err == 0, "closest_refs entry out of range");

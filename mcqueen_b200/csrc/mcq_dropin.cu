@@ -39,6 +39,7 @@ struct Scratch {
   int8_t *trip = nullptr, *trip_pad = nullptr, *cons = nullptr;
   int *closest = nullptr, *aoff = nullptr, *Fn = nullptr, *Tn = nullptr, *d_err = nullptr;
   int2 *desc = nullptr;
+  uint32_t *rowdesc = nullptr;
   uint8_t *slot_of = nullptr, *trip_tab = nullptr, *G = nullptr;
   double *E = nullptr, *R = nullptr, *F = nullptr, *T = nullptr;
   // host staging
@@ -47,10 +48,10 @@ struct Scratch {
   std::vector<int> h_n;
 
   void release() {
-    void *p[] = {trip, trip_pad, cons, closest, aoff, desc, Fn, Tn, slot_of, trip_tab, G, E, R, F, T};
+    void *p[] = {trip, trip_pad, cons, closest, aoff, desc, rowdesc, Fn, Tn, slot_of, trip_tab, G, E, R, F, T};
     for (void *x : p)
       if (x) cudaFree(x);
-    trip = trip_pad = cons = nullptr; closest = aoff = Fn = Tn = nullptr; desc = nullptr; slot_of = trip_tab = G = nullptr;
+    trip = trip_pad = cons = nullptr; closest = aoff = Fn = Tn = nullptr; desc = nullptr; rowdesc = nullptr; slot_of = trip_tab = G = nullptr;
     E = R = F = T = nullptr;
   }
 
@@ -99,6 +100,10 @@ struct Scratch {
       for (int s = 0; s < S; s++) dh[s] = make_int2(64 * s, 64);
       DK(cudaMalloc((void **)&desc, (size_t)S * sizeof(int2)));
       DK(cudaMemcpy(desc, dh.data(), dh.size() * sizeof(int2), cudaMemcpyHostToDevice));
+      std::vector<uint32_t> rh(S);
+      for (int s = 0; s < S; s++) rh[s] = (64u << 25) | (uint32_t)(64 * s);
+      DK(cudaMalloc((void **)&rowdesc, (size_t)S * sizeof(uint32_t)));
+      DK(cudaMemcpy(rowdesc, rh.data(), rh.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     DK(cudaMemcpy(slot_of, so.data(), so.size(), cudaMemcpyHostToDevice));
     DK(cudaMemcpy(closest, cl.data(), cl.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -109,7 +114,7 @@ struct Scratch {
   McqStatic statics(int N) const {
     McqStatic st{};
     st.Q = 1; st.S = S; st.L = L; st.Ls = Ls; st.Lg = Lg; st.N = N; st.H = 1;
-    st.G = G; st.aoff = aoff; st.toff = aoff; st.desc = desc;   // one row of 64 entries per site
+    st.G = G; st.aoff = aoff; st.toff = aoff; st.desc = desc; st.rowdesc = rowdesc;   // one row of 64 entries per site
     st.query_codon = nullptr;                   // -> always row 0 of the site's block
     return st;
   }

@@ -45,7 +45,9 @@ struct McqStatic {           // device-resident static tables
   const uint8_t *G;          // [Q][S][Lg], states permuted lane-major (see k_gather)
   const int *aoff;           // [S+1] first non-consensus slot of site s in ATAB / ncodon; K_s = aoff[s+1]-aoff[s]
   const int *toff;           // [S+1] offset of site s's block of rows in TAB
-  const int2 *desc;          // [S] {toff[s], K_s}: what a warp needs to stage site s, in one load
+  const int2 *desc;          // [S] {toff[s], K_s}
+  const uint32_t *rowdesc;   // [Q][S] K_s << 25 | offset of row (s, to(q,s)) in TAB: what a warp needs to stage
+                             // the emission row of a site, in one word (built by mcq_launch_rowdesc)
   const uint8_t *ncodon;     // [aoff[S]] codon of each non-consensus slot
   const int *nsite;          // [aoff[S]] site of each non-consensus slot
   const uint8_t *cons_codon; // [S]
@@ -140,6 +142,8 @@ cudaError_t mcq_launch_gather(const int8_t *ref_triplets, int8_t *trip_pad /*[N]
                               uint8_t *G, uint8_t *hla_chars /*[Q][H] '0'/'1' -> 0/1 in place, or null*/, int Q, int S,
                               int L, int Lg, int N, int H, int *err /*device flag: 2 = closest out of range*/,
                               cudaStream_t stream);
+// rowdesc[q][s] from desc and query_codon (st.rowdesc itself is not read)
+cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, cudaStream_t stream);
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_dot(const DotArgs &a, cudaStream_t stream);

@@ -401,72 +401,32 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef MCQ_WPB
 #define MCQ_WPB 1                // warps (= queries) per block: small blocks balance best over the SMs
 #endif
-#define MCQ_ES 66                // doubles per staged emission row: slots 0..64 and a constant 0 at MCQ_NOSLOT
+#define MCQ_ES 67                // doubles per staged row: emission slots 0..64, a constant 0 at MCQ_NOSLOT, R[s]
+#define MCQ_RSLOT 66             // where the site's recombination probability travels
 
-// per-site lookahead state of a warp: everything stage_site needs for the NEXT site it will stage is
-// fetched one iteration early, so that no load sits between the wait and the cp.async issue
-struct SiteAhead {
-  int to;     // the query's codon at the site (row of the emission table)
-  int toff;   // start of the site's block in the table
-  int kr;     // entries per row
-};
-__device__ __forceinline__ SiteAhead look_ahead(const McqStatic &st, const uint8_t *__restrict__ qc, int t, bool valid) {
-  SiteAhead a;
-  a.to = 0; a.toff = 0; a.kr = 0;
-  if (valid) {
-    if (qc) a.to = qc[t];
-    const int2 d = st.desc[t];     // {offset of the site's block in the table, entries per row}
-    a.toff = d.x;
-    a.kr = d.y;
+// What a warp needs to stage the emission row of (query, site) is one word of the static table rowdesc:
+// bits 0..24 the offset of row (s, to(q,s)) in TAB, bits 25..31 the entries per row K_s (0 = nothing to
+// stage, also used for sites outside the range).  The words are fetched MCQ_RING sites ahead of their use.
+#define MCQ_RD_SHIFT 25
+#define MCQ_RD_MASK 0x1FFFFFFu
+
+__global__ void __launch_bounds__(256) k_rowdesc(const McqStatic st, uint32_t *__restrict__ out) {
+  const size_t n = (size_t)st.Q * st.S;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % (size_t)st.S);
+    const int2 d = st.desc[s];     // {offset of the site's block in the table, entries per row}
+    const unsigned to = st.query_codon ? st.query_codon[i] : 0u;
+    out[i] = ((unsigned)d.y << MCQ_RD_SHIFT) | ((unsigned)d.x + to * (unsigned)d.y);
   }
-  return a;
 }
 
-// Stage the rows of site t into ring slot t % MCQ_RING: one commit group per call, empty when the
-// site lies outside the range.
-template <int NJ>
-__device__ __forceinline__ void stage_site(uint8_t *gring, double *ering, int t, bool valid, const SiteAhead &sa,
-                                           int q, const McqStatic &st, const McqEmis &em,
-                                           const uint8_t *__restrict__ Gq, int lane) {
-  if (valid) {
-    const int slot = t % MCQ_RING;
-    const uint8_t *src = Gq + (size_t)t * (64 * NJ);
-    uint8_t *dst = gring + slot * (64 * NJ);
-#pragma unroll
-    for (int i = 0; i < (NJ + 7) / 8; i++) {
-      const int o = (lane + 32 * i) * 16;
-      if (o < 64 * NJ) cp_async16(dst + o, src + o);
-    }
-    const int kr = sa.kr;             // at most 64 entries: two predicated copies, no loop
-    const double *row = em.tab + (size_t)sa.toff + (size_t)sa.to * kr;
-    double *ed = ering + slot * MCQ_ES;
-    if (lane < kr) cp_async8(ed + 1 + lane, row + lane);
-    if (lane + 32 < kr) cp_async8(ed + 33 + lane, row + 32 + lane);
-    if (lane == 0 && em.ec != nullptr) cp_async8(ed, em.ec + (size_t)q * st.S + t);
-  }
-  cp_async_commit();
+cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, cudaStream_t stream) {
+  const size_t n = (size_t)st.Q * st.S;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_rowdesc<<<blocks, 256, 0, stream>>>(st, out);
+  return cudaGetLastError();
 }
-
-// the 2*NJ slot bytes a lane owns at one site: one vector load from the staged (permuted) G row
-template <int NJ>
-struct LaneSlots {
-  unsigned w[(2 * NJ + 3) / 4];
-  __device__ __forceinline__ void load(const uint8_t *gs, int lane) {
-    const uint8_t *p = gs + lane * (2 * NJ);
-    if constexpr (NJ == 1) w[0] = *reinterpret_cast<const uint16_t *>(p);
-    else if constexpr (NJ == 2) w[0] = *reinterpret_cast<const uint32_t *>(p);
-    else if constexpr (NJ == 4) { const uint2 v = *reinterpret_cast<const uint2 *>(p); w[0] = v.x; w[1] = v.y; }
-    else {
-#pragma unroll
-      for (int i = 0; i < NJ / 8; i++) {
-        const uint4 v = reinterpret_cast<const uint4 *>(p)[i];
-        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-      }
-    }
-  }
-  __device__ __forceinline__ unsigned first(int j) const { return (w[j >> 1] >> ((j & 1) * 16)) & 0xFFu; }
-  __device__ __forceinline__ unsigned second(int j) const { return (w[j >> 1] >> ((j & 1) * 16 + 8)) & 0xFFu; }
-};
 
 // ------------------------------------------------------------------------------------------
 // K4: forward recursion.  One warp per query; lane l holds states 64j+2l, 64j+2l+1 (j < NJ) of
@@ -503,22 +463,25 @@ __device__ __forceinline__ void cp_async8_if(unsigned sa, const void *gmem, bool
 }
 
 // Stage the rows of one site into ring slot KS (a constant): one commit group per call, empty when the
-// site lies outside the range (then sa.kr == 0 as well).  g_sh / e_sh: shared-window addresses of the
-// rings, already offset by this lane's 16 / 8 bytes; gsrc = the site's G row, tabl = the emission table,
-// both offset by this lane's share; ecp = the query's consensus-row value of the site (lane 0 copies it).
+// site lies outside the range (its descriptor word is then 0 as well).  g_sh / e_sh: shared-window addresses
+// of the rings, already offset by this lane's 16 / 8 bytes; gsrc = the site's G row, tabl = the emission
+// table, both offset by this lane's share; ecp = the query's consensus-row value of the site (lane 0 copies
+// it), Rp = the site's recombination probability (lane 1).
 template <int NJ, int KS>
-__device__ __forceinline__ void stage_k(unsigned g_sh, unsigned e_sh, bool valid, const SiteAhead &sa,
+__device__ __forceinline__ void stage_k(unsigned g_sh, unsigned e_sh, bool valid, unsigned rd,
                                         const double *__restrict__ tabl, const double *__restrict__ ecp, bool has_ec,
-                                        const uint8_t *__restrict__ gsrc, int lane) {
+                                        const double *__restrict__ Rp, const uint8_t *__restrict__ gsrc, int lane) {
 #pragma unroll
   for (int i = 0; i < (NJ + 7) / 8; i++)
     cp_async16_if(g_sh + KS * (64 * NJ) + 512 * i, gsrc + 512 * i, valid && (lane + 32 * i) * 16 < 64 * NJ);
-  const int kr = sa.kr;             // at most 64 entries: two predicated copies, no loop
-  const double *row = tabl + (sa.toff + sa.to * kr);
+  const int kr = (int)(rd >> MCQ_RD_SHIFT);   // at most 64 entries: two predicated copies, no loop
+  const double *row = tabl + (rd & MCQ_RD_MASK);
   const unsigned ed = e_sh + (KS * MCQ_ES + 1) * 8;
   cp_async8_if(ed, row, lane < kr);
   cp_async8_if(ed + 256, row + 32, lane + 32 < kr);
-  cp_async8_if(ed - 8, ecp, valid && has_ec && lane == 0);
+  // lane 0: the consensus-row value into slot 0; lane 1: R[s] into MCQ_RSLOT
+  const bool l0 = lane == 0;
+  cp_async8_if(l0 ? ed - 8 : ed + (MCQ_RSLOT - 2) * 8, l0 ? ecp : Rp, valid && (l0 ? has_ec : lane == 1));
   cp_async_commit();
 }
 
@@ -548,64 +511,45 @@ __device__ __forceinline__ void load_slots(const uint8_t *gl, unsigned (&w)[(2 *
 template <int NJ>
 struct FwdWarp {              // what one warp carries from site to site
   double p0[NJ], p1[NJ];      // the running column
-  double tot, Rnext;
+  double tot;
   int cnt, t;                 // rescale counter; next site to stage
-  SiteAhead ahead;            // look-ahead of site t
+  unsigned rd[MCQ_RING];      // descriptor words of sites t .. t+3 (entry = ring slot of the site)
+  unsigned sel[MCQ_RING];     // column selectors of sites s .. s+3 (entry = ring slot of the site)
   // running pointers (advanced once per site, no per-site index arithmetic)
   const uint8_t *gsrc;        // G row of site t (this lane's 16 bytes)
-  const uint8_t *qcp;         // the query's codon at site t + 1
-  const int2 *descp;          // descriptor of site t + 1
-  const double *Rp;           // R of the site after the one being computed
+  const uint32_t *rdp;        // descriptor word of site t + MCQ_RING
+  const double *Rp;           // R of site t
   double *Fs;                 // column of the site being computed in buffer 0 (this lane's states)
   int *Fnp;                   // its rescale counter (output array)
-  const uint8_t *selp;        // column selector of the site after the next one
-  unsigned selnext;           // column selector of the next site
+  const uint8_t *selp;        // column selector of site s + MCQ_RING
 };
-
-// the look-ahead of the site after w.t, through the running pointers
-template <int NJ>
-__device__ __forceinline__ SiteAhead next_ahead(FwdWarp<NJ> &w, bool has_qc, bool valid) {
-  SiteAhead a;
-  a.to = 0; a.toff = 0; a.kr = 0;
-  if (valid) {
-    if (has_qc) a.to = *w.qcp;
-    const int2 d = *w.descp;
-    a.toff = d.x; a.kr = d.y;
-  }
-  w.qcp++; w.descp++;
-  return a;
-}
 
 // one site of the recursion, its rows in ring slot K
 template <int NJ, bool FULL, bool PRE, bool STORE, int K>
 __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s, const uint8_t *gl, const double *ering,
-                                         unsigned g_sh, unsigned e_sh, bool has_qc, const double *tabl,
+                                         unsigned g_sh, unsigned e_sh, const double *tabl,
                                          const double *tabl_pre, const double *ecq, const double *ecq_pre,
                                          int lane, const bool (&inrow)[NJ], double invN, ptrdiff_t delta,
                                          bool has_sel, int *Fnc) {
   cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed (this lane's copies)
   __syncwarp();                  // ... and every other lane's; the slot of site s-1 is free again
   {
+    constexpr int KT = (K + MCQ_PF) & 3;       // ring slot of site t = s + MCQ_PF
     const int t = w.t;
-    const SiteAhead cur = w.ahead;
-    w.ahead = next_ahead(w, has_qc, t + 1 <= a.end);
+    const unsigned cur = w.rd[KT];
+    w.rd[KT] = (t + MCQ_RING <= a.end) ? *w.rdp : 0u;   // consumed four sites from now
+    w.rdp++;
     const bool pre = PRE && t < a.start;
     const double *eq = pre ? ecq_pre : ecq;
-    stage_k<NJ, (K + MCQ_PF) & 3>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.gsrc, lane);
+    stage_k<NJ, KT>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.Rp, w.gsrc, lane);
     w.gsrc += 64 * NJ;
+    w.Rp++;
     w.t = t + 1;
   }
   unsigned g[(2 * NJ + 3) / 4];
   load_slots<NJ, K>(gl, g);
   const double *es = ering + K * MCQ_ES;
-  const double Rs = w.Rnext;
-  {
-    double rn = 0.0;
-    if (s + 1 <= a.end) rn = *w.Rp;
-    if (s + 1 == a.r_site) rn = a.r_value;
-    w.Rnext = rn;
-    w.Rp++;
-  }
+  const double Rs = (s == a.r_site) ? a.r_value : es[MCQ_RSLOT];
   // forward_backward.c:138 divides by N and :141-142 adds then multiplies; here the reciprocal and
   // a fused multiply-add keep the per-site dependency chain short (each one rounding away from
   // the reference's sequence, far inside the tolerance - the order of the sum differs anyway)
@@ -630,9 +574,9 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
     // the column goes into the buffer that holds the current one (a catch-up site, an in-place refill)
     // or into the other one (a proposal): the same offset, `delta` doubles away
     const bool pre = PRE && s < a.start;
-    const unsigned cur1 = w.selnext;
+    const unsigned cur1 = w.sel[K];
     if (has_sel) {
-      if (s + 1 <= a.end) w.selnext = *w.selp;
+      if (s + MCQ_RING <= a.end) w.sel[K] = *w.selp;   // consumed four sites from now
       w.selp++;
     }
     const bool into1 = (cur1 != 0) != (!a.in_place && !pre);
@@ -663,8 +607,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   const int S = a.st.S, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
   const uint8_t *__restrict__ Gl = a.st.G + (size_t)q * S * (64 * NJ) + lane * 16;
-  const bool has_qc = a.st.query_codon != nullptr;
-  const uint8_t *__restrict__ qc = has_qc ? a.st.query_codon + (size_t)q * S : nullptr;
+  const uint32_t *__restrict__ rdq = a.st.rowdesc + (size_t)q * S;
   const double *ecq = a.em.ec ? a.em.ec + (size_t)q * S : nullptr;
   const double *ecq_pre = (PRE && a.em_pre.ec) ? a.em_pre.ec + (size_t)q * S : nullptr;
   const double *tabl = a.em.tab + lane, *tabl_pre = PRE ? a.em_pre.tab + lane : nullptr;
@@ -701,28 +644,31 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   {
     const bool pre = PRE && 0 < a.start;
     const double *eq = pre ? ecq_pre : ecq;
-    stage_k<NJ, 3>(g_sh, e_sh, s0 == 0, look_ahead(a.st, qc, 0, s0 == 0), pre ? tabl_pre : tabl, eq, eq != nullptr, Gl, lane);
+    stage_k<NJ, 3>(g_sh, e_sh, s0 == 0, s0 == 0 ? rdq[0] : 0u, pre ? tabl_pre : tabl, eq, eq != nullptr, a.R, Gl, lane);
   }
 #define MCQ_FWD_PROLOGUE(K)                                                                                  \
   {                                                                                                          \
     const int tt = sA + K;                                                                                   \
     const bool pre = PRE && tt < a.start;                                                                    \
     const double *eq = pre ? ecq_pre : ecq;                                                                  \
-    stage_k<NJ, K>(g_sh, e_sh, tt <= a.end, look_ahead(a.st, qc, tt, tt <= a.end), pre ? tabl_pre : tabl,    \
-                   eq + tt, eq != nullptr, Gl + (size_t)tt * (64 * NJ), lane);                               \
+    stage_k<NJ, K>(g_sh, e_sh, tt <= a.end, tt <= a.end ? rdq[tt] : 0u, pre ? tabl_pre : tabl, eq + tt,      \
+                   eq != nullptr, a.R + tt, Gl + (size_t)tt * (64 * NJ), lane);                              \
   }
   MCQ_FWD_PROLOGUE(0) MCQ_FWD_PROLOGUE(1) MCQ_FWD_PROLOGUE(2)
 #undef MCQ_FWD_PROLOGUE
   w.t = sA + MCQ_PF;
-  w.ahead = look_ahead(a.st, qc, w.t, w.t <= a.end);
+#pragma unroll
+  for (int k = 0; k < MCQ_RING; k++) {
+    const int tt = w.t + k;                      // ring slot (tt - sA) & 3 = (k + 3) & 3
+    w.rd[(k + MCQ_PF) & 3] = (tt <= a.end) ? rdq[tt] : 0u;
+    w.sel[k] = (has_sel && sA + k <= a.end) ? selq[sA + k] : 0u;
+  }
   w.gsrc = Gl + (size_t)w.t * (64 * NJ);
-  w.qcp = qc + w.t + 1;
-  w.descp = a.st.desc + w.t + 1;
-  w.Rp = a.R + sA + 1;
+  w.rdp = rdq + w.t + MCQ_RING;
+  w.Rp = a.R + w.t;
   w.Fs = X0 + (size_t)sA * Ls;
   w.Fnp = STORE ? Fno + sA : nullptr;
-  w.selnext = (has_sel && sA <= a.end) ? selq[sA] : 0u;
-  w.selp = selq + sA + 1;
+  w.selp = selq + sA + MCQ_RING;
   const double invN = 1.0 / (double)a.st.N;
 
   if (s0 == 0) {
@@ -765,9 +711,8 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
     w.tot = warp_sum(loc);
   }
 
-  w.Rnext = (sA <= a.end) ? ((sA == a.r_site) ? a.r_value : a.R[sA]) : 0.0;
-#define MCQ_FWD_SITE(K, SITE)                                                                                     \
-  fwd_site<NJ, FULL, PRE, STORE, K>(a, w, SITE, gl, ering, g_sh, e_sh, has_qc, tabl, tabl_pre, ecq, ecq_pre, lane, \
+#define MCQ_FWD_SITE(K, SITE)                                                                             \
+  fwd_site<NJ, FULL, PRE, STORE, K>(a, w, SITE, gl, ering, g_sh, e_sh, tabl, tabl_pre, ecq, ecq_pre, lane, \
                                     inrow, invN, delta, has_sel, Fnc)
   for (int s = sA; s <= a.end; s += 4) {
     MCQ_FWD_SITE(0, s);
@@ -851,56 +796,45 @@ struct BwdWarp {
   double b0[NJ], b1[NJ], e0[NJ], e1[NJ];
   double sx, Rnext;
   int cnt, t;
-  SiteAhead ahead;
+  unsigned rd[MCQ_RING];      // descriptor words of sites t .. t-3 (entry = ring slot of the site)
   const uint8_t *gsrc;        // G row of site t (this lane's 16 bytes)
-  const uint8_t *qcp;         // the query's codon at site t - 1
-  const int2 *descp;          // descriptor of site t - 1
+  const uint32_t *rdp;        // descriptor word of site t - MCQ_RING
   const double *ecp;          // consensus-row value of site t (unused when the rows carry none)
-  const double *Rp;           // R[s] of the site being computed (= R[(s-1)+1], read for the next one)
+  const double *Rp;           // R of site t
   double *Bs;                 // output column of the site being computed
   int *Bnp;
 };
 
-template <int NJ>
-__device__ __forceinline__ SiteAhead prev_ahead(BwdWarp<NJ> &w, bool has_qc, bool valid) {
-  SiteAhead a;
-  a.to = 0; a.toff = 0; a.kr = 0;
-  if (valid) {
-    if (has_qc) a.to = *w.qcp;
-    const int2 d = *w.descp;
-    a.toff = d.x; a.kr = d.y;
-  }
-  w.qcp--; w.descp--;
-  return a;
-}
-
+// stage site w.t into ring slot (K + MCQ_PF) & 3 and fetch the descriptor word needed four sites on
 template <int NJ, int K>
-__device__ __forceinline__ void bwd_stage(const BwdArgs &a, BwdWarp<NJ> &w, unsigned g_sh, unsigned e_sh, bool has_qc,
+__device__ __forceinline__ void bwd_stage(const BwdArgs &a, BwdWarp<NJ> &w, unsigned g_sh, unsigned e_sh,
                                           const double *tabl, int bottom, int lane) {
+  constexpr int KT = (K + MCQ_PF) & 3;
   const int t = w.t;
-  const SiteAhead cur = w.ahead;
-  w.ahead = prev_ahead(w, has_qc, t - 1 >= bottom);
-  stage_k<NJ, (K + MCQ_PF) & 3>(g_sh, e_sh, t >= bottom, cur, tabl, w.ecp, a.em.ec != nullptr, w.gsrc, lane);
+  const unsigned cur = w.rd[KT];
+  w.rd[KT] = (t - MCQ_RING >= bottom) ? *w.rdp : 0u;
+  w.rdp--;
+  stage_k<NJ, KT>(g_sh, e_sh, t >= bottom, cur, tabl, w.ecp, a.em.ec != nullptr, w.Rp, w.gsrc, lane);
   w.gsrc -= 64 * NJ;
   w.ecp--;
+  w.Rp--;
   w.t = t - 1;
 }
 
 // one site of the recursion: computes column s from column s+1; the rows of site s are in ring slot K
 template <int NJ, bool FULL, int K>
 __device__ __forceinline__ void bwd_site(const BwdArgs &a, BwdWarp<NJ> &w, const uint8_t *gl, const double *ering,
-                                         unsigned g_sh, unsigned e_sh, bool has_qc, const double *tabl, int bottom,
+                                         unsigned g_sh, unsigned e_sh, const double *tabl, int bottom,
                                          int lane, const bool (&inrow)[NJ], const double (&m0)[NJ],
                                          const double (&m1)[NJ], double invN) {
   cp_async_wait<MCQ_PF - 1>();   // rows of site s
   __syncwarp();
-  bwd_stage<NJ, K>(a, w, g_sh, e_sh, has_qc, tabl, bottom, lane);
+  bwd_stage<NJ, K>(a, w, g_sh, e_sh, tabl, bottom, lane);
   unsigned g[(2 * NJ + 3) / 4];
   load_slots<NJ, K>(gl, g);
   const double *es = ering + K * MCQ_ES;
   const double Rn = w.Rnext;
-  w.Rnext = *w.Rp;                              // R[(s-1)+1] for the next site
-  w.Rp--;
+  w.Rnext = es[MCQ_RSLOT];                      // R[(s-1)+1] for the next site
   const double jump = w.sx * (Rn * invN);       // forward_backward.c:219 (reciprocal: see k_forward)
   const double stay = 1 - Rn;
   double locv = 0.0, locy = 0.0, locv2 = 0.0, locy2 = 0.0;
@@ -947,8 +881,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   const int S = a.st.S, L = a.st.L, Ls = a.st.Ls;
   const size_t qoff = (size_t)q * S * Ls;
   const uint8_t *__restrict__ Gl = a.st.G + (size_t)q * S * (64 * NJ) + lane * 16;
-  const bool has_qc = a.st.query_codon != nullptr;
-  const uint8_t *__restrict__ qc = has_qc ? a.st.query_codon + (size_t)q * S : nullptr;
+  const uint32_t *__restrict__ rdq = a.st.rowdesc + (size_t)q * S;
   const double *ecq = a.em.ec ? a.em.ec + (size_t)q * S : nullptr;
   const double *tabl = a.em.tab + lane;
   double *__restrict__ Bq = a.B + qoff + 2 * lane;
@@ -1008,18 +941,21 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
 #define MCQ_BWD_PROLOGUE(K)                                                                                  \
   {                                                                                                          \
     const int tt = tA - K;                                                                                   \
-    stage_k<NJ, K>(g_sh, e_sh, tt >= bottom, look_ahead(a.st, qc, tt, tt >= bottom), tabl, ecq + tt,        \
-                   ecq != nullptr, Gl + (ptrdiff_t)tt * (64 * NJ), lane);                                    \
+    stage_k<NJ, K>(g_sh, e_sh, tt >= bottom, tt >= bottom ? rdq[tt] : 0u, tabl, ecq + tt, ecq != nullptr,    \
+                   a.R + tt, Gl + (ptrdiff_t)tt * (64 * NJ), lane);                                          \
   }
   MCQ_BWD_PROLOGUE(0) MCQ_BWD_PROLOGUE(1) MCQ_BWD_PROLOGUE(2)
 #undef MCQ_BWD_PROLOGUE
   w.t = tA - MCQ_PF;
-  w.ahead = look_ahead(a.st, qc, w.t, w.t >= bottom);
+#pragma unroll
+  for (int k = 0; k < MCQ_RING; k++) {
+    const int tt = w.t - k;                      // ring slot (tA - tt) & 3 = (k + 3) & 3
+    w.rd[(k + MCQ_PF) & 3] = (tt >= bottom) ? rdq[tt] : 0u;
+  }
   w.gsrc = Gl + (ptrdiff_t)w.t * (64 * NJ);
-  w.qcp = qc + (w.t - 1);
-  w.descp = a.st.desc + (w.t - 1);
+  w.rdp = rdq + (w.t - MCQ_RING);
   w.ecp = ecq + w.t;
-  w.Rp = a.R + s;
+  w.Rp = a.R + w.t;
   w.Bs = Bq + (size_t)s * Ls;
   w.Bnp = Bnq + s;
   const double invN = 1.0 / (double)a.st.N;
@@ -1028,7 +964,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   {
     cp_async_wait<MCQ_PF - 1>();
     __syncwarp();
-    bwd_stage<NJ, 0>(a, w, g_sh, e_sh, has_qc, tabl, bottom, lane);
+    bwd_stage<NJ, 0>(a, w, g_sh, e_sh, tabl, bottom, lane);
     unsigned g[(2 * NJ + 3) / 4];
     load_slots<NJ, 0>(gl, g);
     const double *es = ering;
@@ -1039,11 +975,11 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
       loc += w.b0[j] * w.e0[j]; loc += w.b1[j] * w.e1[j];
     }
     w.sx = warp_sum(loc);
+    w.Rnext = es[MCQ_RSLOT];                    // R[s+1]
   }
 
-  w.Rnext = a.R[s + 1];
 #define MCQ_BWD_SITE(K) \
-  bwd_site<NJ, FULL, K>(a, w, gl, ering, g_sh, e_sh, has_qc, tabl, bottom, lane, inrow, m0, m1, invN)
+  bwd_site<NJ, FULL, K>(a, w, gl, ering, g_sh, e_sh, tabl, bottom, lane, inrow, m0, m1, invN)
   for (; s >= bottom; s -= 4) {
     MCQ_BWD_SITE(1);
     if (s - 1 < bottom) break;
