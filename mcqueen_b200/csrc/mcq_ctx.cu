@@ -82,6 +82,8 @@ static const int kNcclSum = 0;     // ncclSum
 // ------------------------------------------------------------------------------------------
 // the context
 // ------------------------------------------------------------------------------------------
+static const int kUploadChunks = 8;   // query chunks of mcq_ctx_upload_static (transfer under gather)
+
 struct mcq_ctx {
   mcq_dims d;
   int Ls = 0, Lg = 0, NA = 0;          // NA = number of non-consensus slots (sum_s K_s)
@@ -89,6 +91,7 @@ struct mcq_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;            // the backward refill of an accept runs beside the forward refill
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_chunk[1 + kUploadChunks] = {nullptr};   // upload_static: panel landed, chunk k landed
   size_t bytes = 0;
   bool have_static = false, have_params = false, have_state = false;
 
@@ -246,6 +249,7 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (cudaEvent_t &e : c->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
   CK(cudaEventCreate(&c->evt0));
@@ -292,6 +296,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   cudaEventDestroy(c->evt1);
   for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
   cudaStreamSynchronize(c->stream2);
+  for (cudaEvent_t e : c->ev_chunk) if (e) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_fork);
   cudaEventDestroy(c->ev_join);
   cudaStreamDestroy(c->stream2);
@@ -459,23 +464,40 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
                 cons_codon_h == c->cons_codon_h,
             "re-upload changes the per-site codon lists: create a new context");
   }
-  // the large inputs go first (DMA from the caller's buffers); the '0'/'1' characters of hla_types are
-  // turned into 0/1 and closest_refs is range-checked on the device
-  CK(cudaMemcpyAsync(c->st_trip, ref_triplets, (size_t)N * S, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->st_closest, closest_refs, (size_t)Q * L * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->st_cons, cons_query_nucls, (size_t)Q * 3 * S, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->query_codon, query_codons, (size_t)Q * S, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->hla, hla_types, (size_t)Q * H, cudaMemcpyHostToDevice, c->stream));
+  // The inputs are DMA'd from the caller's buffers on the copy stream, the panel first, then the per-query
+  // arrays in chunks of queries; each chunk is gathered on the main stream as soon as it has landed, so the
+  // gather of chunk k runs under the transfer of chunk k+1.  The '0'/'1' characters of hla_types are turned
+  // into 0/1 and closest_refs is range-checked on the device.
+  CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
   CK(cudaMemcpyAsync(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+  CK(cudaEventRecord(c->ev_fork, c->stream));                 // the copy stream starts behind earlier work
+  CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  CK(cudaMemcpyAsync(c->st_trip, ref_triplets, (size_t)N * S, cudaMemcpyHostToDevice, c->stream2));
+  CK(cudaEventRecord(c->ev_chunk[0], c->stream2));
+  CK(cudaStreamWaitEvent(c->stream, c->ev_chunk[0], 0));
   {
     KScope ks(c, MCQ_K_GATHER);
-    CK(mcq_launch_gather(c->st_trip, c->st_trip_pad, c->st_closest, c->st_cons, c->st_slot_of, c->st_trip_tab, c->G, c->hla, Q, S, L,
-                         c->Lg, N, H, c->d_err, c->stream));
+    CK(mcq_launch_gather_prepare(c->st_trip, c->st_trip_pad, c->st_slot_of, c->st_trip_tab, S, N, c->stream));
   }
-  CK(mcq_launch_rowdesc(make_static(c), c->rowdesc, c->stream));
-  c->launches++;
+  const int nchunk = Q < 4 * kUploadChunks ? 1 : kUploadChunks;
+  const McqStatic st_all = make_static(c);
+  for (int k = 0; k < nchunk; k++) {
+    const size_t q0 = (size_t)Q * k / nchunk, q1 = (size_t)Q * (k + 1) / nchunk, nq = q1 - q0;
+    CK(cudaMemcpyAsync(c->st_closest + q0 * L, closest_refs + q0 * L, nq * L * sizeof(int), cudaMemcpyHostToDevice, c->stream2));
+    CK(cudaMemcpyAsync(c->st_cons + q0 * 3 * S, cons_query_nucls + q0 * 3 * S, nq * 3 * S, cudaMemcpyHostToDevice, c->stream2));
+    CK(cudaMemcpyAsync(c->query_codon + q0 * S, query_codons + q0 * S, nq * S, cudaMemcpyHostToDevice, c->stream2));
+    CK(cudaMemcpyAsync(c->hla + q0 * H, hla_types + q0 * H, nq * H, cudaMemcpyHostToDevice, c->stream2));
+    CK(cudaEventRecord(c->ev_chunk[1 + k], c->stream2));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_chunk[1 + k], 0));
+    {
+      KScope ks(c, MCQ_K_GATHER);
+      CK(mcq_launch_gather(c->st_trip_pad, c->st_closest + q0 * L, c->st_cons + q0 * 3 * S, c->st_slot_of, c->st_trip_tab,
+                           c->G + q0 * S * c->Lg, c->hla + q0 * H, (int)nq, S, L, c->Lg, N, H, c->d_err, c->stream));
+    }
+    CK(mcq_launch_rowdesc(st_all, c->rowdesc, (int)q0, (int)nq, c->stream));
+    c->launches++;
+  }
   CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   REQUIRE(*c->h_err == 0, "closest_refs entry out of range");

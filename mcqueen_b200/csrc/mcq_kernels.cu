@@ -192,27 +192,33 @@ __global__ void __launch_bounds__(256) k_hla_bits(uint8_t *hla, size_t n) {
   if (i < n) hla[i] = (hla[i] == '1');
 }
 
-cudaError_t mcq_launch_gather(const int8_t *ref_triplets, int8_t *trip_pad, const int *closest, const int8_t *cons_nucls,
-                              const uint8_t *slot_of, uint8_t *trip_tab, uint8_t *G, uint8_t *hla_chars, int Q, int S,
-                              int L, int Lg, int N, int H, int *err, cudaStream_t stream) {
+// query-independent part: the per-site triplet -> slot table and the re-pitched reference rows
+cudaError_t mcq_launch_gather_prepare(const int8_t *ref_triplets, int8_t *trip_pad, const uint8_t *slot_of,
+                                      uint8_t *trip_tab, int S, int N, cudaStream_t stream) {
+  const int sblocks = (S + 31) / 32, Sp = sblocks * 32;
+  k_trip_table<<<sblocks * 32, 128, 0, stream>>>(slot_of, trip_tab, S);
+  const size_t words = (size_t)N * (Sp / 4);
+  unsigned blocks = (unsigned)((words + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_pad_rows<<<blocks, 256, 0, stream>>>(ref_triplets, reinterpret_cast<uint32_t *>(trip_pad), N, S, Sp);
+  return cudaGetLastError();
+}
+
+// G rows (and the 0/1 HLA flags) of Q queries; the pointers address the first of them
+cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int *closest, const int8_t *cons_nucls,
+                              const uint8_t *slot_of, const uint8_t *trip_tab, uint8_t *G, uint8_t *hla_chars, int Q,
+                              int S, int L, int Lg, int N, int H, int *err, cudaStream_t stream) {
   const int sblocks = (S + 31) / 32, Sp = sblocks * 32;
   if (hla_chars != nullptr) {
     const size_t n = (size_t)Q * H;
     k_hla_bits<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(hla_chars, n);
-  }
-  k_trip_table<<<sblocks * 32, 128, 0, stream>>>(slot_of, trip_tab, S);
-  {
-    const size_t words = (size_t)N * (Sp / 4);
-    unsigned blocks = (unsigned)((words + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k_pad_rows<<<blocks, 256, 0, stream>>>(ref_triplets, reinterpret_cast<uint32_t *>(trip_pad), N, S, Sp);
   }
   const int threads = Lg / 4 < 32 ? 32 : Lg / 4;
   for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
     int nq = Q - q0 < 65535 ? Q - q0 : 65535;
     dim3 grid(sblocks, nq);
     k_gather<<<grid, threads, 0, stream>>>(trip_pad, Sp, closest + (size_t)q0 * L, cons_nucls + (size_t)q0 * 3 * S,
-                                              slot_of, trip_tab, G + (size_t)q0 * S * Lg, S, L, Lg, N, err);
+                                           slot_of, trip_tab, G + (size_t)q0 * S * Lg, S, L, Lg, N, err);
   }
   return cudaGetLastError();
 }
@@ -410,9 +416,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #define MCQ_RD_SHIFT 25
 #define MCQ_RD_MASK 0x1FFFFFFu
 
-__global__ void __launch_bounds__(256) k_rowdesc(const McqStatic st, uint32_t *__restrict__ out) {
-  const size_t n = (size_t)st.Q * st.S;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) k_rowdesc(const McqStatic st, uint32_t *__restrict__ out, int q0, int nq) {
+  const size_t i0 = (size_t)q0 * st.S, n = i0 + (size_t)nq * st.S;
+  for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int s = (int)(i % (size_t)st.S);
     const int2 d = st.desc[s];     // {offset of the site's block in the table, entries per row}
     const unsigned to = st.query_codon ? st.query_codon[i] : 0u;
@@ -420,11 +426,11 @@ __global__ void __launch_bounds__(256) k_rowdesc(const McqStatic st, uint32_t *_
   }
 }
 
-cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, cudaStream_t stream) {
-  const size_t n = (size_t)st.Q * st.S;
+cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, int q0, int nq, cudaStream_t stream) {
+  const size_t n = (size_t)nq * st.S;
   unsigned blocks = (unsigned)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_rowdesc<<<blocks, 256, 0, stream>>>(st, out);
+  k_rowdesc<<<blocks, 256, 0, stream>>>(st, out, q0, nq);
   return cudaGetLastError();
 }
 
