@@ -124,8 +124,10 @@ struct mcq_ctx {
   bool has_pending = false;
   int opt_sparse_esc = 0;
   int opt_lazy = 1;          // MCQ_OPT_LAZY_REFILL
-  // host-side bounds on the per-query validity marks: every fv[q] >= fv_lo, every bv[q] <= bv_hi
-  int fv_lo = -1, bv_hi = 1 << 30;
+  // host mirror of the per-query validity marks fv / bv (every update is issued from the host, so the
+  // mirror is exact) and of the 0/1 carrier table: a catch-up is launched only when one is really owed
+  std::vector<int> fv_h, bv_h;
+  std::vector<uint8_t> hla_h;
 
   int timing = 0;            // 0 off, 1 per API call, 2 per kernel launch as well
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
@@ -498,6 +500,15 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     CK(mcq_launch_rowdesc(st_all, c->rowdesc, (int)q0, (int)nq, c->stream));
     c->launches++;
   }
+  c->hla_h.resize((size_t)Q * H);
+  for (size_t i = 0; i < c->hla_h.size(); i++) c->hla_h[i] = hla_types[i] == '1';
+  // new data: nothing of F or B is valid until the next mcq_ctx_init_state
+  c->fv_h.assign(Q, -1);
+  c->bv_h.assign(Q, S);
+  CK(mcq_launch_set_valid(c->fv, c->bv, Q, H, -1, S, nullptr, 0, c->stream));
+  c->launches++;
+  c->have_state = false;
+  c->has_pending = false;
   CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   REQUIRE(*c->h_err == 0, "closest_refs entry out of range");
@@ -687,25 +698,38 @@ static int reduce_llk(mcq_ctx *c, const double *per_query, double *out) {
     CK(cudaSetDevice((c)->d.device));                                              \
   } while (0)
 
-// validity marks of F and B (lazy refills): on the device per query, on the host as bounds
+// the queries an operation touches: all of them, or the carriers of one HLA type
+template <typename Fn>
+static void for_active(mcq_ctx *c, bool sparse, int hla, Fn fn) {
+  const int Q = c->d.num_query, H = c->d.num_hla_types;
+  if (!sparse) { for (int q = 0; q < Q; q++) fn(q); return; }
+  const uint8_t *col = c->hla_h.data() + hla;
+  for (int q = 0; q < Q; q++) if (col[(size_t)q * H]) fn(q);
+}
+
+// validity marks of F and B (lazy refills): on the device per query, mirrored on the host
 static int set_marks(mcq_ctx *c, int f, int b, bool sparse, int hla) {
   CK(mcq_launch_set_valid(c->fv, c->bv, c->d.num_query, c->d.num_hla_types, f, b, sparse ? c->hla : nullptr, hla, c->stream));
   c->launches++;
-  if (f >= -1) c->fv_lo = sparse ? (c->fv_lo < f ? c->fv_lo : f) : f;
-  if (b >= 0) c->bv_hi = sparse ? (c->bv_hi > b ? c->bv_hi : b) : b;
+  for_active(c, sparse, hla, [&](int q) {
+    if (f >= -1) c->fv_h[q] = f;
+    if (b >= 0) c->bv_h[q] = b;
+  });
   return 0;
 }
 
 // Complete F (to the last site) and B (down to site 0) for every query whose refill is still owed.
 static int flush_lazy(mcq_ctx *c) {
   const int S = c->d.num_sites;
-  if (c->fv_lo < S - 1) {
+  bool owe_f = false, owe_b = false;
+  for_active(c, false, 0, [&](int q) { owe_f |= c->fv_h[q] < S - 1; owe_b |= c->bv_h[q] > 0; });
+  if (owe_f) {
     if (run_forward(c, c->tab, c->ec, S, S - 1, FWD_IN_PLACE, 0, nullptr, -1, 0.0, false, 0, true)) return 1;
-    c->fv_lo = S - 1;
+    for (int &v : c->fv_h) v = S - 1;
   }
-  if (c->bv_hi > 0) {
+  if (owe_b) {
     if (run_backward(c, S - 1, false, 0, nullptr, true, 0)) return 1;
-    c->bv_hi = 0;
+    for (int &v : c->bv_h) v = 0;
   }
   return 0;
 }
@@ -791,14 +815,18 @@ extern "C" int mcq_ctx_init_state(mcq_ctx *c, double *llk) {
 // kernel itself, B by a backward launch beside it on the second stream, joined by k_dot.
 static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const McqOverride &ov, int r_site,
                       double r_value, bool sparse) {
-  const bool need_f = c->opt_lazy && c->fv_lo < ov.start - 1;
-  const bool need_b = c->opt_lazy && c->bv_hi > ov.end;
-  if (!need_b) {
-    if (run_forward(c, tab, ec, ov.start, ov.end, FWD_PROPOSAL, 1, c->llk_prop, r_site, r_value, sparse, ov.hla,
-                    need_f)) return 1;
-    if (need_f && !sparse) c->fv_lo = ov.start - 1;
-    return 0;
-  }
+  bool need_f = false, need_b = false;
+  if (c->opt_lazy)
+    for_active(c, sparse, ov.hla, [&](int q) { need_f |= c->fv_h[q] < ov.start - 1; need_b |= c->bv_h[q] > ov.end; });
+  // what the launches below leave behind: F current up to start-1, B current down to end, where they were not
+  if (need_f || need_b)
+    for_active(c, sparse, ov.hla, [&](int q) {
+      if (c->fv_h[q] < ov.start - 1) c->fv_h[q] = ov.start - 1;
+      if (c->bv_h[q] > ov.end) c->bv_h[q] = ov.end;
+    });
+  if (!need_b)
+    return run_forward(c, tab, ec, ov.start, ov.end, FWD_PROPOSAL, 1, c->llk_prop, r_site, r_value, sparse, ov.hla,
+                       need_f);
   const bool dual = c->timing < 2;
   if (dual) {
     CK(cudaEventRecord(c->ev_fork, c->stream));
@@ -818,10 +846,6 @@ static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const Mcq
   {
     KScope ks(c, MCQ_K_SUM);
     CK(mcq_launch_dot(d, c->stream));
-  }
-  if (!sparse) {          // every query is now valid this far; a sparse evaluation leaves the bounds alone
-    if (need_f) c->fv_lo = ov.start - 1;
-    c->bv_hi = ov.end;
   }
   return 0;
 }
