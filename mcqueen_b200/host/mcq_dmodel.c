@@ -441,8 +441,10 @@ static int env_int(const char *name, int dflt)
  * mailboxes (default) or the 128-byte NCCL id (--nccl). */
 static void blob_path(char *path, size_t n, const char *tag, int r)
 {
-  snprintf(path, n, "/tmp/mcq_%s_%s_%s_%d", tag, getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0",
-           getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : "run", r);
+  /* the launcher's pid is common to the ranks of one launch and differs between launches, so files a
+   * crashed earlier run left behind are never picked up */
+  snprintf(path, n, "/tmp/mcq_%s_%s_%s_%ld_%d", tag, getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0",
+           getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : "run", (long)getppid(), r);
 }
 
 static void blob_put(const char *tag, int r, const unsigned char *data, size_t len)
@@ -655,6 +657,12 @@ int main(int argc, char **argv)
   if(!c.sample_prior) {
     CHECK(mcq_ctx_init_state(c.ctx, &c.llk));
     printf("Total log-likelihood using initialise F: %f.\n", c.llk);
+    if(world > 1) {
+      /* the first exchange has completed on every rank, so every rank has read every hand-over file */
+      char mine[PATH_MAX];
+      blob_path(mine, sizeof(mine), opt_nccl ? "nccl" : "peer", opt_nccl ? 0 : rank);
+      if(!opt_nccl || rank == 0) unlink(mine);
+    }
   }
   if(resume_path != NULL) printf("Likelihood from loaded .json file: %f.\n", resume_llk);
 
