@@ -204,7 +204,9 @@ size_t mcq_ctx_device_bytes(const mcq_ctx *ctx);
  * issued by the previous API call on this context. */
 int mcq_ctx_last_timing(const mcq_ctx *ctx, float *ms, int *launches);
 /* When enabled every API call brackets its kernels with CUDA events (costs a sync).
- * on == 2 additionally brackets every kernel launch, accumulated per kernel class. */
+ * on == 2 additionally brackets every kernel launch, accumulated per kernel class.
+ * on == 3 brackets only the forward-kernel launches and adds no host wait to the calls: the pairs
+ * are read out by the next mcq_ctx_kernel_time (what bench.py uses inside its timed region). */
 int mcq_ctx_enable_timing(mcq_ctx *ctx, int on);
 enum { MCQ_K_GATHER = 0, MCQ_K_EMISSION = 1, MCQ_K_FORWARD = 2, MCQ_K_BACKWARD = 3, MCQ_K_COMMIT = 4,
        MCQ_K_SUM = 5, MCQ_K_CLASSES = 6 };

@@ -129,7 +129,9 @@ struct mcq_ctx {
   std::vector<int> fv_h, bv_h;
   std::vector<uint8_t> hla_h;
 
-  int timing = 0;            // 0 off, 1 per API call, 2 per kernel launch as well
+  int timing = 0;            // 0 off, 1 per API call, 2 per kernel launch as well, 3 forward launches only (read later)
+  std::vector<cudaEvent_t> fev;      // level 3: pairs bracketing forward launches, resolved by mcq_ctx_kernel_time
+  size_t fev_used = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   float last_ms = 0.f;
   int last_launches = 0, launches = 0;
@@ -186,11 +188,11 @@ struct CallScope {   // brackets one API call for mcq_ctx_last_timing
   explicit CallScope(mcq_ctx *ctx) : c(ctx) {
     c->launches = 0;
     c->kev_class.clear();
-    if (c->timing) cudaEventRecord(c->ev0, c->stream);
+    if (c->timing == 1 || c->timing == 2) cudaEventRecord(c->ev0, c->stream);
   }
   ~CallScope() {
     c->last_launches = c->launches;
-    if (c->timing) {
+    if (c->timing == 1 || c->timing == 2) {
       cudaEventRecord(c->ev1, c->stream);
       cudaEventSynchronize(c->ev1);
       cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
@@ -203,13 +205,25 @@ struct CallScope {   // brackets one API call for mcq_ctx_last_timing
   }
 };
 
-struct KScope {      // brackets one kernel launch (timing level 2) and counts it
+struct KScope {      // brackets one kernel launch (timing level 2; level 3: forward launches only) and counts it
   mcq_ctx *c;
   int idx = -1;
+  cudaEvent_t late = nullptr;
   KScope(mcq_ctx *ctx, int kclass) : c(ctx) {
     c->launches++;
     c->k_n[kclass]++;
-    if (c->timing >= 2) {
+    if (c->timing == 3 && kclass == MCQ_K_FORWARD) {
+      // no host wait in the call: the pair is read out when the caller asks for the class total
+      while (c->fev.size() < c->fev_used + 2) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->fev.push_back(e);
+      }
+      cudaEventRecord(c->fev[c->fev_used], c->stream);
+      late = c->fev[c->fev_used + 1];
+      c->fev_used += 2;
+    }
+    if (c->timing == 2) {
       idx = (int)c->kev_class.size();
       while (c->kev.size() < (size_t)2 * (idx + 1)) {
         cudaEvent_t e;
@@ -222,6 +236,7 @@ struct KScope {      // brackets one kernel launch (timing level 2) and counts i
   }
   ~KScope() {
     if (idx >= 0) cudaEventRecord(c->kev[2 * idx + 1], c->stream);
+    if (late) cudaEventRecord(late, c->stream);
   }
 };
 
@@ -297,6 +312,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   cudaEventDestroy(c->evt0);
   cudaEventDestroy(c->evt1);
   for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->fev) cudaEventDestroy(e);
   cudaStreamSynchronize(c->stream2);
   for (cudaEvent_t e : c->ev_chunk) if (e) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_fork);
@@ -316,6 +332,16 @@ extern "C" int mcq_ctx_enable_timing(mcq_ctx *c, int on) {
 extern "C" int mcq_ctx_kernel_time(mcq_ctx *c, int kclass, float *ms_total, int *launches, int reset) {
   REQUIRE(c, "null context");
   REQUIRE(kclass >= 0 && kclass < MCQ_K_CLASSES, "kernel class");
+  if (c->fev_used) {           // level 3: the deferred forward pairs
+    CK(cudaSetDevice(c->d.device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < c->fev_used; i += 2) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, c->fev[i], c->fev[i + 1]));
+      c->k_ms[MCQ_K_FORWARD] += ms;
+    }
+    c->fev_used = 0;
+  }
   if (ms_total) *ms_total = c->k_ms[kclass];
   if (launches) *launches = c->k_n[kclass];
   if (reset)
@@ -600,12 +626,15 @@ enum FwdMode {
 };
 
 static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int start, int end, FwdMode mode, int llk_mode,
-                       double *llk_out, int r_site, double r_value, bool sparse, int hla, bool lazy = false) {
+                       double *llk_out, int r_site, double r_value, bool sparse, int hla, bool lazy = false,
+                       bool mark_end = false) {
   FwdArgs a;
   a.st = make_static(c);
   a.em.tab = tab; a.em.ec = ec; a.R = c->m.R; a.r_site = r_site; a.r_value = r_value;
   a.em_pre.tab = c->tab; a.em_pre.ec = c->ec;
   a.fv = lazy ? c->fv : nullptr;   // catch up F before `start` where it is stale
+  a.mark_fv = mark_end ? c->fv : nullptr;
+  if (mark_end) for (int &v : c->fv_h) v = end;      // (never combined with `sparse`)
   a.Fin = c->F; a.Fn_in = c->Fn; a.Fout = c->T; a.sel = c->sel;
   a.Fn_out = (mode == FWD_PROPOSAL) ? c->Tn : c->Fn;
   a.in_place = mode == FWD_IN_PLACE; a.no_store = mode == FWD_NO_STORE;
@@ -739,7 +768,7 @@ extern "C" int mcq_ctx_flush(mcq_ctx *c) {
   REQUIRE(c->have_state, "mcq_ctx_init_state has not been called");
   CallScope scope(c);
   if (flush_lazy(c)) return 1;
-  if (!c->timing) CK(cudaStreamSynchronize(c->stream));
+  if (c->timing == 0 || c->timing == 3) CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -750,7 +779,7 @@ extern "C" int mcq_ctx_emission(mcq_ctx *c, int start, int end, int which_hla, i
   CallScope scope(c);
   McqOverride none{}; none.kind = -1;
   if (run_emission(c, start, end, which_hla, mode, none, cur_set(c), cur_set(c))) return 1;
-  if (!c->timing) CK(cudaStreamSynchronize(c->stream));
+  if (c->timing == 0 || c->timing == 3) CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -760,8 +789,7 @@ extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
   const int S = c->d.num_sites;
   McqOverride none{}; none.kind = -1;
   if (with_emission && run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
-  if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_IN_PLACE, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
-  if (set_marks(c, S - 1, -1, false, 0)) return 1;
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_IN_PLACE, 2, c->llk_cur, -1, 0.0, false, 0, false, true)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->has_pending = false;
   return 0;
@@ -787,7 +815,7 @@ extern "C" int mcq_ctx_backward_fill(mcq_ctx *c) {
   CallScope scope(c);
   if (run_backward(c, c->d.num_sites - 1, false, 0)) return 1;
   if (set_marks(c, -2, 0, false, 0)) return 1;
-  if (!c->timing) CK(cudaStreamSynchronize(c->stream));
+  if (c->timing == 0 || c->timing == 3) CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -827,7 +855,7 @@ static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const Mcq
   if (!need_b)
     return run_forward(c, tab, ec, ov.start, ov.end, FWD_PROPOSAL, 1, c->llk_prop, r_site, r_value, sparse, ov.hla,
                        need_f);
-  const bool dual = c->timing < 2;
+  const bool dual = c->timing != 2;
   if (dual) {
     CK(cudaEventRecord(c->ev_fork, c->stream));
     CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
@@ -953,7 +981,7 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
       if (set_marks(c, ov.end, ov.end, sparse, ov.hla)) return 1;
     } else {
       // F after the range and B from the range down to 0 do not depend on each other: two streams
-      const bool dual = c->timing < 2 && ov.end + 1 < S;
+      const bool dual = c->timing != 2 && ov.end + 1 < S;
       if (dual) {
         CK(cudaEventRecord(c->ev_fork, c->stream));
         CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));

@@ -79,6 +79,7 @@ struct FwdArgs {
   McqEmis em;                // emission rows read for sites start..end
   McqEmis em_pre;            // current emission rows, for the catch-up sites before `start`
   int *fv;                   // [Q] last valid column of Fin per query; nullptr = column start-1 is valid
+  int *mark_fv;              // [Q] or nullptr: receives `end` for every query the launch ran (a full sweep)
   const double *R;
   int r_site; double r_value;     // R override at one site (-1 = none)
   // Two column buffers: Fin = buffer 0, Fout = buffer 1.  sel[q][s] (0/1, or nullptr = always 0) names the

@@ -732,6 +732,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
 #undef MCQ_FWD_SITE
   cp_async_wait<0>();
   if (caught_up && lane == 0) a.fv[q] = a.start - 1;
+  if (a.mark_fv != nullptr && lane == 0) a.mark_fv[q] = a.end;
 
   // K6 epilogue: the per-query log-likelihood at the last column of the range
   if (a.llk_mode != 0) {
