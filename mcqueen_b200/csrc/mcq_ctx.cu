@@ -94,6 +94,7 @@ struct mcq_ctx {
   cudaEvent_t ev_chunk[1 + kUploadChunks] = {nullptr};   // upload_static: panel landed, chunk k landed
   size_t bytes = 0;
   bool have_static = false, have_params = false, have_state = false;
+  bool have_fwd = false;     // a full forward sweep has run since the last upload: with a backward fill it makes a state
 
   // static (device)
   uint8_t *G = nullptr, *ncodon = nullptr, *cons_in_list = nullptr, *cons_codon = nullptr;
@@ -534,12 +535,14 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   CK(mcq_launch_set_valid(c->fv, c->bv, Q, H, -1, S, nullptr, 0, c->stream));
   c->launches++;
   c->have_state = false;
+  c->have_fwd = false;
   c->has_pending = false;
   CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   REQUIRE(*c->h_err == 0, "closest_refs entry out of range");
   c->have_static = true;
   c->have_state = false;
+  c->have_fwd = false;
   c->has_pending = false;
   return 0;
 }
@@ -607,6 +610,11 @@ static int run_emission(mcq_ctx *c, int start, int end, int which_hla, int mode,
   a.a0 = c->aoff_h[start]; a.a1 = c->aoff_h[end + 1];
   a.tab_src = src.tab; a.atab_src = src.atab; a.ec_src = src.ec; a.ac_src = src.ac;
   a.tab_dst = dst.tab; a.atab_dst = dst.atab; a.ec_dst = dst.ec; a.ac_dst = dst.ac;
+  if (mode == 2) {
+    KScope ks(c, MCQ_K_EMISSION);
+    CK(mcq_launch_emission_both(a, c->stream));
+    return 0;
+  }
   if (mode != 0) {
     KScope ks(c, MCQ_K_EMISSION);
     CK(mcq_launch_emission_table(a, c->stream));
@@ -792,6 +800,7 @@ extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
   if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_IN_PLACE, 2, c->llk_cur, -1, 0.0, false, 0, false, true)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->has_pending = false;
+  c->have_fwd = true;
   return 0;
 }
 
@@ -815,6 +824,7 @@ extern "C" int mcq_ctx_backward_fill(mcq_ctx *c) {
   CallScope scope(c);
   if (run_backward(c, c->d.num_sites - 1, false, 0)) return 1;
   if (set_marks(c, -2, 0, false, 0)) return 1;
+  if (c->have_fwd) c->have_state = true;      // mcq_ctx_full_llk + mcq_ctx_backward_fill = mcq_ctx_init_state
   if (c->timing == 0 || c->timing == 3) CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

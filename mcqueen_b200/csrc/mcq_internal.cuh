@@ -158,6 +158,7 @@ cudaError_t mcq_launch_set_valid(int *fv, int *bv, int Q, int H, int f, int b, c
 // create_codon_to_codon_HLA
 cudaError_t mcq_launch_emission_table(const EmisArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_emission_cons(const EmisArgs &a, cudaStream_t stream);
+cudaError_t mcq_launch_emission_both(const EmisArgs &a, cudaStream_t stream);   // the two above in one launch
 cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots,
                                   const double *tab, const double *atab, const double *ec, const double *ac,
                                   double *tab_o, double *atab_o, double *ec_o, double *ac_o, cudaStream_t stream);

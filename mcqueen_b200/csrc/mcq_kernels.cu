@@ -252,8 +252,7 @@ __device__ __forceinline__ double eff_rate_out(const McqModel &m, const McqOverr
 // non-consensus codons.  Nothing in it depends on the query except its codon `to`, so it is
 // evaluated once per (slot, to): one thread each, 64 x (non-consensus slots of the range).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_emission_table(const EmisArgs a) {
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void emission_table_entry(const EmisArgs &a, unsigned idx) {
   if (idx >= (unsigned)(a.a1 - a.a0) * 64u) return;
   const int j = a.a0 + (int)(idx >> 6), to = (int)(idx & 63);
   const int s = a.st.nsite[j], c1 = a.st.ncodon[j];
@@ -279,6 +278,10 @@ __global__ void __launch_bounds__(256) k_emission_table(const EmisArgs a) {
   if (to == 0) a.atab_dst[j] = A;
 }
 
+__global__ void __launch_bounds__(256) k_emission_table(const EmisArgs a) {
+  emission_table_entry(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 cudaError_t mcq_launch_emission_table(const EmisArgs &a, cudaStream_t stream) {
   const unsigned n = (unsigned)(a.a1 - a.a0) * 64u;
   if (n == 0) return cudaSuccess;
@@ -289,9 +292,8 @@ cudaError_t mcq_launch_emission_table(const EmisArgs &a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 // K3c: the escape part (mcmc_moves.c:125-167): the consensus row, one thread per (query, site).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_emission_cons(const EmisArgs a) {
+__device__ __forceinline__ void emission_cons_entry(const EmisArgs &a, unsigned idx) {
   const unsigned W = (unsigned)(a.end - a.start + 1);
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (unsigned)a.st.Q * W) return;
   const int q = (int)(idx / W), s = a.start + (int)(idx % W);
   const int S = a.st.S, H = a.st.H;
@@ -325,6 +327,24 @@ __global__ void __launch_bounds__(256) k_emission_cons(const EmisArgs a) {
   if (to == cons) v = (1 - A) * (1 - back) + back;
   a.ec_dst[o] = v;
   a.ac_dst[o] = A;
+}
+
+__global__ void __launch_bounds__(256) k_emission_cons(const EmisArgs a) {
+  emission_cons_entry(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// both parts in one launch (DO_HLA_BOTH): the first nb_table blocks take the shared rows, the rest the
+// per-query consensus values
+__global__ void __launch_bounds__(256) k_emission_both(const EmisArgs a, unsigned nb_table) {
+  if (blockIdx.x < nb_table) emission_table_entry(a, blockIdx.x * blockDim.x + threadIdx.x);
+  else emission_cons_entry(a, (blockIdx.x - nb_table) * blockDim.x + threadIdx.x);
+}
+
+cudaError_t mcq_launch_emission_both(const EmisArgs &a, cudaStream_t stream) {
+  const unsigned n1 = (unsigned)(a.a1 - a.a0) * 64u, n2 = (unsigned)a.st.Q * (unsigned)(a.end - a.start + 1);
+  const unsigned nb1 = (n1 + 255) / 256, nb2 = (n2 + 255) / 256;
+  k_emission_both<<<nb1 + nb2, 256, 0, stream>>>(a, nb1);
+  return cudaGetLastError();
 }
 
 cudaError_t mcq_launch_emission_cons(const EmisArgs &a, cudaStream_t stream) {

@@ -301,6 +301,35 @@ def test_contract_tolerance_on_c2_slice(api):
     ctx.close()
 
 
+def test_reupload_invalidates_the_state(api):
+    """New static data makes F and B meaningless: proposals are refused until a state exists again
+    (mcq_ctx_init_state, or mcq_ctx_full_llk + mcq_ctx_backward_fill), and that state matches the oracle."""
+    import copy
+    p = make_problem("toy")
+    p2 = copy.copy(p)             # the same panel, the queries in reverse order
+    for name in ("closest_refs", "cons_query_nucls", "query_codons", "hla"):
+        setattr(p2, name, np.ascontiguousarray(getattr(p, name)[::-1]))
+    cpu2 = CpuState(checker(), p2)
+    ctx = api.Context.from_problem(p)
+    ctx.init_state()
+    ctx.propose(REC, 5, value0=0.02); ctx.accept()
+    ctx.upload_static(p2.ref_triplets, p2.closest_refs, p2.cons_query_nucls, p2.query_codons, p2.hla,
+                      p2.consensus_codons, p2.n_site_codons, p2.site_codons)
+    ctx.set_params(mu=p2.mu, kappa=p2.kappa, phi=p2.phi, prior=p2.prior, R=p2.R, omega=p2.omega,
+                   rate_out=p2.rate_out_of_codons(), esc=p2.esc, rev=p2.rev[0])
+    with pytest.raises(api._lib.McqError, match="init_state"):
+        ctx.propose(REC, 5, value0=0.02)
+    llk = ctx.full_llk(True)
+    assert abs(llk - cpu2.llk) <= RTOL_LLK * abs(cpu2.llk)
+    ctx.backward_fill()
+    mv = dict(kind=REV, start=10, end=30, value0=1.3)
+    want, got = cpu2.propose(**mv), ctx.propose(**mv)
+    assert abs(got - want) <= RTOL_LLK * abs(want)
+    cpu2.accept(); ctx.accept()
+    assert_state_matches(ctx, cpu2, [0, p.Q - 1])
+    ctx.close()
+
+
 def test_errors_are_loud(api):
     with pytest.raises(api._lib.McqError):
         api.Context(10, 2000, 100, 5, 1)          # closest_n > 1024
