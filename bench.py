@@ -375,8 +375,11 @@ def main():
     for a in host_arrays:
         api.host_register(a)
     rate_out = p.rate_out_of_codons()
-    h2d = sum(a.nbytes for a in host_arrays) + p.consensus_codons.nbytes + p.n_site_codons.nbytes + \
-        p.site_codons.nbytes + 8 * (64 + 2 * S + 64 * S + H * S + S)
+    # per rank; with the peer exchange attached each rank DMAs 1/world of the reference panel and reads the
+    # rest from its peers over NVLink (MCQ_OPT_SHARED_PANEL)
+    panel_share = p.ref_triplets.nbytes // world if comm_kind == "peer" else p.ref_triplets.nbytes
+    h2d = panel_share + sum(a.nbytes for a in host_arrays[1:]) + p.consensus_codons.nbytes + \
+        p.n_site_codons.nbytes + p.site_codons.nbytes + 8 * (64 + 2 * S + 64 * S + H * S + S)
     d2h = 8 * p.Q + 8
 
     e2e_parts = np.zeros(4)
@@ -491,7 +494,8 @@ def main():
                     "breakdown_ms": dict(zip(["upload_static", "set_params", "full_llk", "read_back"],
                                              (e2e_parts / args.steps * 1e3).round(3).tolist()), gather_kernel=round(gather_ms, 3)),
                     "what": "mcq_ctx_upload_static + mcq_ctx_set_params + mcq_ctx_full_llk + per-query llk "
-                            "read-back, all inputs from pinned host buffers every step"},
+                            "read-back, all inputs from pinned host buffers every step (bytes per rank" +
+                            ("; the reference panel is DMA'd in 1/N slices and completed over NVLink)" if world > 1 and comm_kind == "peer" else ")")},
             "roofline": {"bound": "hbm", "kernel": "k_forward", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": bytes_per_cell, "launch_ms": fwd_ms_avg,

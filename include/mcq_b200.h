@@ -186,6 +186,11 @@ enum {
                               next evaluation that needs those columns, with the parameters then
                               current - the same values, computed when first read.  0: refill at
                               once, the reference's schedule. */
+  MCQ_OPT_SHARED_PANEL = 3 /* default 1, effective once mcq_ctx_attach_peers has run: in
+                              mcq_ctx_upload_static every rank DMAs 1/nranks of ref_triplets from the
+                              host and reads the rest from its peers over NVLink.  All ranks must then
+                              call mcq_ctx_upload_static together and with the same panel.  0: every
+                              rank uploads the whole panel itself. */
 };
 int mcq_ctx_set_option(mcq_ctx *ctx, int option, int value);
 
@@ -224,7 +229,8 @@ int mcq_host_unregister(void *ptr);
 
 /* ---- multi-GPU: queries are sharded over ranks, one scalar is exchanged ---------------- */
 /* (a) NVLink peer exchange (preferred on one NVSwitch box): each rank exports a 64-byte CUDA IPC
- * handle of its mailbox, the launcher gathers them, every rank attaches all of them; the shard totals
+ * handle of its mailbox (and of its copy of the reference panel, MCQ_OPT_SHARED_PANEL), the launcher
+ * gathers them, every rank attaches all of them; the shard totals
  * are then exchanged by peer stores inside the reduction kernel and added in rank order.
  * `handles` is [nranks][64], entry `rank` may be anything. At most 16 ranks. */
 int mcq_ctx_peer_handle(mcq_ctx *ctx, unsigned char handle[64]);

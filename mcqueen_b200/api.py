@@ -23,6 +23,7 @@ BUF_F, BUF_B, BUF_TMP_F = 0, 1, 2
 TAB_C2C, TAB_A, TAB_TMP_C2C, TAB_TMP_A = 0, 1, 2, 3
 OPT_SPARSE_ESC = 1
 OPT_LAZY_REFILL = 2
+OPT_SHARED_PANEL = 3
 K_GATHER, K_EMISSION, K_FORWARD, K_BACKWARD, K_COMMIT, K_SUM = range(6)
 
 

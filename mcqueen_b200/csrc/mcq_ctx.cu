@@ -152,9 +152,14 @@ struct mcq_ctx {
   struct {
     double *value[16];
     unsigned long long *seq[16];
+    unsigned long long *bar[16];
     int nranks, rank;
   } box{};
-  void *mailbox = nullptr;          // this rank's own mailbox allocation
+  void *mailbox = nullptr;          // this rank's own mailbox allocation (+ the shared panel behind it)
+  bool trip_in_mailbox = false;     // st_trip lives behind the mailbox: peers read their slices of the panel from it
+  const int8_t *peer_trip[16] = {nullptr};
+  unsigned long long bar_seq = 0;
+  int opt_shared_panel = 1;         // MCQ_OPT_SHARED_PANEL
   void *peer_map[16] = {nullptr};   // IPC mappings of the peers' mailboxes
   bool have_peers = false;
   unsigned long long step = 0;
@@ -299,7 +304,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
                   c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->sel, c->st_trip, c->st_trip_pad, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
   for (void *p : ptrs)
-    if (p) cudaFree(p);
+    if (p && !(p == (void *)c->st_trip && c->trip_in_mailbox)) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
   if (c->h_err) cudaFreeHost(c->h_err);
   if (c->h_slot) cudaFreeHost(c->h_slot);
@@ -388,6 +393,7 @@ extern "C" int mcq_ctx_last_timing(const mcq_ctx *c, float *ms, int *launches) {
 extern "C" int mcq_ctx_set_option(mcq_ctx *c, int option, int value) {
   REQUIRE(c, "null context");
   if (option == MCQ_OPT_SPARSE_ESC) { c->opt_sparse_esc = value; return 0; }
+  if (option == MCQ_OPT_SHARED_PANEL) { c->opt_shared_panel = value; return 0; }
   if (option == MCQ_OPT_LAZY_REFILL) {
     if (!value && c->have_state && mcq_ctx_flush(c)) return 1;   // leave lazy mode with F and B complete
     c->opt_lazy = value;
@@ -456,7 +462,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     ALLOC(c->rowdesc, (size_t)Q * S);
     ALLOC(c->hla, (size_t)Q * H);
     ALLOC(c->G, (size_t)Q * S * c->Lg);
-    ALLOC(c->st_trip, (size_t)N * S);
+    if (!c->st_trip) ALLOC(c->st_trip, (size_t)N * S);
     ALLOC(c->st_trip_pad, (size_t)N * ((S + 31) / 32 * 32));
     ALLOC(c->st_cons, (size_t)Q * 3 * S);
     ALLOC(c->st_closest, (size_t)Q * L);
@@ -502,7 +508,23 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventRecord(c->ev_fork, c->stream));                 // the copy stream starts behind earlier work
   CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-  CK(cudaMemcpyAsync(c->st_trip, ref_triplets, (size_t)N * S, cudaMemcpyHostToDevice, c->stream2));
+  const bool shared_panel = c->have_peers && c->trip_in_mailbox && c->opt_shared_panel && c->box.nranks > 1;
+  if (shared_panel) {
+    // every rank DMAs one slice of the panel rows from the host; the others arrive from the peers' copies
+    // over NVLink once all slices have landed (a barrier over the ranks: all of them are in this call)
+    const int R = c->box.nranks, me = c->box.rank;
+    const size_t r0 = (size_t)N * me / R, r1 = (size_t)N * (me + 1) / R;
+    CK(cudaMemcpyAsync(c->st_trip + r0 * S, ref_triplets + r0 * S, (r1 - r0) * S, cudaMemcpyHostToDevice, c->stream2));
+    CK(mcq_launch_peer_barrier(&c->box, ++c->bar_seq, c->d_err, c->stream2));
+    for (int k = 1; k < R; k++) {
+      const int p = (me + k) % R;            // staggered, so that no peer serves everybody at once
+      const size_t p0 = (size_t)N * p / R, p1 = (size_t)N * (p + 1) / R;
+      CK(cudaMemcpyAsync(c->st_trip + p0 * S, c->peer_trip[p] + p0 * S, (p1 - p0) * S, cudaMemcpyDeviceToDevice, c->stream2));
+    }
+    c->launches++;
+  } else {
+    CK(cudaMemcpyAsync(c->st_trip, ref_triplets, (size_t)N * S, cudaMemcpyHostToDevice, c->stream2));
+  }
   CK(cudaEventRecord(c->ev_chunk[0], c->stream2));
   CK(cudaStreamWaitEvent(c->stream, c->ev_chunk[0], 0));
   {
@@ -537,8 +559,16 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   c->have_state = false;
   c->have_fwd = false;
   c->has_pending = false;
+  if (shared_panel) {
+    // nobody may overwrite its slice (the next upload) before every peer has read it
+    CK(mcq_launch_peer_barrier(&c->box, ++c->bar_seq, c->d_err, c->stream2));
+    CK(cudaEventRecord(c->ev_join, c->stream2));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->launches++;
+  }
   CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
+  REQUIRE(*c->h_err != 3, "panel exchange timed out: a rank did not reach the same mcq_ctx_upload_static");
   REQUIRE(*c->h_err == 0, "closest_refs entry out of range");
   c->have_static = true;
   c->have_state = false;
@@ -1077,16 +1107,30 @@ extern "C" int mcq_ctx_get_query_llk(mcq_ctx *c, int proposed, double *out) {
 // multi-GPU
 // ------------------------------------------------------------------------------------------
 // ---- NVLink peer mailboxes ----------------------------------------------------------------
-// layout of one mailbox: double value[2][16]; unsigned long long seq[2][16]
-static const size_t kMailboxBytes = 2 * 16 * (sizeof(double) + sizeof(unsigned long long));
+// layout of the exported allocation: double value[2][16]; u64 seq[2][16]; u64 bar[16]; then, from
+// kPanelOffset, this rank's copy of the reference panel (st_trip): with it behind the same IPC handle the
+// ranks of a box DMA one slice of the panel each from the host and read the other slices from their peers
+// over NVLink (mcq_ctx_upload_static), instead of every rank pulling the whole panel over PCIe.
+static const size_t kMailboxBytes = 2 * 16 * (sizeof(double) + sizeof(unsigned long long)) + 16 * sizeof(unsigned long long);
+static const size_t kPanelOffset = 1024;
+static_assert(kMailboxBytes <= kPanelOffset, "mailbox header");
 
 extern "C" int mcq_ctx_peer_handle(mcq_ctx *c, unsigned char handle[64]) {
   REQUIRE(c && handle, "null argument");
   CK(cudaSetDevice(c->d.device));
   if (!c->mailbox) {
-    CK(cudaMalloc(&c->mailbox, kMailboxBytes));
-    CK(cudaMemset(c->mailbox, 0, kMailboxBytes));
+    const size_t panel = (size_t)c->d.total_num_refs * c->d.num_sites;
+    CK(cudaMalloc(&c->mailbox, kPanelOffset + panel));
+    c->bytes += kPanelOffset + panel;
+    CK(cudaMemset(c->mailbox, 0, kPanelOffset));
     CK(cudaDeviceSynchronize());
+    // the panel staging buffer moves behind the mailbox (it is refilled by every mcq_ctx_upload_static)
+    if (c->st_trip) {
+      CK(cudaFree(c->st_trip));
+      c->bytes -= panel;
+    }
+    c->st_trip = (int8_t *)c->mailbox + kPanelOffset;
+    c->trip_in_mailbox = true;
   }
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, c->mailbox));
@@ -1112,12 +1156,15 @@ extern "C" int mcq_ctx_attach_peers(mcq_ctx *c, int nranks, int rank, const unsi
     // every rank indexes a mailbox as [slot][R] with R = nranks
     c->box.value[r] = (double *)base;
     c->box.seq[r] = (unsigned long long *)(base + 2 * 16 * sizeof(double));
+    c->box.bar[r] = (unsigned long long *)(base + 2 * 16 * (sizeof(double) + sizeof(unsigned long long)));
+    c->peer_trip[r] = (const int8_t *)base + kPanelOffset;
   }
   c->box.nranks = nranks;
   c->box.rank = rank;
   c->nranks = nranks;
   c->have_peers = true;
   c->step = 0;
+  c->bar_seq = 0;
   return 0;
 }
 

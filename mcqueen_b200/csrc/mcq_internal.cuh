@@ -177,7 +177,9 @@ struct McqHostSlot {
 // hs: device view of the slot (nullptr = none), seq: the number to publish
 cudaError_t mcq_launch_sum(const double *v, int n, double *out, McqHostSlot *hs, unsigned long long seq,
                            cudaStream_t stream);
-// `box` points at a host copy of the PeerBox struct of mcq_kernels.cu (16 value + 16 seq pointers, nranks, rank)
+// barrier over the attached ranks (monotone `count`); err: device flag, 3 = a peer never arrived
+cudaError_t mcq_launch_peer_barrier(const void *box, unsigned long long count, int *err, cudaStream_t stream);
+// `box` points at a host copy of the PeerBox struct of mcq_kernels.cu (16 value + 16 seq + 16 bar pointers, nranks, rank)
 cudaError_t mcq_launch_sum_exchange(const double *v, int n, double *out, const void *box, unsigned long long step,
                                     int *err, McqHostSlot *hs, unsigned long long seq, cudaStream_t stream);
 

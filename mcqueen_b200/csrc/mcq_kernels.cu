@@ -1228,8 +1228,33 @@ __global__ void __launch_bounds__(1024) k_sum(const double *__restrict__ v, int 
 struct PeerBox {
   double *value[16];               // value[r] = peer r's mailbox values  [2][R]
   unsigned long long *seq[16];     // seq[r]   = peer r's mailbox flags   [2][R]
+  unsigned long long *bar[16];     // bar[r]   = peer r's barrier counters [R]
   int nranks, rank;
 };
+
+// Barrier over the ranks of one box through the mailboxes: lane r stores the (monotone) barrier number
+// into entry `me` of peer r's counters and waits until entry r of its own counters has reached it.
+// Everything earlier on the launching stream (copies included) is complete and visible before the store.
+__global__ void __launch_bounds__(32) k_peer_barrier(PeerBox box, unsigned long long count, int *__restrict__ err) {
+  const int R = box.nranks, me = box.rank, lane = threadIdx.x;
+  bool ok = true;
+  if (lane < R) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(box.bar[lane] + me) = count;
+    volatile unsigned long long *mine = box.bar[me] + lane;
+    const long long t0 = clock64();
+    while (*mine < count) {
+      if (clock64() - t0 > 20000000000LL) { ok = false; break; }   // ~10 s
+    }
+    __threadfence_system();
+  }
+  if (!__all_sync(0xffffffffu, ok) && lane == 0) *err = 3;
+}
+
+cudaError_t mcq_launch_peer_barrier(const void *box, unsigned long long count, int *err, cudaStream_t stream) {
+  k_peer_barrier<<<1, 32, 0, stream>>>(*static_cast<const PeerBox *>(box), count, err);
+  return cudaGetLastError();
+}
 
 __global__ void __launch_bounds__(1024) k_sum_exchange(const double *__restrict__ v, int n, double *__restrict__ out,
                                                        PeerBox box, unsigned long long step, int *__restrict__ err,

@@ -32,6 +32,11 @@ def _worker(rank, world, port, kind, out):
         ids = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.attach_comm(world, rank, ids[0])
+    # a second upload, now that the ranks know each other: with peers attached every rank DMAs one slice
+    # of the reference panel and reads the other slices from its peers (MCQ_OPT_SHARED_PANEL)
+    for _ in range(3):
+        ctx.upload_static(p.ref_triplets, p.closest_refs[q0:q1], p.cons_query_nucls[q0:q1], p.query_codons[q0:q1],
+                          p.hla[q0:q1], p.consensus_codons, p.n_site_codons, p.site_codons)
     vals = [ctx.init_state()]
     vals.append(ctx.propose(api.PROP_ESC, 10, 40, hla=1, value0=1.5, value1=0.8, split=25))
     ctx.accept()
