@@ -118,6 +118,8 @@ struct mcq_ctx {
   double *llk_cur = nullptr, *llk_prop = nullptr, *d_sum = nullptr;
   int *fv = nullptr, *bv = nullptr;   // per query: F valid up to fv, B valid from bv (lazy refills)
   double *h_sum = nullptr;   // pinned
+  double *pblock = nullptr, *h_pblock = nullptr;   // parameter block (device) and its pinned staging copy
+  size_t pblock_n = 0;
   McqHostSlot *h_slot = nullptr, *d_slot = nullptr;   // host-mapped result slot and its device view
   unsigned long long eval_seq = 0;
 
@@ -278,8 +280,13 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   CK(cudaEventCreate(&c->evt0));
   CK(cudaEventCreate(&c->evt1));
   const size_t S = dims->num_sites, Q = dims->num_query, H = dims->num_hla_types;
-  ALLOC(c->m.R, S); ALLOC(c->m.omega, S); ALLOC(c->m.rate_out, S * 64);
-  ALLOC(c->m.esc, H * S); ALLOC(c->m.rev, S); ALLOC(c->m.prior, 64);
+  // the parameter arrays are one block, mirrored by a pinned staging block: a full mcq_ctx_set_params is
+  // one DMA.  Order: prior[64] R[S] omega[S] rev[S] esc[H][S] rate_out[S][64]
+  c->pblock_n = 64 + 3 * S + H * S + 64 * S;
+  ALLOC(c->pblock, c->pblock_n);
+  CK(cudaMallocHost((void **)&c->h_pblock, c->pblock_n * sizeof(double)));
+  c->m.prior = c->pblock; c->m.R = c->m.prior + 64; c->m.omega = c->m.R + S; c->m.rev = c->m.omega + S;
+  c->m.esc = c->m.rev + S; c->m.rate_out = c->m.esc + H * S;
   ALLOC(c->llk_cur, Q); ALLOC(c->llk_prop, Q); ALLOC(c->d_sum, 1);
   ALLOC(c->fv, Q); ALLOC(c->bv, Q);
   CK(cudaMallocHost((void **)&c->h_sum, sizeof(double)));
@@ -300,12 +307,13 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   cudaSetDevice(c->d.device);
   cudaStreamSynchronize(c->stream);
   void *ptrs[] = {c->desc, c->rowdesc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
-                  c->m.R, c->m.omega, c->m.rate_out, c->m.esc, c->m.rev, c->m.prior,
+                  c->pblock,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
                   c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->sel, c->st_trip, c->st_trip_pad, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
   for (void *p : ptrs)
     if (p && !(p == (void *)c->st_trip && c->trip_in_mailbox)) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
+  if (c->h_pblock) cudaFreeHost(c->h_pblock);
   if (c->h_err) cudaFreeHost(c->h_err);
   if (c->h_slot) cudaFreeHost(c->h_slot);
   if (c->d_err) cudaFree(c->d_err);
@@ -585,19 +593,34 @@ extern "C" int mcq_ctx_set_params(mcq_ctx *c, const mcq_params *p) {
   CK(cudaSetDevice(c->d.device));
   const size_t S = c->d.num_sites, H = c->d.num_hla_types;
   c->m.mu = p->mu; c->m.kappa = p->kappa; c->m.phi = p->phi;
-  if (p->prior_C2) CK(cudaMemcpyAsync(c->m.prior, p->prior_C2, 64 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  if (p->R) CK(cudaMemcpyAsync(c->m.R, p->R, S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  if (p->omega) CK(cudaMemcpyAsync(c->m.omega, p->omega, S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  std::vector<double> tr;
-  if (p->rate_out_of_codons) {
-    tr.resize(S * 64);
-    for (size_t cd = 0; cd < 64; cd++)
-      for (size_t s = 0; s < S; s++) tr[s * 64 + cd] = p->rate_out_of_codons[cd * S + s];
-    CK(cudaMemcpyAsync(c->m.rate_out, tr.data(), S * 64 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));     // the staging block may still feed an earlier copy
+  double *h = c->h_pblock;
+  double *h_prior = h, *h_R = h_prior + 64, *h_omega = h_R + S, *h_rev = h_omega + S, *h_esc = h_rev + S,
+         *h_rate = h_esc + H * S;
+  if (p->prior_C2) memcpy(h_prior, p->prior_C2, 64 * sizeof(double));
+  if (p->R) memcpy(h_R, p->R, S * sizeof(double));
+  if (p->omega) memcpy(h_omega, p->omega, S * sizeof(double));
+  if (p->HLA_select_rev) memcpy(h_rev, p->HLA_select_rev, S * sizeof(double));
+  if (p->HLA_select_esc) memcpy(h_esc, p->HLA_select_esc, H * S * sizeof(double));
+  if (p->rate_out_of_codons)      // [64][S] -> site-major [S][64]
+    for (size_t cd = 0; cd < 64; cd++) {
+      const double *src = p->rate_out_of_codons + cd * S;
+      for (size_t s = 0; s < S; s++) h_rate[s * 64 + cd] = src[s];
+    }
+  if (p->prior_C2 && p->R && p->omega && p->HLA_select_rev && p->HLA_select_esc && p->rate_out_of_codons) {
+    CK(cudaMemcpyAsync(c->pblock, h, c->pblock_n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  } else {                        // only what was given
+    auto put = [&](double *dst, const double *src, size_t n) {
+      return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    };
+    if (p->prior_C2) CK(put(c->m.prior, h_prior, 64));
+    if (p->R) CK(put(c->m.R, h_R, S));
+    if (p->omega) CK(put(c->m.omega, h_omega, S));
+    if (p->HLA_select_rev) CK(put(c->m.rev, h_rev, S));
+    if (p->HLA_select_esc) CK(put(c->m.esc, h_esc, H * S));
+    if (p->rate_out_of_codons) CK(put(c->m.rate_out, h_rate, 64 * S));
   }
-  if (p->HLA_select_esc) CK(cudaMemcpyAsync(c->m.esc, p->HLA_select_esc, H * S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  if (p->HLA_select_rev) CK(cudaMemcpyAsync(c->m.rev, p->HLA_select_rev, S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  // no host wait: the copy is ordered before every later kernel on the context's stream
   c->have_params = true;
   c->has_pending = false;
   return 0;
