@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 #include "mcq_internal.cuh"
@@ -335,20 +336,25 @@ int hamming_device(const DevBuf &refp_, size_t npad, int N, const DevBuf &qryp_,
   return hamming_launch<8>(refp, npad, N, qryp, Q, W, D, st);
 }
 
-// closest_seqs.c:57-64 + util.c:24-30: forward shuffle with j = (int)((i+1) * random()/RAND_MAX)
-struct Pair { int idx; unsigned key; };
-void tie_shuffle_and_take(std::vector<Pair> &sorted_prefix, int n, int *out) {
-  const int M = (int)sorted_prefix.size();
-  int lo = n - 1, hi = n - 1;
-  const unsigned edge = sorted_prefix[n].key;          // element one past the cut (closest_seqs.c:85)
-  while (lo > 0 && sorted_prefix[lo - 1].key == edge) lo--;
-  hi = M - 1;                                          // the prefix ends with the whole "== edge" group
-  for (int i = 0; i <= hi - lo; i++) {
+// closest_seqs.c:57-64 + util.c:24-30: forward shuffle with j = (int)((i+1) * random()/RAND_MAX), applied to
+// the reference's window of the sorted list: element n-1 extended over its neighbours equal to the distance
+// T of element n (closest_seqs.c:85-88).  With the "< T" group (n_lt <= n elements, sorted on the device)
+// and the "== T" group (in index order) that window starts at lo = min(n_lt, n-1) and runs to the end of the
+// "== T" group; everything before lo is output as sorted.
+void tie_shuffle_and_take(const int *lt_sorted, int n_lt, const int *eq_group, long long n_eq, int n,
+                          std::vector<int> &win, int *out) {
+  const int lo = n_lt < n - 1 ? n_lt : n - 1;
+  memcpy(out, lt_sorted, (size_t)lo * sizeof(int));
+  win.clear();
+  for (int i = lo; i < n_lt; i++) win.push_back(lt_sorted[i]);          // at most element n-1
+  win.insert(win.end(), eq_group, eq_group + n_eq);
+  const int M = (int)win.size();
+  for (int i = 0; i < M; i++) {
     const double u = (i + 1) * ((double)random() / (double)RAND_MAX);
     const int j = (int)u;
-    std::swap(sorted_prefix[lo + i], sorted_prefix[lo + j]);
+    std::swap(win[i], win[j]);
   }
-  for (int i = 0; i < n; i++) out[i] = sorted_prefix[i].idx;
+  memcpy(out + lo, win.data(), (size_t)(n - lo) * sizeof(int));
 }
 
 // device selection over rows of D (V = uint16_t counts or int32 values), host shuffle, output
@@ -387,21 +393,16 @@ int select_rows(const V *D, int Q, int N, int n, int skip_first, int L, int *clo
                                            dltk.as<unsigned>(), dpool.as<int>());
     CK(cudaGetLastError());
   }
-  std::vector<int> lti((size_t)Q * cap), pool((size_t)std::max<long long>(off[Q], 1));
-  std::vector<unsigned> ltk((size_t)Q * cap);
-  CK(cudaMemcpyAsync(lti.data(), dlti.p, lti.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(ltk.data(), dltk.p, ltk.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(pool.data(), dpool.p, (size_t)off[Q] * sizeof(int), cudaMemcpyDeviceToHost, st));
+  // (the keys of the "< T" group stay on the device: the host only needs the sorted indices)
+  std::unique_ptr<int[]> lti(new int[(size_t)Q * cap]), pool(new int[(size_t)std::max<long long>(off[Q], 1)]);
+  CK(cudaMemcpyAsync(lti.get(), dlti.p, (size_t)Q * cap * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(pool.get(), dpool.p, (size_t)off[Q] * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
 
   // host: the reference's sequential tie shuffle, in query order (one shared libc random() stream)
-  std::vector<Pair> pre;
-  std::vector<int> tmp(n);
+  std::vector<int> win, tmp(n);
   for (int q = 0; q < Q; q++) {
-    pre.clear();
-    for (int i = 0; i < n_lt[q]; i++) pre.push_back({lti[(size_t)q * cap + i], ltk[(size_t)q * cap + i]});
-    for (long long i = off[q]; i < off[q + 1]; i++) pre.push_back({pool[i], Tk[q]});
-    tie_shuffle_and_take(pre, n, tmp.data());
+    tie_shuffle_and_take(lti.get() + (size_t)q * cap, n_lt[q], pool.get() + off[q], off[q + 1] - off[q], n, win, tmp.data());
     if (skip_first) memcpy(closest_refs + (size_t)q * L, tmp.data() + 1, (size_t)L * sizeof(int));   // dmodel.c:380-386
     else memcpy(closest_refs + (size_t)q * L, tmp.data(), (size_t)L * sizeof(int));
   }
