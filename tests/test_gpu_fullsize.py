@@ -109,6 +109,46 @@ def test_c4_proposals_are_reversible_and_consistent(api, c4):
     assert abs(s1 - d1) <= 1e-11 * abs(d1)
 
 
+def test_c4_lazy_refills_and_likelihood_only_sweep(api, c4):
+    """At the full C4 size: the sweep that writes no column gives the bits of the stored one; after a run of
+    accepted moves with owed refills (selector flips, catch-ups inside later proposals) the F.B identity holds
+    at every site, the state equals a fresh evaluation of the accepted parameters, and replaying the same
+    moves with the reference's refill schedule gives the same proposal totals bit for bit."""
+    p, ctx = c4
+    ctx.set_option(api.OPT_SPARSE_ESC, 0)
+    ctx.set_params(mu=p.mu, kappa=p.kappa, phi=p.phi, prior=p.prior, R=p.R, omega=p.omega,
+                   rate_out=p.rate_out_of_codons(), esc=p.esc, rev=p.rev[0])
+    moves = [dict(kind=api.PROP_REV, start=300, end=380, value0=1.3),
+             dict(kind=api.PROP_REC, start=120, value0=0.03),
+             dict(kind=api.PROP_ESC, start=40, end=110, hla=2, value0=0.7, value1=1.6, split=80),
+             dict(kind=api.PROP_SEL, start=450, value0=1.8),
+             dict(kind=api.PROP_ESC, start=200, end=499, hla=5, value0=1.2)]
+    totals = {}
+    for lazy in (1, 0):
+        ctx.set_option(api.OPT_LAZY_REFILL, lazy)
+        ctx.set_params(mu=p.mu, kappa=p.kappa, phi=p.phi, R=p.R, omega=p.omega,
+                       rate_out=p.rate_out_of_codons(), esc=p.esc, rev=p.rev[0])
+        llk = ctx.init_state()
+        assert ctx.llk_only(False) == llk and ctx.llk_only(True) == llk
+        out = []
+        for mv in moves:
+            out.append(ctx.propose(**mv))
+            ctx.accept()
+        totals[lazy] = out
+        per_q = ctx.query_llk()
+        assert abs(float(np.sum(per_q)) - out[-1]) <= 1e-10 * abs(out[-1])
+        for q in (3, 6021):
+            F, Fn = ctx.matrix(api.BUF_F, q)
+            B, Bn = ctx.matrix(api.BUF_B, q)
+            per_site = np.log((F * B).sum(0)) - (Fn + Bn) * np.log(1e6)
+            assert np.max(np.abs(per_site - per_q[q])) < 1e-9 * abs(per_q[q])
+        # the accepted parameters, evaluated from scratch
+        fresh = ctx.llk_only(False)
+        assert abs(fresh - out[-1]) <= 1e-11 * abs(out[-1])
+    assert totals[0] == totals[1]
+    ctx.set_option(api.OPT_LAZY_REFILL, 1)
+
+
 def test_c3_closest_L_full_panel(api):
     """C3: 100 000 references x 1 500 nt, L = 500.  Bit-exact against the oracle on the first queries
     (the tie-shuffle stream of query k depends only on queries 0..k), structural properties on all."""
