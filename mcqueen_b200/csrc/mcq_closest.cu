@@ -269,6 +269,125 @@ __global__ void __launch_bounds__(512) k_select_fill(const V *__restrict__ D, in
 }
 
 // ------------------------------------------------------------------------------------------
+// The batched path (16-bit mismatch counts, at most num_bases): one read of the row builds the full
+// histogram of the distances in shared memory (warp-aggregated atomics: the counts cluster on few
+// values), from which T, n_lt and n_eq follow; the fill kernel gives every warp a contiguous span of the
+// row, counts first, then writes the "< T" pairs and the "== T" indices at warp-local offsets (ballots
+// keep the index order), two block barriers in all.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) k_select_hist(const uint16_t *__restrict__ D, int N, int n, int nbins,
+                                                     unsigned *__restrict__ Tkey, int *__restrict__ n_lt,
+                                                     int *__restrict__ n_eq) {
+  extern __shared__ unsigned hist[];          // nbins counters
+  __shared__ unsigned warp_sum[16];
+  const uint16_t *row = D + (size_t)blockIdx.x * N;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < N; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool valid = i < N;
+    const unsigned k = valid ? row[i] : 0x10000u + lane;      // a key nobody shares
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[k], (unsigned)__popc(peers));
+  }
+  __syncthreads();
+  // the bin that holds rank n: every thread sums a contiguous chunk of bins, block scan of the partials
+  const int chunk = (nbins + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int b0 = min(nbins, (int)threadIdx.x * chunk), b1 = min(nbins, b0 + chunk);
+  unsigned local = 0;
+  for (int b = b0; b < b1; b++) local += hist[b];
+  unsigned incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sum[wid] = incl;
+  __syncthreads();
+  unsigned base = 0;
+  for (int w = 0; w < wid; w++) base += warp_sum[w];
+  const unsigned excl = base + incl - local;
+  if ((unsigned)n >= excl && (unsigned)n < excl + local) {
+    unsigned cum = excl;
+    for (int b = b0; b < b1; b++) {
+      const unsigned h = hist[b];
+      if ((unsigned)n < cum + h) {
+        Tkey[blockIdx.x] = (unsigned)b; n_lt[blockIdx.x] = (int)cum; n_eq[blockIdx.x] = (int)h;
+        break;
+      }
+      cum += h;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) k_select_fill_spans(const uint16_t *__restrict__ D, int N, int cap,
+                                                           const unsigned *__restrict__ Tkey,
+                                                           const long long *__restrict__ eq_off,
+                                                           int *__restrict__ lt_idx, unsigned *__restrict__ lt_key,
+                                                           int *__restrict__ eq_pool) {
+  extern __shared__ u64 keys[];          // cap2 = next pow2 >= cap
+  __shared__ unsigned cnt_lt[16], cnt_eq[16];
+  const int q = blockIdx.x;
+  const uint16_t *row = D + (size_t)q * N;
+  const unsigned T = Tkey[q];
+  int cap2 = 1;
+  while (cap2 < cap) cap2 <<= 1;
+  for (int i = threadIdx.x; i < cap2; i += blockDim.x) keys[i] = ~0ull;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int span = ((N + nw - 1) / nw + 31) / 32 * 32;          // a multiple of the warp width
+  const int s0 = min(N, wid * span), s1 = min(N, s0 + span);
+  unsigned c_lt = 0, c_eq = 0;
+  for (int i = s0 + lane; i < s1; i += 32) {
+    const unsigned k = row[i];
+    c_lt += (k < T); c_eq += (k == T);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c_lt += __shfl_xor_sync(0xffffffffu, c_lt, o);
+    c_eq += __shfl_xor_sync(0xffffffffu, c_eq, o);
+  }
+  if (lane == 0) { cnt_lt[wid] = c_lt; cnt_eq[wid] = c_eq; }
+  __syncthreads();
+  unsigned lt_at = 0, eq_at = 0;
+  for (int w = 0; w < wid; w++) { lt_at += cnt_lt[w]; eq_at += cnt_eq[w]; }
+  int *eq_out = eq_pool + eq_off[q];
+  const unsigned below = (1u << lane) - 1;
+  for (int i0 = s0; i0 < s1; i0 += 32) {
+    const int i = i0 + lane;
+    const unsigned k = i < s1 ? row[i] : 0xffffffffu;
+    const unsigned b_lt = __ballot_sync(0xffffffffu, k < T), b_eq = __ballot_sync(0xffffffffu, k == T);
+    if (k < T) {
+      const unsigned slot = lt_at + __popc(b_lt & below);
+      if (slot < (unsigned)cap2) keys[slot] = ((u64)k << 32) | (unsigned)i;
+    }
+    if (k == T) eq_out[eq_at + __popc(b_eq & below)] = i;
+    lt_at += __popc(b_lt); eq_at += __popc(b_eq);
+  }
+  __syncthreads();
+  // bitonic sort of the "< T" keys (padding = all ones sorts last)
+  for (int size = 2; size <= cap2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < cap2; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = ((i & size) == 0);
+          const u64 a = keys[i], b = keys[j];
+          if ((a > b) == up) { keys[i] = b; keys[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  unsigned nlt = 0;
+  for (int w = 0; w < nw; w++) nlt += cnt_lt[w];
+  const int take = min((int)nlt, cap);
+  for (int i = threadIdx.x; i < take; i += blockDim.x) {
+    lt_idx[(size_t)q * cap + i] = (int)(keys[i] & 0xffffffffu);
+    lt_key[(size_t)q * cap + i] = (unsigned)(keys[i] >> 32);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 namespace {
@@ -359,14 +478,25 @@ void tie_shuffle_and_take(const int *lt_sorted, int n_lt, const int *eq_group, l
 
 // device selection over rows of D (V = uint16_t counts or int32 values), host shuffle, output
 template <typename V>
-int select_rows(const V *D, int Q, int N, int n, int skip_first, int L, int *closest_refs, cudaStream_t st) {
+int select_rows(const V *D, int Q, int N, int n, int skip_first, int L, int *closest_refs, cudaStream_t st,
+                int max_key = -1) {
   DevBuf dT, dlt, deq, doff, dlti, dltk, dpool;
   CK(cudaMalloc(&dT.p, (size_t)Q * sizeof(unsigned)));
   CK(cudaMalloc(&dlt.p, (size_t)Q * sizeof(int)));
   CK(cudaMalloc(&deq.p, (size_t)Q * sizeof(int)));
   {
     EventTimer t(st, &g_ms_select);
-    k_select_count<V><<<Q, 512, 0, st>>>(D, N, n, dT.as<unsigned>(), dlt.as<int>(), deq.as<int>());
+    bool done = false;
+    if constexpr (sizeof(V) == 2) {
+      // the full histogram of the counts fits in shared memory: one read of the row
+      const size_t hbytes = (size_t)(max_key + 1) * sizeof(unsigned);
+      if (max_key >= 0 && hbytes <= 200 * 1024) {
+        CK(cudaFuncSetAttribute(k_select_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hbytes));
+        k_select_hist<<<Q, 512, hbytes, st>>>(D, N, n, max_key + 1, dT.as<unsigned>(), dlt.as<int>(), deq.as<int>());
+        done = true;
+      }
+    }
+    if (!done) k_select_count<V><<<Q, 512, 0, st>>>(D, N, n, dT.as<unsigned>(), dlt.as<int>(), deq.as<int>());
     CK(cudaGetLastError());
   }
   std::vector<int> n_lt(Q), n_eq(Q);
@@ -386,11 +516,17 @@ int select_rows(const V *D, int Q, int N, int n, int skip_first, int L, int *clo
   CK(cudaMalloc(&dpool.p, (size_t)std::max<long long>(off[Q], 1) * sizeof(int)));
   CK(cudaMemcpyAsync(doff.p, off.data(), (size_t)(Q + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   const size_t smem = (size_t)cap2 * sizeof(u64);
-  CK(cudaFuncSetAttribute(k_select_fill<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     EventTimer t(st, &g_ms_select);
-    k_select_fill<V><<<Q, 512, smem, st>>>(D, N, cap, dT.as<unsigned>(), doff.as<long long>(), dlti.as<int>(),
-                                           dltk.as<unsigned>(), dpool.as<int>());
+    if constexpr (sizeof(V) == 2) {
+      CK(cudaFuncSetAttribute(k_select_fill_spans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_select_fill_spans<<<Q, 512, smem, st>>>(D, N, cap, dT.as<unsigned>(), doff.as<long long>(), dlti.as<int>(),
+                                                dltk.as<unsigned>(), dpool.as<int>());
+    } else {
+      CK(cudaFuncSetAttribute(k_select_fill<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_select_fill<V><<<Q, 512, smem, st>>>(D, N, cap, dT.as<unsigned>(), doff.as<long long>(), dlti.as<int>(),
+                                             dltk.as<unsigned>(), dpool.as<int>());
+    }
     CK(cudaGetLastError());
   }
   // (the keys of the "< T" group stay on the device: the host only needs the sorted indices)
@@ -474,7 +610,8 @@ extern "C" int mcq_closest_batch(int device, const char *ref_seqs, size_t ref_st
   StreamGuard sg;
   if (distances(device, ref_seqs, ref_stride, num_refs, query_seqs, query_stride, num_query, num_bases, D, sg))
     return 1;
-  return select_rows<uint16_t>(D.as<uint16_t>(), num_query, num_refs, n, skip_first, closest_n, closest_refs, sg.s);
+  return select_rows<uint16_t>(D.as<uint16_t>(), num_query, num_refs, n, skip_first, closest_n, closest_refs, sg.s,
+                               num_bases);
 }
 
 // ------------------------------------------------------------------------------------------
