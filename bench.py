@@ -206,7 +206,8 @@ def run_ref_bench(p, threads, seconds, path=None, total_queries=None):
 # dmodel MCMC steps/s (second half of BASELINE.json's metric): the C driver on the GPU library next
 # to the reference dmodel on the host CPU, same files, same seeds, default move mix with annealing
 # ------------------------------------------------------------------------------------------------
-def mcmc_steps_per_s(workload, steps, ref_steps=12, variants=(("gpu", []), ("gpu_sparse_esc", ["--sparse_esc"]))):
+def mcmc_steps_per_s(workload, steps, ref_steps=12,
+                     variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]), ("gpu_sparse_esc", ["--sparse_esc"]))):
     import re
     import shutil
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -215,7 +216,10 @@ def mcmc_steps_per_s(workload, steps, ref_steps=12, variants=(("gpu", []), ("gpu
     if not os.path.exists(driver):
         return {"error": "mcqueen_b200/host/mcq_dmodel not built"}
     tmp = tempfile.mkdtemp(prefix="mcq_mcmc_")
-    out = {"workload": workload, "steps": steps}
+    out = {"workload": workload, "steps": steps,
+           "variants": "gpu = driver defaults (escape-window proposals re-evaluate carriers only when the shard is "
+                       "large enough to be bound by bytes); dense_esc = every query, as the reference; eager_refill = "
+                       "dense_esc with the reference's refill after every accept"}
     try:
         paths, L, _ = make_chain_inputs(os.path.join(tmp, "in"), workload, seed=SEED, query_model="dsim")
         out["data"] = "queries drawn from the model itself (dsim recipe, mcqueen_b200/synth.py)"
@@ -511,8 +515,9 @@ def main():
             line["mcmc"] = mcmc_steps_per_s("C2", args.mcmc_steps)
             # the same driver at the headline shape (no CPU side: the reference would need hours)
             line["mcmc_c4"] = mcmc_steps_per_s(args.workload, 600, ref_steps=0,
-                                               variants=(("gpu", []), ("gpu_sparse_esc", ["--sparse_esc"]),
-                                                         ("gpu_eager_refill", ["--eager_refill"])))
+                                               variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]),
+                                                         ("gpu_sparse_esc", ["--sparse_esc"]),
+                                                         ("gpu_eager_refill", ["--dense_esc", "--eager_refill"])))
         if world == 1 and args.cpu_seconds > 0:
             ncpu = os.cpu_count() or 1
             v, desc = run_ref_bench(p, ncpu, args.cpu_seconds)

@@ -350,7 +350,8 @@ static void move_mutation(Chain *c, double temperature)
 static int chain_length = 50000, sample_rate = 100, closest_n = 100, runtime_hours = 0;
 static const char *ref_path, *query_path, *out_dir, *hla_path, *cons_path;
 static bool separate_reference_set = true, no_hla = false, no_rev = false, no_rec = false, no_anneal = false;
-static bool opt_sample_prior = false, opt_sparse = false, runtime_set = false, states_set = false, opt_nccl = false,
+static int opt_sparse = -1;   /* -1 auto, 0 dense, 1 sparse */
+static bool opt_sample_prior = false, runtime_set = false, states_set = false, opt_nccl = false,
             opt_eager = false;
 static int opt_omega_prior = MCQ_PRIOR_EXPONENTIAL, opt_esc_prior = MCQ_PRIOR_LOG_NORMAL;
 static int opt_rev_prior = MCQ_PRIOR_LOG_NORMAL, opt_device = -1;
@@ -366,7 +367,7 @@ static void usage(void)
           "  -q self-reference mode  -i no HLA inference  -j no reversion inference  -o no recombination\n"
           "  -v/-e/-w omega prior gamma/log-normal/uniform   -g/-k/-f escape prior gamma/normal/flat\n"
           "  -a/-d/-u reversion prior gamma/normal/flat   -b sample the prior   -z no simulated annealing\n"
-          "  --seed N --gsl_seed N (default: clock)  --device D  --sparse_esc  --trace FILE  --nccl\n"
+          "  --seed N --gsl_seed N (default: clock)  --device D  --sparse_esc | --dense_esc  --trace FILE  --nccl\n"
           "  --eager_refill  refill F and B at every accept (the reference's schedule) instead of when next read\n");
   exit(EXIT_FAILURE);
 }
@@ -388,7 +389,8 @@ static void parse(int argc, char **argv)
       {"no_simulated_annealing", no_argument, NULL, 'z'}, {"seed", required_argument, NULL, 1001},
       {"gsl_seed", required_argument, NULL, 1002}, {"device", required_argument, NULL, 1003},
       {"sparse_esc", no_argument, NULL, 1004}, {"trace", required_argument, NULL, 1005},
-      {"nccl", no_argument, NULL, 1006}, {"eager_refill", no_argument, NULL, 1007}, {NULL, 0, NULL, 0}};
+      {"nccl", no_argument, NULL, 1006}, {"eager_refill", no_argument, NULL, 1007}, {"dense_esc", no_argument, NULL, 1008},
+      {NULL, 0, NULL, 0}};
   int o;
   while((o = getopt_long(argc, argv, "H:n:s:t:c:r:l:qijovewgkfadubz", lo, NULL)) != -1) {
     switch(o) {
@@ -417,7 +419,8 @@ static void parse(int argc, char **argv)
       case 1001: opt_seed = atol(optarg); break;
       case 1002: opt_gsl_seed = atol(optarg); break;
       case 1003: opt_device = atoi(optarg); break;
-      case 1004: opt_sparse = true; break;
+      case 1004: opt_sparse = 1; break;
+      case 1008: opt_sparse = 0; break;
       case 1005: trace_path = optarg; break;
       case 1006: opt_nccl = true; break;
       case 1007: opt_eager = true; break;
@@ -638,7 +641,13 @@ int main(int argc, char **argv)
                               d.query_codons, d.hla, d.consensus_codons, d.n_site_codons, d.site_codons));
   mcq_params prm = {c.mu, kappa, phi, prior, c.R, c.omega, rate_out, c.esc, c.rev};
   CHECK(mcq_ctx_set_params(c.ctx, &prm));
+  /* An escape-window proposal changes the emissions of the carriers of one HLA type only.  Re-evaluating just
+   * those queries pays when the evaluation is bound by bytes (large shards of wide queries) and costs when it
+   * is bound by the chain of dependent sites (small shards: the catch-ups of differently stale queries no
+   * longer coincide); by default the shard's size decides (the same on every rank). */
+  if(opt_sparse < 0) opt_sparse = (double)Qall / world * ((closest_n + 15) / 16 * 16) >= 262144.0 ? 1 : 0;
   if(opt_sparse) CHECK(mcq_ctx_set_option(c.ctx, MCQ_OPT_SPARSE_ESC, 1));
+  printf("escape-window proposals: %s\n", opt_sparse ? "carriers only (--dense_esc for all queries)" : "all queries (--sparse_esc for carriers only)");
   if(opt_eager) CHECK(mcq_ctx_set_option(c.ctx, MCQ_OPT_LAZY_REFILL, 0));
   if(world > 1 && !opt_nccl) {
     /* shard totals are exchanged by NVLink peer stores inside the reduction kernel */

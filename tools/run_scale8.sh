@@ -12,7 +12,7 @@ make_chain_inputs("/tmp/c4in", "C4", seed=20261019)
 PY
 D=mcqueen_b200/host/mcq_dmodel
 A="-H /tmp/c4in/query.HLA.csv -l 500 -n 1000 -s 100000 /tmp/c4in/ref.fasta /tmp/c4in/query.fasta"
-for extra in "" "--sparse_esc"; do
+for extra in "" "--dense_esc"; do
   echo "== 8 GPUs $extra"
   $TR --no-python --nproc-per-node 8 --master-port 29524 $D --seed 1 --gsl_seed 1 $extra $A /tmp/c4out8 2>&1 | grep -E "MCMC loop|final log" | sort | uniq -c
 done
