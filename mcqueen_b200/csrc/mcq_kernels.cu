@@ -561,16 +561,16 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
   __syncwarp();                  // ... and every other lane's; the slot of site s-1 is free again
   {
     constexpr int KT = (K + MCQ_PF) & 3;       // ring slot of site t = s + MCQ_PF
-    const int t = w.t;
+    // the running pointers address the group's first site: constant offsets inside the group of four,
+    // one bump per group
+    const int t = w.t + K;
     const unsigned cur = w.rd[KT];
-    w.rd[KT] = (t + MCQ_RING <= a.end) ? *w.rdp : 0u;   // consumed four sites from now
-    w.rdp++;
+    w.rd[KT] = (t + MCQ_RING <= a.end) ? w.rdp[K] : 0u;   // consumed four sites from now
     const bool pre = PRE && t < a.start;
     const double *eq = pre ? ecq_pre : ecq;
-    stage_k<NJ, KT>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.Rp, w.gsrc, lane);
-    w.gsrc += 64 * NJ;
-    w.Rp++;
-    w.t = t + 1;
+    stage_k<NJ, KT>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.Rp + K,
+                    w.gsrc + K * (64 * NJ), lane);
+    if (K == 3) { w.t += 4; w.rdp += 4; w.Rp += 4; w.gsrc += 4 * (64 * NJ); }
   }
   unsigned g[(2 * NJ + 3) / 4];
   load_slots<NJ, K>(gl, g);
@@ -601,21 +601,18 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
     // or into the other one (a proposal): the same offset, `delta` doubles away
     const bool pre = PRE && s < a.start;
     const unsigned cur1 = w.sel[K];
-    if (has_sel) {
-      if (s + MCQ_RING <= a.end) w.sel[K] = *w.selp;   // consumed four sites from now
-      w.selp++;
-    }
+    if (has_sel && s + MCQ_RING <= a.end) w.sel[K] = w.selp[K];   // consumed four sites from now
     const bool into1 = (cur1 != 0) != (!a.in_place && !pre);
-    double *__restrict__ Fs = into1 ? w.Fs + delta : w.Fs;
+    const size_t row = FULL ? (size_t)(64 * NJ) : (size_t)a.st.Ls;   // doubles per column
+    double *__restrict__ Fs = (into1 ? w.Fs + delta : w.Fs) + K * row;
 #pragma unroll
     for (int j = 0; j < NJ; j++)
       if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(w.p0[j], w.p1[j]));
     if (lane == 0) {
       if (pre) Fnc[s] = w.cnt;
-      else *w.Fnp = w.cnt;
+      else w.Fnp[K] = w.cnt;
     }
-    w.Fs += a.st.Ls;
-    w.Fnp++;
+    if (K == 3) { w.Fs += 4 * row; w.Fnp += 4; w.selp += 4; }
   }
 }
 
@@ -836,16 +833,15 @@ struct BwdWarp {
 template <int NJ, int K>
 __device__ __forceinline__ void bwd_stage(const BwdArgs &a, BwdWarp<NJ> &w, unsigned g_sh, unsigned e_sh,
                                           const double *tabl, int bottom, int lane) {
+  // (the staging calls run K = 0, 1, 2, 3, 0, ...: the running pointers address the site of K = 0, constant
+  // offsets inside the group of four, one bump per group)
   constexpr int KT = (K + MCQ_PF) & 3;
-  const int t = w.t;
+  const int t = w.t - K;
   const unsigned cur = w.rd[KT];
-  w.rd[KT] = (t - MCQ_RING >= bottom) ? *w.rdp : 0u;
-  w.rdp--;
-  stage_k<NJ, KT>(g_sh, e_sh, t >= bottom, cur, tabl, w.ecp, a.em.ec != nullptr, w.Rp, w.gsrc, lane);
-  w.gsrc -= 64 * NJ;
-  w.ecp--;
-  w.Rp--;
-  w.t = t - 1;
+  w.rd[KT] = (t - MCQ_RING >= bottom) ? *(w.rdp - K) : 0u;
+  stage_k<NJ, KT>(g_sh, e_sh, t >= bottom, cur, tabl, w.ecp - K, a.em.ec != nullptr, w.Rp - K,
+                  w.gsrc - K * (64 * NJ), lane);
+  if (K == 3) { w.t -= 4; w.rdp -= 4; w.ecp -= 4; w.Rp -= 4; w.gsrc -= 4 * (64 * NJ); }
 }
 
 // one site of the recursion: computes column s from column s+1; the rows of site s are in ring slot K
@@ -889,12 +885,15 @@ __device__ __forceinline__ void bwd_site(const BwdArgs &a, BwdWarp<NJ> &w, const
     for (int j = 0; j < NJ; j++) { w.b0[j] *= MCQ_BIG; w.b1[j] *= MCQ_BIG; }
     w.sx *= MCQ_BIG;
   }
+  // (the sites run K = 1, 2, 3, 0, 1, ...: the output pointers address the site of K = 1)
+  constexpr int J = (K + 3) & 3;
+  const size_t row = FULL ? (size_t)(64 * NJ) : (size_t)a.st.Ls;   // doubles per column
+  double *__restrict__ Bs = w.Bs - J * row;
 #pragma unroll
   for (int j = 0; j < NJ; j++)
-    if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(w.Bs + 64 * j), make_double2(w.b0[j], w.b1[j]));
-  if (lane == 0) *w.Bnp = w.cnt;
-  w.Bs -= a.st.Ls;
-  w.Bnp--;
+    if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(Bs + 64 * j), make_double2(w.b0[j], w.b1[j]));
+  if (lane == 0) *(w.Bnp - J) = w.cnt;
+  if (K == 0) { w.Bs -= 4 * row; w.Bnp -= 4; }
 }
 
 template <int NJ, bool FULL>
