@@ -403,12 +403,20 @@ def main():
         e2e_parts[:] += (t1 - t0, t2 - t1, t3 - t2, t4 - t3)
         return tot, per_q
 
+    # the gather's share of an upload (bracketing kernels costs host time: outside the timed loop)
+    ctx.enable_timing(2)
+    ctx.kernel_time(api.K_GATHER, reset=True)
+    for _ in range(3):
+        ctx.upload_static(p.ref_triplets, p.closest_refs, p.cons_query_nucls, p.query_codons, p.hla,
+                          p.consensus_codons, p.n_site_codons, p.site_codons)
+    gather_ms = ctx.kernel_time(api.K_GATHER)[0] / 3
+    ctx.enable_timing(0)
+    # the upload returns when the DMAs are done; the evaluation follows the device-side set-up chunk by chunk
+    ctx.set_option(api.OPT_ASYNC_UPLOAD, 1)
     for _ in range(2):
         e2e_step()
     barrier()
     e2e_parts[:] = 0
-    ctx.enable_timing(2)
-    ctx.kernel_time(api.K_GATHER, reset=True)
     ctx.timer_start()
     t_e2e = time.perf_counter()
     for _ in range(args.steps):
@@ -416,8 +424,7 @@ def main():
     ms_e2e_dev = ctx.timer_stop()
     barrier()
     t_e2e = (time.perf_counter() - t_e2e) * 1e3
-    gather_ms = ctx.kernel_time(api.K_GATHER)[0] / max(args.steps, 1)
-    ctx.enable_timing(0)
+    ctx.set_option(api.OPT_ASYNC_UPLOAD, 0)
     for a in host_arrays:
         api.host_unregister(a)
     assert abs(tot - llk0) <= 1e-12 * abs(llk0)
@@ -498,7 +505,8 @@ def main():
                     "breakdown_ms": dict(zip(["upload_static", "set_params", "full_llk", "read_back"],
                                              (e2e_parts / args.steps * 1e3).round(3).tolist()), gather_kernel=round(gather_ms, 3)),
                     "what": "mcq_ctx_upload_static + mcq_ctx_set_params + mcq_ctx_full_llk + per-query llk "
-                            "read-back, all inputs from pinned host buffers every step (bytes per rank" +
+                            "read-back, all inputs from pinned host buffers every step, MCQ_OPT_ASYNC_UPLOAD: the evaluation "
+                            "follows the upload's device-side set-up chunk by chunk (bytes per rank" +
                             ("; the reference panel is DMA'd in 1/N slices and completed over NVLink)" if world > 1 and comm_kind == "peer" else ")")},
             "roofline": {"bound": "hbm", "kernel": "k_forward", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

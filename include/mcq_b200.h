@@ -140,6 +140,14 @@ int mcq_ctx_full_llk(mcq_ctx *ctx, int with_emission, double *llk);
  * proposal, mcmc_moves.c:1124-1134, is evaluated this way).  with_emission != 0 rebuilds the
  * emission table first and marks F and B as owed (see MCQ_OPT_LAZY_REFILL). */
 int mcq_ctx_llk_only(mcq_ctx *ctx, int with_emission, double *llk);
+/* One-off tuning of the sweep kernels for this shard (call after mcq_ctx_init_state): the full forward
+ * sweep (stored and likelihood-only) and the full backward sweep are timed at every number of resident
+ * blocks per SM the kernels allow, and the fastest is used for launches of that kernel with this many
+ * queries from then on (process-wide).  Every block of a sweep lives for the whole sweep of its query,
+ * so the residency decides how the last wave fills and how many write streams the HBM sees; the best
+ * value depends on the shard size.  The state is left as it was.  blocks_per_sm (may be NULL) receives
+ * the three choices.  Takes a few dozen sweeps. */
+int mcq_ctx_tune(mcq_ctx *ctx, int blocks_per_sm[3]);
 /* update_B_numerical_recipes(update = S-1) for every query. */
 int mcq_ctx_backward_fill(mcq_ctx *ctx);
 
@@ -186,11 +194,16 @@ enum {
                               next evaluation that needs those columns, with the parameters then
                               current - the same values, computed when first read.  0: refill at
                               once, the reference's schedule. */
-  MCQ_OPT_SHARED_PANEL = 3 /* default 1, effective once mcq_ctx_attach_peers has run: in
+  MCQ_OPT_SHARED_PANEL = 3, /* default 1, effective once mcq_ctx_attach_peers has run: in
                               mcq_ctx_upload_static every rank DMAs 1/nranks of ref_triplets from the
                               host and reads the rest from its peers over NVLink.  All ranks must then
                               call mcq_ctx_upload_static together and with the same panel.  0: every
                               rank uploads the whole panel itself. */
+  MCQ_OPT_ASYNC_UPLOAD = 4 /* default 0.  1: mcq_ctx_upload_static returns as soon as the caller's buffers
+                              have been DMA'd (they may be reused); the device-side set-up runs on, chunk
+                              by chunk, and the next mcq_ctx_full_llk evaluates each chunk of queries as
+                              soon as it is ready, under the set-up of the next one.  A closest_refs entry
+                              out of range is then reported by that evaluation, not by the upload. */
 };
 int mcq_ctx_set_option(mcq_ctx *ctx, int option, int value);
 

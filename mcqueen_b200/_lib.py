@@ -50,6 +50,7 @@ SYMBOLS = {
     "mcq_ctx_init_state": (C.c_int, [_V, c_double_p]),
     "mcq_ctx_full_llk": (C.c_int, [_V, C.c_int, c_double_p]),
     "mcq_ctx_llk_only": (C.c_int, [_V, C.c_int, c_double_p]),
+    "mcq_ctx_tune": (C.c_int, [_V, c_int_p]),
     "mcq_ctx_backward_fill": (C.c_int, [_V]),
     "mcq_ctx_propose": (C.c_int, [_V, C.POINTER(McqProposal), c_double_p]),
     "mcq_ctx_accept": (C.c_int, [_V]),

@@ -24,6 +24,7 @@ TAB_C2C, TAB_A, TAB_TMP_C2C, TAB_TMP_A = 0, 1, 2, 3
 OPT_SPARSE_ESC = 1
 OPT_LAZY_REFILL = 2
 OPT_SHARED_PANEL = 3
+OPT_ASYNC_UPLOAD = 4
 K_GATHER, K_EMISSION, K_FORWARD, K_BACKWARD, K_COMMIT, K_SUM = range(6)
 
 
@@ -227,6 +228,13 @@ class Context:
         v = C.c_double()
         check(self.lib.mcq_ctx_llk_only(self._h, 1 if with_emission else 0, C.byref(v)))
         return v.value
+
+    def tune(self):
+        """Times the full sweeps at every residency; returns the blocks per SM chosen for
+        (forward stored, forward likelihood-only, backward)."""
+        k = (C.c_int * 3)()
+        check(self.lib.mcq_ctx_tune(self._h, k))
+        return tuple(k)
 
     def backward_fill(self):
         check(self.lib.mcq_ctx_backward_fill(self._h))

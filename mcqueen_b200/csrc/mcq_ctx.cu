@@ -82,6 +82,7 @@ static const int kNcclSum = 0;     // ncclSum
 // ------------------------------------------------------------------------------------------
 // the context
 // ------------------------------------------------------------------------------------------
+static const int kPipeStreams = 3;    // chunks of a pipelined evaluation in flight at once
 static const int kUploadChunks = 8;   // query chunks of mcq_ctx_upload_static (transfer under gather)
 
 struct mcq_ctx {
@@ -92,6 +93,16 @@ struct mcq_ctx {
   cudaStream_t stream2 = nullptr;            // the backward refill of an accept runs beside the forward refill
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chunk[1 + kUploadChunks] = {nullptr};   // upload_static: panel landed, chunk k landed
+  // MCQ_OPT_ASYNC_UPLOAD: mcq_ctx_upload_static returns once the DMAs are done; the chunks' gathers are
+  // still running on the main stream, ev_ready[k] marks chunk k complete, and the next mcq_ctx_full_llk
+  // evaluates chunk by chunk on stream3 behind them (pipe_n chunks, queries pipe_q[k] .. pipe_q[k+1]-1)
+  cudaStream_t stream3 = nullptr;   // the pipelined evaluation: stream3 and pipe_st[] in turn
+  cudaStream_t pipe_st[kPipeStreams - 1] = {nullptr};
+  cudaEvent_t ev_ps[kPipeStreams - 1] = {nullptr};
+  cudaEvent_t ev_ready[kUploadChunks] = {nullptr}, ev_params = nullptr, ev_static = nullptr, ev_pipe = nullptr;
+  int pipe_n = 0, pipe_q[kUploadChunks + 1] = {0};
+  bool params_on_copy_stream = false;
+  int opt_async_upload = 0;
   size_t bytes = 0;
   bool have_static = false, have_params = false, have_state = false;
   bool have_fwd = false;     // a full forward sweep has run since the last upload: with a backward fill it makes a state
@@ -275,6 +286,21 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (cudaEvent_t &e : c->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaEvent_t &e : c->ev_ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_params, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_static, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_pipe, cudaEventDisableTiming));
+  {
+    // the pipelined evaluation outranks the set-up kernels still queued on the main stream: its long-lived
+    // one-warp blocks are dispatched first and the set-up fills the rest of the SMs
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < kPipeStreams - 1; i++) {
+      CK(cudaStreamCreateWithPriority(&c->pipe_st[i], cudaStreamNonBlocking, hi));
+      CK(cudaEventCreateWithFlags(&c->ev_ps[i], cudaEventDisableTiming));
+    }
+  }
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
   CK(cudaEventCreate(&c->evt0));
@@ -329,6 +355,15 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   for (cudaEvent_t e : c->fev) cudaEventDestroy(e);
   cudaStreamSynchronize(c->stream2);
   for (cudaEvent_t e : c->ev_chunk) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_ready) if (e) cudaEventDestroy(e);
+  if (c->ev_params) cudaEventDestroy(c->ev_params);
+  if (c->ev_static) cudaEventDestroy(c->ev_static);
+  if (c->ev_pipe) cudaEventDestroy(c->ev_pipe);
+  if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
+  for (int i = 0; i < kPipeStreams - 1; i++) {
+    if (c->pipe_st[i]) { cudaStreamSynchronize(c->pipe_st[i]); cudaStreamDestroy(c->pipe_st[i]); }
+    if (c->ev_ps[i]) cudaEventDestroy(c->ev_ps[i]);
+  }
   cudaEventDestroy(c->ev_fork);
   cudaEventDestroy(c->ev_join);
   cudaStreamDestroy(c->stream2);
@@ -402,6 +437,7 @@ extern "C" int mcq_ctx_set_option(mcq_ctx *c, int option, int value) {
   REQUIRE(c, "null context");
   if (option == MCQ_OPT_SPARSE_ESC) { c->opt_sparse_esc = value; return 0; }
   if (option == MCQ_OPT_SHARED_PANEL) { c->opt_shared_panel = value; return 0; }
+  if (option == MCQ_OPT_ASYNC_UPLOAD) { c->opt_async_upload = value; return 0; }
   if (option == MCQ_OPT_LAZY_REFILL) {
     if (!value && c->have_state && mcq_ctx_flush(c)) return 1;   // leave lazy mode with F and B complete
     c->opt_lazy = value;
@@ -515,6 +551,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   CK(cudaMemcpyAsync(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventRecord(c->ev_fork, c->stream));                 // the copy stream starts behind earlier work
+  CK(cudaEventRecord(c->ev_static, c->stream));               // ... and so does a pipelined evaluation
   CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
   const bool shared_panel = c->have_peers && c->trip_in_mailbox && c->opt_shared_panel && c->box.nranks > 1;
   if (shared_panel) {
@@ -556,6 +593,8 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     }
     CK(mcq_launch_rowdesc(st_all, c->rowdesc, (int)q0, (int)nq, c->stream));
     c->launches++;
+    CK(cudaEventRecord(c->ev_ready[k], c->stream));
+    c->pipe_q[k] = (int)q0; c->pipe_q[k + 1] = (int)q1;
   }
   c->hla_h.resize((size_t)Q * H);
   for (size_t i = 0; i < c->hla_h.size(); i++) c->hla_h[i] = hla_types[i] == '1';
@@ -574,6 +613,15 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     c->launches++;
   }
+  if (c->opt_async_upload) {
+    // the caller's buffers are free once the DMAs are done; the gathers run on, the range check of
+    // closest_refs is reported by the next evaluation (its reduction publishes the device flag)
+    CK(cudaStreamSynchronize(c->stream2));
+    c->pipe_n = nchunk;
+    c->have_static = true;
+    return 0;
+  }
+  c->pipe_n = 0;
   CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
   REQUIRE(*c->h_err != 3, "panel exchange timed out: a rank did not reach the same mcq_ctx_upload_static");
@@ -593,7 +641,12 @@ extern "C" int mcq_ctx_set_params(mcq_ctx *c, const mcq_params *p) {
   CK(cudaSetDevice(c->d.device));
   const size_t S = c->d.num_sites, H = c->d.num_hla_types;
   c->m.mu = p->mu; c->m.kappa = p->kappa; c->m.phi = p->phi;
-  CK(cudaStreamSynchronize(c->stream));     // the staging block may still feed an earlier copy
+  // With an asynchronous upload in flight the main stream is busy gathering: the parameters then travel on
+  // the copy stream and the pipelined evaluation waits for ev_params.
+  cudaStream_t pst = c->pipe_n > 0 ? c->stream2 : c->stream;
+  c->params_on_copy_stream = c->pipe_n > 0;
+  if (c->pipe_n > 0) CK(cudaStreamSynchronize(c->stream2));
+  else CK(cudaStreamSynchronize(c->stream));     // the staging block may still feed an earlier copy
   double *h = c->h_pblock;
   double *h_prior = h, *h_R = h_prior + 64, *h_omega = h_R + S, *h_rev = h_omega + S, *h_esc = h_rev + S,
          *h_rate = h_esc + H * S;
@@ -608,10 +661,10 @@ extern "C" int mcq_ctx_set_params(mcq_ctx *c, const mcq_params *p) {
       for (size_t s = 0; s < S; s++) h_rate[s * 64 + cd] = src[s];
     }
   if (p->prior_C2 && p->R && p->omega && p->HLA_select_rev && p->HLA_select_esc && p->rate_out_of_codons) {
-    CK(cudaMemcpyAsync(c->pblock, h, c->pblock_n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->pblock, h, c->pblock_n * sizeof(double), cudaMemcpyHostToDevice, pst));
   } else {                        // only what was given
     auto put = [&](double *dst, const double *src, size_t n) {
-      return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+      return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, pst);
     };
     if (p->prior_C2) CK(put(c->m.prior, h_prior, 64));
     if (p->R) CK(put(c->m.R, h_R, S));
@@ -621,6 +674,10 @@ extern "C" int mcq_ctx_set_params(mcq_ctx *c, const mcq_params *p) {
     if (p->rate_out_of_codons) CK(put(c->m.rate_out, h_rate, 64 * S));
   }
   // no host wait: the copy is ordered before every later kernel on the context's stream
+  if (c->params_on_copy_stream) {
+    CK(cudaEventRecord(c->ev_params, c->stream2));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_params, 0));      // everything later on the main stream sees them too
+  }
   c->have_params = true;
   c->has_pending = false;
   return 0;
@@ -688,7 +745,7 @@ enum FwdMode {
 
 static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int start, int end, FwdMode mode, int llk_mode,
                        double *llk_out, int r_site, double r_value, bool sparse, int hla, bool lazy = false,
-                       bool mark_end = false) {
+                       bool mark_end = false, int *tuned_blocks = nullptr) {
   FwdArgs a;
   a.st = make_static(c);
   a.em.tab = tab; a.em.ec = ec; a.R = c->m.R; a.r_site = r_site; a.r_value = r_value;
@@ -704,14 +761,15 @@ static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int star
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
   a.logBIG = c->logBIG;
   KScope ks(c, MCQ_K_FORWARD);
-  CK(mcq_launch_forward(a, c->stream));
+  if (tuned_blocks != nullptr) CK(mcq_tune_forward(a, c->stream, tuned_blocks, nullptr));
+  else CK(mcq_launch_forward(a, c->stream));
   return 0;
 }
 
 // lazy: every query continues from its own bv mark down to column `bottom`; otherwise the reference's
 // update_B(update) down to column 0
 static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream_t stream = nullptr,
-                        bool lazy = false, int bottom = 0) {
+                        bool lazy = false, int bottom = 0, int *tuned_blocks = nullptr) {
   if (stream == nullptr) stream = c->stream;
   BwdArgs a;
   a.st = make_static(c);
@@ -725,18 +783,19 @@ static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream
     return 0;
   }
   KScope ks(c, MCQ_K_BACKWARD);
-  CK(mcq_launch_backward(a, c->stream));
+  if (tuned_blocks != nullptr) CK(mcq_tune_backward(a, c->stream, tuned_blocks, nullptr));
+  else CK(mcq_launch_backward(a, c->stream));
   return 0;
 }
 
 // Wait for the reduction kernel to publish evaluation `want` in the host-mapped slot.  The stream is
 // queried now and then so that a failed launch cannot leave the host spinning.
-static int wait_slot(mcq_ctx *c, unsigned long long want) {
+static int wait_slot(mcq_ctx *c, unsigned long long want, cudaStream_t st) {
   volatile unsigned long long *seq = &c->h_slot->seq;
   for (unsigned spins = 1; *seq != want; spins++) {
     __builtin_ia32_pause();
     if ((spins & 0x3FFF) == 0) {
-      const cudaError_t e = cudaStreamQuery(c->stream);
+      const cudaError_t e = cudaStreamQuery(st);
       if (e == cudaSuccess) {
         if (*seq == want) break;
         return mcq_fail(__FILE__, __LINE__, "the reduction kernel finished without publishing its result");
@@ -749,33 +808,48 @@ static int wait_slot(mcq_ctx *c, unsigned long long want) {
 }
 
 // total over the shard (+ all ranks), brought to the host
-static int reduce_llk(mcq_ctx *c, const double *per_query, double *out) {
+// what the device error flag said when the reduction published its result
+static int slot_error(mcq_ctx *c) {
+  switch (c->h_slot->err) {
+    case 0: return 0;
+    case 1: return mcq_fail(__FILE__, __LINE__, "peer exchange timed out: a rank did not reach the same evaluation");
+    case 2: return mcq_fail(__FILE__, __LINE__, "closest_refs entry out of range (found by the last mcq_ctx_upload_static)");
+    case 3: return mcq_fail(__FILE__, __LINE__, "panel exchange timed out: a rank did not reach the same mcq_ctx_upload_static");
+    default: return mcq_fail(__FILE__, __LINE__, "device error flag set");
+  }
+}
+
+static int reduce_llk(mcq_ctx *c, const double *per_query, double *out, cudaStream_t st = nullptr) {
+  if (st == nullptr) st = c->stream;
   const unsigned long long want = ++c->eval_seq;
   if (c->have_peers) {
     // shard total + NVLink mailbox exchange in one kernel
     {
       KScope ks(c, MCQ_K_SUM);
       c->step++;
-      CK(mcq_launch_sum_exchange(per_query, c->d.num_query, c->d_sum, &c->box, c->step, c->d_err, c->d_slot, want, c->stream));
+      CK(mcq_launch_sum_exchange(per_query, c->d.num_query, c->d_sum, &c->box, c->step, c->d_err, c->d_slot, want, st));
     }
-    if (wait_slot(c, want)) return 1;
-    REQUIRE(c->h_slot->err == 0, "peer exchange timed out: a rank did not reach the same evaluation");
+    if (wait_slot(c, want, st)) return 1;
+    if (slot_error(c)) return 1;
     if (out) *out = c->h_slot->value;
     return 0;
   }
   {
     KScope ks(c, MCQ_K_SUM);
-    CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->comm ? nullptr : c->d_slot, want, c->stream));
+    CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->comm ? nullptr : c->d_slot, want, c->d_err, st));
   }
   if (c->comm) {
-    int r = g_nccl.AllReduce(c->d_sum, c->d_sum, 1, kNcclDouble, kNcclSum, c->comm, c->stream);
+    int r = g_nccl.AllReduce(c->d_sum, c->d_sum, 1, kNcclDouble, kNcclSum, c->comm, st);
     if (r != 0) return mcq_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce failed");
-    CK(cudaMemcpyAsync(c->h_sum, c->d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(c->h_sum, c->d_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    REQUIRE(*c->h_err == 0, "device error flag set (closest_refs out of range in the last mcq_ctx_upload_static?)");
     if (out) *out = *c->h_sum;
     return 0;
   }
-  if (wait_slot(c, want)) return 1;
+  if (wait_slot(c, want, st)) return 1;
+  if (slot_error(c)) return 1;
   if (out) *out = c->h_slot->value;
   return 0;
 }
@@ -844,9 +918,77 @@ extern "C" int mcq_ctx_emission(mcq_ctx *c, int start, int end, int which_hla, i
   return 0;
 }
 
+// The evaluation behind an asynchronous upload: chunk k of the queries is evaluated on stream3 as soon as its
+// gather has finished on the main stream (ev_ready[k]), so the sweep of chunk k runs under the gather of chunk
+// k+1 and the transfers behind it.  Same kernels on views of the per-query arrays that start at the chunk.
+static int full_llk_pipelined(mcq_ctx *c, int with_emission, double *llk) {
+  const int S = c->d.num_sites, H = c->d.num_hla_types, Ls = c->Ls;
+  // kPipeStreams streams in turn: a chunk of queries alone leaves the SMs short of warps, several in flight do not
+  cudaStream_t st = c->stream3;
+  CK(cudaStreamWaitEvent(st, c->ev_static, 0));          // the small static tables of this upload
+  if (c->params_on_copy_stream) CK(cudaStreamWaitEvent(st, c->ev_params, 0));
+  McqOverride none{}; none.kind = -1;
+  const McqStatic all = make_static(c);
+  if (with_emission) {       // the shared rows once, the per-query consensus values chunk by chunk below
+    EmisArgs e;
+    e.st = all; e.m = c->m; e.ov = none; e.start = 0; e.end = S - 1; e.which_hla = -1;
+    e.a0 = c->aoff_h[0]; e.a1 = c->aoff_h[S];
+    e.tab_src = e.tab_dst = c->tab; e.atab_src = e.atab_dst = c->atab; e.ec_src = e.ec_dst = c->ec; e.ac_src = e.ac_dst = c->ac;
+    c->launches++; c->k_n[MCQ_K_EMISSION]++;
+    CK(mcq_launch_emission_table(e, st));
+  }
+  CK(cudaEventRecord(c->ev_ps[0], c->stream3));          // the other streams start behind the shared rows
+  for (int i = 0; i < kPipeStreams - 1; i++) CK(cudaStreamWaitEvent(c->pipe_st[i], c->ev_ps[0], 0));
+  for (int k = 0; k < c->pipe_n; k++) {
+    const size_t q0 = (size_t)c->pipe_q[k], nq = (size_t)c->pipe_q[k + 1] - q0;
+    st = (k % kPipeStreams) ? c->pipe_st[k % kPipeStreams - 1] : c->stream3;
+    CK(cudaStreamWaitEvent(st, c->ev_ready[k], 0));
+    McqStatic v = all;       // the chunk's view
+    v.Q = (int)nq;
+    v.G = all.G + q0 * S * c->Lg; v.rowdesc = all.rowdesc + q0 * S;
+    v.query_codon = all.query_codon + q0 * S; v.hla = all.hla + q0 * H;
+    if (with_emission) {
+      EmisArgs e;
+      e.st = v; e.m = c->m; e.ov = none; e.start = 0; e.end = S - 1; e.which_hla = -1;
+      e.a0 = c->aoff_h[0]; e.a1 = c->aoff_h[S];
+      e.tab_src = e.tab_dst = c->tab; e.atab_src = e.atab_dst = c->atab;
+      e.ec_src = e.ec_dst = c->ec + q0 * S; e.ac_src = e.ac_dst = c->ac + q0 * S;
+      c->launches++; c->k_n[MCQ_K_EMISSION]++;
+      CK(mcq_launch_emission_cons(e, st));
+    }
+    FwdArgs a;
+    a.st = v;
+    a.em.tab = c->tab; a.em.ec = c->ec + q0 * S; a.em_pre = a.em; a.R = c->m.R; a.r_site = -1; a.r_value = 0.0;
+    a.fv = nullptr; a.mark_fv = c->fv + q0;
+    a.Fin = c->F + q0 * S * Ls; a.Fout = c->T + q0 * S * Ls; a.sel = c->sel + q0 * S;
+    a.Fn_in = c->Fn + q0 * S; a.Fn_out = c->Fn + q0 * S;
+    a.in_place = 1; a.no_store = 0; a.start = 0; a.end = S - 1; a.llk_mode = 2;
+    a.B = c->B + q0 * S * Ls; a.Bn = c->Bn + q0 * S; a.llk_out = c->llk_cur + q0; a.llk_keep = c->llk_cur + q0;
+    a.active = nullptr; a.active_hla = 0; a.logBIG = c->logBIG;
+    c->launches++; c->k_n[MCQ_K_FORWARD]++;
+    CK(mcq_launch_forward(a, st));
+  }
+  for (int &m : c->fv_h) m = S - 1;
+  c->pipe_n = 0;
+  c->params_on_copy_stream = false;
+  st = c->stream3;
+  for (int i = 0; i < kPipeStreams - 1; i++) {
+    CK(cudaEventRecord(c->ev_ps[i], c->pipe_st[i]));
+    CK(cudaStreamWaitEvent(st, c->ev_ps[i], 0));
+  }
+  if (reduce_llk(c, c->llk_cur, llk, st)) return 1;      // (waits for the result: everything above is done)
+  CK(cudaEventRecord(c->ev_pipe, st));
+  CK(cudaStreamWaitEvent(c->stream, c->ev_pipe, 0));
+  c->has_pending = false;
+  c->have_fwd = true;
+  return 0;
+}
+
 extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
   READY(c);
   CallScope scope(c);
+  if (c->pipe_n > 0 && (c->timing == 0 || c->timing == 3)) return full_llk_pipelined(c, with_emission, llk);
+  c->pipe_n = 0;
   const int S = c->d.num_sites;
   McqOverride none{}; none.kind = -1;
   if (with_emission && run_emission(c, 0, S - 1, -1, 2, none, cur_set(c), cur_set(c))) return 1;
@@ -859,6 +1001,7 @@ extern "C" int mcq_ctx_full_llk(mcq_ctx *c, int with_emission, double *llk) {
 
 extern "C" int mcq_ctx_llk_only(mcq_ctx *c, int with_emission, double *llk) {
   READY(c);
+  c->pipe_n = 0;             // (everything here runs on the main stream, behind an asynchronous upload's set-up)
   CallScope scope(c);
   const int S = c->d.num_sites;
   McqOverride none{}; none.kind = -1;
@@ -869,6 +1012,23 @@ extern "C" int mcq_ctx_llk_only(mcq_ctx *c, int with_emission, double *llk) {
   if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_NO_STORE, 2, c->llk_cur, -1, 0.0, false, 0)) return 1;
   if (reduce_llk(c, c->llk_cur, llk)) return 1;
   c->has_pending = false;
+  return 0;
+}
+
+extern "C" int mcq_ctx_tune(mcq_ctx *c, int blocks_per_sm[3]) {
+  READY(c);
+  REQUIRE(c->have_state, "mcq_ctx_init_state has not been called");
+  c->pipe_n = 0;
+  CallScope scope(c);
+  if (flush_lazy(c)) return 1;            // the sweeps below recompute what is current: same inputs, same outputs
+  const int S = c->d.num_sites;
+  int k[3] = {0, 0, 0};
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_IN_PLACE, 2, c->llk_cur, -1, 0.0, false, 0, false, true, &k[0])) return 1;
+  if (run_forward(c, c->tab, c->ec, 0, S - 1, FWD_NO_STORE, 2, c->llk_prop, -1, 0.0, false, 0, false, false, &k[1])) return 1;
+  if (run_backward(c, S - 1, false, 0, nullptr, false, 0, &k[2])) return 1;
+  CK(cudaStreamSynchronize(c->stream));
+  c->has_pending = false;
+  if (blocks_per_sm) for (int i = 0; i < 3; i++) blocks_per_sm[i] = k[i];
   return 0;
 }
 
@@ -884,6 +1044,7 @@ extern "C" int mcq_ctx_backward_fill(mcq_ctx *c) {
 
 extern "C" int mcq_ctx_init_state(mcq_ctx *c, double *llk) {
   READY(c);
+  c->pipe_n = 0;
   CallScope scope(c);
   const int S = c->d.num_sites;
   McqOverride none{}; none.kind = -1;

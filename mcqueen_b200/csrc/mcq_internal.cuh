@@ -149,6 +149,10 @@ cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int *closest, const 
 cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, int q0, int nq, cudaStream_t stream);
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
+// time the launch at every residency (blocks per SM) the kernel allows and keep the fastest for launches of
+// this kernel with this many queries; the launch itself must be repeatable (same inputs, same outputs)
+cudaError_t mcq_tune_forward(const FwdArgs &a, cudaStream_t stream, int *best_blocks, float *best_ms);
+cudaError_t mcq_tune_backward(const BwdArgs &a, cudaStream_t stream, int *best_blocks, float *best_ms);
 cudaError_t mcq_launch_dot(const DotArgs &a, cudaStream_t stream);
 // fv[q] := f, bv[q] := b for the queries selected by (active, hla) (all when active == nullptr); a
 // negative value leaves that array untouched
@@ -175,8 +179,9 @@ struct McqHostSlot {
   int err;
 };
 // hs: device view of the slot (nullptr = none), seq: the number to publish
+// err: device error flag copied into the slot with the result (nullptr: none)
 cudaError_t mcq_launch_sum(const double *v, int n, double *out, McqHostSlot *hs, unsigned long long seq,
-                           cudaStream_t stream);
+                           const int *err, cudaStream_t stream);
 // barrier over the attached ranks (monotone `count`); err: device flag, 3 = a peer never arrived
 cudaError_t mcq_launch_peer_barrier(const void *box, unsigned long long count, int *err, cudaStream_t stream);
 // `box` points at a host copy of the PeerBox struct of mcq_kernels.cu (16 value + 16 seq + 16 bar pointers, nranks, rank)

@@ -13,6 +13,8 @@
 // without FMA contraction (its Makefile:22 gives -O3 only), and with contraction off the emission
 // rows are bit-identical to the reference's and a cell update differs from it only through the
 // order of the per-site sum over copy states (a warp butterfly here, ascending r there).
+#include <mutex>
+#include <unordered_map>
 #include "mcq_internal.cuh"
 #include "../../include/mcq_b200.h"
 
@@ -616,8 +618,10 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
   }
 }
 
+// (at most 120 registers: 17 one-warp blocks per SM - NJ = 8 without catch-up misses that by two registers
+// otherwise; NJ = 16 is exempt)
 template <int NJ, bool FULL, bool PRE, bool STORE>
-__global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
+__global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE) ? 120 : 255) k_forward(const FwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
   __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -773,40 +777,136 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_forward(const FwdArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Resident blocks per SM of the sweep kernels.  Every block lives for the whole sweep of its query, so how
+// many queries are in flight decides both how the last wave of a launch fills and how many write streams
+// the HBM sees at once; the best number depends on the kernel and on the number of queries (measured at
+// C4: 17 per SM for 10 000 queries, 12 for 5 000, 10 for 2 500).  mcq_tune_* time the candidates once and
+// record the winner per (kernel, grid size); launches look it up and lower the residency with unused
+// dynamic shared memory.  Untuned launches run at the hardware maximum.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Residency {
+  std::mutex mu;
+  std::unordered_map<const void *, int> maxb;                       // hardware maximum per kernel
+  std::unordered_map<const void *, std::unordered_map<int, int>> pad;   // kernel -> blocks -> bytes
+  std::unordered_map<const void *, std::unordered_map<unsigned, int>> tuned;   // kernel -> grid -> blocks
+} g_res;
+
+int max_blocks(const void *func) {           // (g_res.mu held)
+  auto it = g_res.maxb.find(func);
+  if (it != g_res.maxb.end()) return it->second;
+  int b = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, func, 32 * MCQ_WPB, 0) != cudaSuccess) b = 0;
+  g_res.maxb[func] = b;
+  return b;
+}
+
+// smallest dynamic shared memory request that leaves at most `blocks` blocks resident (g_res.mu held)
+int pad_for(const void *func, int blocks) {
+  if (blocks <= 0 || blocks >= max_blocks(func)) return 0;
+  auto &m = g_res.pad[func];
+  auto it = m.find(blocks);
+  if (it != m.end()) return it->second;
+  int lo = 0, hi = 46 * 1024;
+  while (lo < hi) {
+    const int mid = (lo + hi) / 2;
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, func, 32 * MCQ_WPB, (size_t)mid) != cudaSuccess) return 0;
+    if (b <= blocks) hi = mid;
+    else lo = mid + 1;
+  }
+  m[blocks] = lo;
+  return lo;
+}
+
+int residency_smem(const void *func, unsigned grid) {
+  std::lock_guard<std::mutex> lock(g_res.mu);
+  auto k = g_res.tuned.find(func);
+  if (k == g_res.tuned.end()) return 0;
+  auto g = k->second.find(grid);
+  return g == k->second.end() ? 0 : pad_for(func, g->second);
+}
+
+// times `launch` (twice per candidate, the second run counts) for every residency from the maximum down to
+// 9 blocks per SM and records the fastest for this grid size
+template <typename Launch>
+cudaError_t tune_residency(const void *func, unsigned grid, cudaStream_t stream, Launch launch, int *best_blocks,
+                           float *best_ms) {
+  int maxb;
+  { std::lock_guard<std::mutex> lock(g_res.mu); maxb = max_blocks(func); }
+  cudaEvent_t e0, e1;
+  cudaError_t err = cudaEventCreate(&e0);
+  if (err != cudaSuccess) return err;
+  err = cudaEventCreate(&e1);
+  if (err != cudaSuccess) return err;
+  int best = maxb;
+  float best_t = 1e30f;
+  for (int k = maxb; k >= 9 && k >= maxb - 8; k--) {
+    int smem;
+    { std::lock_guard<std::mutex> lock(g_res.mu); smem = pad_for(func, k); }
+    float t = 0.f;
+    for (int rep = 0; rep < 2; rep++) {
+      cudaEventRecord(e0, stream);
+      launch(smem);
+      cudaEventRecord(e1, stream);
+      err = cudaEventSynchronize(e1);
+      if (err != cudaSuccess) return err;
+      cudaEventElapsedTime(&t, e0, e1);
+    }
+    if (t < best_t) { best_t = t; best = k; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  { std::lock_guard<std::mutex> lock(g_res.mu); g_res.tuned[func][grid] = best; }
+  if (best_blocks) *best_blocks = best;
+  if (best_ms) *best_ms = best_t;
+  return cudaGetLastError();
+}
+}  // namespace
+
 template <int NJ, bool STORE>
-static cudaError_t launch_forward_nj(const FwdArgs &a, cudaStream_t stream) {
+static cudaError_t launch_forward_nj(const FwdArgs &a, cudaStream_t stream, bool tune, int *best_blocks, float *best_ms) {
   const unsigned blocks = (unsigned)((a.st.Q + MCQ_WPB - 1) / MCQ_WPB);
   const bool full = a.st.Ls == 64 * NJ;
-  if (a.fv != nullptr) {
-    if (full) k_forward<NJ, true, true, STORE><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
-    else k_forward<NJ, false, true, STORE><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
-  } else {
-    if (full) k_forward<NJ, true, false, STORE><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
-    else k_forward<NJ, false, false, STORE><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
-  }
+  void (*kernel)(const FwdArgs);
+  if (a.fv != nullptr) kernel = full ? k_forward<NJ, true, true, STORE> : k_forward<NJ, false, true, STORE>;
+  else kernel = full ? k_forward<NJ, true, false, STORE> : k_forward<NJ, false, false, STORE>;
+  if (tune)
+    return tune_residency((const void *)kernel, blocks, stream,
+                          [&](int smem) { kernel<<<blocks, 32 * MCQ_WPB, smem, stream>>>(a); }, best_blocks, best_ms);
+  kernel<<<blocks, 32 * MCQ_WPB, residency_smem((const void *)kernel, blocks), stream>>>(a);
   return cudaGetLastError();
 }
 
-cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
+static cudaError_t dispatch_forward(const FwdArgs &a, cudaStream_t stream, bool tune, int *best_blocks, float *best_ms) {
   if (a.no_store) {                 // likelihood only: no column is written
     if (a.fv != nullptr || a.start != 0) return cudaErrorInvalidValue;
     switch (a.st.Lg / 64) {
-      case 1: return launch_forward_nj<1, false>(a, stream);
-      case 2: return launch_forward_nj<2, false>(a, stream);
-      case 4: return launch_forward_nj<4, false>(a, stream);
-      case 8: return launch_forward_nj<8, false>(a, stream);
-      case 16: return launch_forward_nj<16, false>(a, stream);
+      case 1: return launch_forward_nj<1, false>(a, stream, tune, best_blocks, best_ms);
+      case 2: return launch_forward_nj<2, false>(a, stream, tune, best_blocks, best_ms);
+      case 4: return launch_forward_nj<4, false>(a, stream, tune, best_blocks, best_ms);
+      case 8: return launch_forward_nj<8, false>(a, stream, tune, best_blocks, best_ms);
+      case 16: return launch_forward_nj<16, false>(a, stream, tune, best_blocks, best_ms);
       default: return cudaErrorInvalidValue;
     }
   }
   switch (a.st.Lg / 64) {
-    case 1: return launch_forward_nj<1, true>(a, stream);
-    case 2: return launch_forward_nj<2, true>(a, stream);
-    case 4: return launch_forward_nj<4, true>(a, stream);
-    case 8: return launch_forward_nj<8, true>(a, stream);
-    case 16: return launch_forward_nj<16, true>(a, stream);
+    case 1: return launch_forward_nj<1, true>(a, stream, tune, best_blocks, best_ms);
+    case 2: return launch_forward_nj<2, true>(a, stream, tune, best_blocks, best_ms);
+    case 4: return launch_forward_nj<4, true>(a, stream, tune, best_blocks, best_ms);
+    case 8: return launch_forward_nj<8, true>(a, stream, tune, best_blocks, best_ms);
+    case 16: return launch_forward_nj<16, true>(a, stream, tune, best_blocks, best_ms);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t mcq_tune_forward(const FwdArgs &a, cudaStream_t stream, int *best_blocks, float *best_ms) {
+  return dispatch_forward(a, stream, true, best_blocks, best_ms);
+}
+
+cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream) {
+  return dispatch_forward(a, stream, false, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1021,22 +1121,33 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
 }
 
 template <int NJ>
-static cudaError_t launch_backward_nj(const BwdArgs &a, cudaStream_t stream) {
+static cudaError_t launch_backward_nj(const BwdArgs &a, cudaStream_t stream, bool tune, int *best_blocks, float *best_ms) {
   const unsigned blocks = (unsigned)((a.st.Q + MCQ_WPB - 1) / MCQ_WPB);
-  if (a.st.Ls == 64 * NJ) k_backward<NJ, true><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
-  else k_backward<NJ, false><<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+  void (*kernel)(const BwdArgs) = (a.st.Ls == 64 * NJ) ? k_backward<NJ, true> : k_backward<NJ, false>;
+  if (tune)
+    return tune_residency((const void *)kernel, blocks, stream,
+                          [&](int smem) { kernel<<<blocks, 32 * MCQ_WPB, smem, stream>>>(a); }, best_blocks, best_ms);
+  kernel<<<blocks, 32 * MCQ_WPB, residency_smem((const void *)kernel, blocks), stream>>>(a);
   return cudaGetLastError();
 }
 
-cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream) {
+static cudaError_t dispatch_backward(const BwdArgs &a, cudaStream_t stream, bool tune, int *best_blocks, float *best_ms) {
   switch (a.st.Lg / 64) {
-    case 1: return launch_backward_nj<1>(a, stream);
-    case 2: return launch_backward_nj<2>(a, stream);
-    case 4: return launch_backward_nj<4>(a, stream);
-    case 8: return launch_backward_nj<8>(a, stream);
-    case 16: return launch_backward_nj<16>(a, stream);
+    case 1: return launch_backward_nj<1>(a, stream, tune, best_blocks, best_ms);
+    case 2: return launch_backward_nj<2>(a, stream, tune, best_blocks, best_ms);
+    case 4: return launch_backward_nj<4>(a, stream, tune, best_blocks, best_ms);
+    case 8: return launch_backward_nj<8>(a, stream, tune, best_blocks, best_ms);
+    case 16: return launch_backward_nj<16>(a, stream, tune, best_blocks, best_ms);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream) {
+  return dispatch_backward(a, stream, false, nullptr, nullptr);
+}
+
+cudaError_t mcq_tune_backward(const BwdArgs &a, cudaStream_t stream, int *best_blocks, float *best_ms) {
+  return dispatch_backward(a, stream, true, best_blocks, best_ms);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1192,15 +1303,18 @@ cudaError_t mcq_launch_commit_params(const McqStatic &st, McqModel m, McqOverrid
 // ------------------------------------------------------------------------------------------
 // the total also goes straight to a host-mapped slot, followed by the evaluation number: the host spins on
 // the number instead of paying for a copy and a stream synchronisation
-__device__ __forceinline__ void publish_to_host(McqHostSlot *hs, double total, unsigned long long seq) {
+__device__ __forceinline__ void publish_to_host(McqHostSlot *hs, double total, unsigned long long seq,
+                                                const int *err = nullptr) {
   if (hs == nullptr) return;
+  // the device error flag of the work before this reduction (range check of an asynchronous upload, ...)
+  if (err != nullptr) *reinterpret_cast<volatile int *>(&hs->err) = *reinterpret_cast<const volatile int *>(err);
   *reinterpret_cast<volatile double *>(&hs->value) = total;
   __threadfence_system();
   *reinterpret_cast<volatile unsigned long long *>(&hs->seq) = seq;
 }
 
 __global__ void __launch_bounds__(1024) k_sum(const double *__restrict__ v, int n, double *__restrict__ out,
-                                              McqHostSlot *hs, unsigned long long seq) {
+                                              McqHostSlot *hs, unsigned long long seq, const int *err) {
   __shared__ double sh[1024];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += 1024) acc += v[i];
@@ -1212,7 +1326,7 @@ __global__ void __launch_bounds__(1024) k_sum(const double *__restrict__ v, int 
   }
   if (threadIdx.x == 0) {
     *out = sh[0];
-    publish_to_host(hs, sh[0], seq);
+    publish_to_host(hs, sh[0], seq, err);
   }
 }
 
@@ -1301,7 +1415,7 @@ __global__ void __launch_bounds__(1024) k_sum_exchange(const double *__restrict_
   for (int r = 0; r < R; r++) total += __shfl_sync(0xffffffffu, got, r);   // rank order on every rank
   if (lane == 0) {
     *out = total;
-    publish_to_host(hs, total, seq);
+    publish_to_host(hs, total, seq, err);
   }
 }
 
@@ -1312,7 +1426,7 @@ cudaError_t mcq_launch_sum_exchange(const double *v, int n, double *out, const v
 }
 
 cudaError_t mcq_launch_sum(const double *v, int n, double *out, McqHostSlot *hs, unsigned long long seq,
-                           cudaStream_t stream) {
-  k_sum<<<1, 1024, 0, stream>>>(v, n, out, hs, seq);
+                           const int *err, cudaStream_t stream) {
+  k_sum<<<1, 1024, 0, stream>>>(v, n, out, hs, seq, err);
   return cudaGetLastError();
 }

@@ -330,6 +330,48 @@ def test_reupload_invalidates_the_state(api):
     ctx.close()
 
 
+@pytest.mark.parametrize("name,over", [("toy", {}), ("toy", dict(L=200, N=260, S=40, Q=70)), ("C2", dict(Q=64))])
+def test_async_upload_pipelined_evaluation(api, name, over):
+    """MCQ_OPT_ASYNC_UPLOAD: the upload returns after the DMAs, the next full evaluation runs chunk by chunk
+    behind the device-side set-up.  Same bits as the synchronous path, repeatedly (the bench's e2e loop), a state
+    can be built on it, and a bad closest_refs entry is reported by the evaluation."""
+    p = make_problem(name, **over)
+    ctx = api.Context.from_problem(p)
+    want = ctx.full_llk(True)
+    per_q = ctx.query_llk().copy()
+    up = (p.ref_triplets, p.closest_refs, p.cons_query_nucls, p.query_codons, p.hla, p.consensus_codons,
+          p.n_site_codons, p.site_codons)
+    prm = dict(mu=p.mu, kappa=p.kappa, phi=p.phi, prior=p.prior, R=p.R, omega=p.omega,
+               rate_out=p.rate_out_of_codons(), esc=p.esc, rev=p.rev[0])
+    ctx.set_option(api.OPT_ASYNC_UPLOAD, 1)
+    for _ in range(3):
+        ctx.upload_static(*up)
+        ctx.set_params(**prm)
+        assert ctx.full_llk(True) == want
+        assert np.array_equal(ctx.query_llk(), per_q)
+    ctx.backward_fill()                       # full_llk + backward_fill = a state
+    cpu = CpuState(checker(), p)
+    assert_state_matches(ctx, cpu, [0, p.Q - 1])
+    mv = dict(kind=REV, start=3, end=min(p.S - 1, 20), value0=1.2)
+    w, g = cpu.propose(**mv), ctx.propose(**mv)
+    assert abs(g - w) <= RTOL_LLK * abs(w)
+    # another evaluation path behind an asynchronous upload: everything queues on the main stream
+    ctx.upload_static(*up)
+    ctx.set_params(**prm)
+    assert abs(ctx.init_state() - want) <= 1e-15 * abs(want)
+    bad = p.closest_refs.copy()
+    bad[p.Q // 2, 1] = p.N
+    ctx.upload_static(up[0], bad, *up[2:])
+    ctx.set_params(**prm)
+    with pytest.raises(api._lib.McqError, match="closest_refs"):
+        ctx.full_llk(True)
+    ctx.set_option(api.OPT_ASYNC_UPLOAD, 0)
+    ctx.upload_static(*up)
+    ctx.set_params(**prm)
+    assert ctx.full_llk(True) == want
+    ctx.close()
+
+
 def test_errors_are_loud(api):
     with pytest.raises(api._lib.McqError):
         api.Context(10, 2000, 100, 5, 1)          # closest_n > 1024
