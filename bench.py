@@ -340,6 +340,8 @@ def main():
             dist.barrier()
 
     llk0 = ctx.init_state()
+    tuned = ctx.tune()        # one-off: resident blocks per SM of the sweep kernels for this shard size
+    config["resident_blocks_per_sm"] = dict(zip(["forward", "forward_llk_only", "backward"], tuned))
     for _ in range(args.warmup):
         ctx.full_llk(True)
 

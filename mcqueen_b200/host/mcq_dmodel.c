@@ -666,6 +666,7 @@ int main(int argc, char **argv)
   if(!c.sample_prior) {
     CHECK(mcq_ctx_init_state(c.ctx, &c.llk));
     printf("Total log-likelihood using initialise F: %f.\n", c.llk);
+    CHECK(mcq_ctx_tune(c.ctx, NULL));   /* residency of the sweep kernels for this shard size */
     if(world > 1) {
       /* the first exchange has completed on every rank, so every rank has read every hand-over file */
       char mine[PATH_MAX];

@@ -372,6 +372,27 @@ def test_async_upload_pipelined_evaluation(api, name, over):
     ctx.close()
 
 
+def test_tune_leaves_state_and_results_unchanged(api):
+    """mcq_ctx_tune only changes how many blocks of the sweep kernels are resident: same bits before and after,
+    also for owed refills pending at the time of the call."""
+    p = make_problem("toy", L=200, N=260, S=40, Q=70)
+    cpu = CpuState(checker(), p)
+    ctx = api.Context.from_problem(p)
+    llk = ctx.init_state()
+    mv = dict(kind=REV, start=5, end=20, value0=1.3)
+    cpu.propose(**mv); cpu.accept()
+    v = ctx.propose(**mv); ctx.accept()          # leaves refills owed
+    k = ctx.tune()
+    assert len(k) == 3 and all(x >= 1 for x in k)
+    assert_state_matches(ctx, cpu, [0, p.Q - 1])
+    assert ctx.full_llk(False) == ctx.llk_only(False)
+    assert abs(ctx.full_llk(False) - v) <= 1e-12 * abs(v)
+    mv2 = dict(kind=ESC, start=10, end=30, hla=1, value0=0.8)
+    w, g = cpu.propose(**mv2), ctx.propose(**mv2)
+    assert abs(g - w) <= RTOL_LLK * abs(w)
+    ctx.close()
+
+
 def test_errors_are_loud(api):
     with pytest.raises(api._lib.McqError):
         api.Context(10, 2000, 100, 5, 1)          # closest_n > 1024
