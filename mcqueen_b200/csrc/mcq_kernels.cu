@@ -618,10 +618,11 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
   }
 }
 
-// (at most 120 registers: 17 one-warp blocks per SM - NJ = 8 without catch-up misses that by two registers
-// otherwise; NJ = 16 is exempt)
+// (register caps: the stored sweep at most 120 = 17 one-warp blocks per SM, which NJ = 8 misses by two registers
+// otherwise; the likelihood-only sweep is issue-bound and wants the warps of 96; NJ = 16 and the catch-up
+// variant are exempt)
 template <int NJ, bool FULL, bool PRE, bool STORE>
-__global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE) ? 120 : 255) k_forward(const FwdArgs a) {
+__global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE) ? (STORE ? 120 : 96) : 255) k_forward(const FwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
   __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
