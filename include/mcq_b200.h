@@ -199,11 +199,14 @@ enum {
                               host and reads the rest from its peers over NVLink.  All ranks must then
                               call mcq_ctx_upload_static together and with the same panel.  0: every
                               rank uploads the whole panel itself. */
-  MCQ_OPT_ASYNC_UPLOAD = 4 /* default 0.  1: mcq_ctx_upload_static returns as soon as the caller's buffers
+  MCQ_OPT_ASYNC_UPLOAD = 4, /* default 0.  1: mcq_ctx_upload_static returns as soon as the caller's buffers
                               have been DMA'd (they may be reused); the device-side set-up runs on, chunk
                               by chunk, and the next mcq_ctx_full_llk evaluates each chunk of queries as
                               soon as it is ready, under the set-up of the next one.  A closest_refs entry
                               out of range is then reported by that evaluation, not by the upload. */
+  MCQ_OPT_UPLOAD_CHUNK_QUERIES = 5 /* default 1250: mcq_ctx_upload_static transfers and sets up the per-query
+                              data in up to 8 chunks of at least this many queries (one chunk = no
+                              pipelining; smaller chunks starve the kernels that follow them). */
 };
 int mcq_ctx_set_option(mcq_ctx *ctx, int option, int value);
 

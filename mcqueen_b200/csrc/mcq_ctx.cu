@@ -103,6 +103,7 @@ struct mcq_ctx {
   int pipe_n = 0, pipe_q[kUploadChunks + 1] = {0};
   bool params_on_copy_stream = false;
   int opt_async_upload = 0;
+  int opt_chunk_queries = 1250;   // MCQ_OPT_UPLOAD_CHUNK_QUERIES
   size_t bytes = 0;
   bool have_static = false, have_params = false, have_state = false;
   bool have_fwd = false;     // a full forward sweep has run since the last upload: with a backward fill it makes a state
@@ -438,6 +439,11 @@ extern "C" int mcq_ctx_set_option(mcq_ctx *c, int option, int value) {
   if (option == MCQ_OPT_SPARSE_ESC) { c->opt_sparse_esc = value; return 0; }
   if (option == MCQ_OPT_SHARED_PANEL) { c->opt_shared_panel = value; return 0; }
   if (option == MCQ_OPT_ASYNC_UPLOAD) { c->opt_async_upload = value; return 0; }
+  if (option == MCQ_OPT_UPLOAD_CHUNK_QUERIES) {
+    REQUIRE(value >= 1, "chunk size must be positive");
+    c->opt_chunk_queries = value;
+    return 0;
+  }
   if (option == MCQ_OPT_LAZY_REFILL) {
     if (!value && c->have_state && mcq_ctx_flush(c)) return 1;   // leave lazy mode with F and B complete
     c->opt_lazy = value;
@@ -576,7 +582,8 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     KScope ks(c, MCQ_K_GATHER);
     CK(mcq_launch_gather_prepare(c->st_trip, c->st_trip_pad, c->st_slot_of, c->st_trip_tab, S, N, c->stream));
   }
-  const int nchunk = Q < 4 * kUploadChunks ? 1 : kUploadChunks;
+  // chunks of at least opt_chunk_queries queries: smaller ones leave the kernels behind them short of warps
+  const int nchunk = std::max(1, std::min(kUploadChunks, Q / std::max(1, c->opt_chunk_queries)));
   const McqStatic st_all = make_static(c);
   for (int k = 0; k < nchunk; k++) {
     const size_t q0 = (size_t)Q * k / nchunk, q1 = (size_t)Q * (k + 1) / nchunk, nq = q1 - q0;

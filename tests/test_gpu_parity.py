@@ -344,6 +344,7 @@ def test_async_upload_pipelined_evaluation(api, name, over):
     prm = dict(mu=p.mu, kappa=p.kappa, phi=p.phi, prior=p.prior, R=p.R, omega=p.omega,
                rate_out=p.rate_out_of_codons(), esc=p.esc, rev=p.rev[0])
     ctx.set_option(api.OPT_ASYNC_UPLOAD, 1)
+    ctx.set_option(api.OPT_UPLOAD_CHUNK_QUERIES, 5)      # several chunks even at test sizes
     for _ in range(3):
         ctx.upload_static(*up)
         ctx.set_params(**prm)

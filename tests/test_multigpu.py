@@ -34,6 +34,7 @@ def _worker(rank, world, port, kind, out):
         ctx.attach_comm(world, rank, ids[0])
     # a second upload, now that the ranks know each other: with peers attached every rank DMAs one slice
     # of the reference panel and reads the other slices from its peers (MCQ_OPT_SHARED_PANEL)
+    ctx.set_option(api.OPT_UPLOAD_CHUNK_QUERIES, 4)      # several chunks even at test sizes
     for _ in range(3):
         ctx.upload_static(p.ref_triplets, p.closest_refs[q0:q1], p.cons_query_nucls[q0:q1], p.query_codons[q0:q1],
                           p.hla[q0:q1], p.consensus_codons, p.n_site_codons, p.site_codons)
