@@ -350,6 +350,12 @@ def test_async_upload_pipelined_evaluation(api, name, over):
         ctx.set_params(**prm)
         assert ctx.full_llk(True) == want
         assert np.array_equal(ctx.query_llk(), per_q)
+    ctx.set_option(api.OPT_UPLOAD_CHUNK_QUERIES, 1250)   # the default: one chunk at this size, no pipelining
+    ctx.upload_static(*up)
+    ctx.set_params(**prm)
+    assert ctx.full_llk(True) == want
+    assert np.array_equal(ctx.query_llk(), per_q)
+    ctx.set_option(api.OPT_UPLOAD_CHUNK_QUERIES, 5)
     ctx.backward_fill()                       # full_llk + backward_fill = a state
     cpu = CpuState(checker(), p)
     assert_state_matches(ctx, cpu, [0, p.Q - 1])
