@@ -112,10 +112,12 @@ __global__ void __launch_bounds__(256) k_pad_rows(const int8_t *__restrict__ src
   }
 }
 
-// One block per (query, 32 sites).  A thread owns FOUR consecutive physical positions of the G rows (= four
-// copy states): it fetches the 32 triplets each of its references shows at the block's sites (one aligned
-// sector per reference, two 16-byte loads), turns each into the site's slot through the table in shared
-// memory and stores one 32-bit word per site - a warp writes 128 contiguous bytes of a G row per store.
+// One block per (query, 32 sites).  A PAIR of lanes owns eight consecutive physical positions of the G rows (=
+// eight copy states): the even lane takes the block's first 16 sites, the odd lane the other 16, so the two
+// 16-byte loads of a pair fall into one aligned 32-byte sector of the reference's (re-pitched) row and a warp
+// instruction touches 16 sectors, not 32 - the kernel is bound by the L1 tag stage.  Each triplet becomes the
+// site's slot through the table in shared memory; per site a lane stores its 8 bytes, the even (odd) lanes of a
+// warp together 128 contiguous bytes of one G row.
 __global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ trip_pad, int Sp,
                                                    const int *__restrict__ closest,
                                                    const int8_t *__restrict__ cons_nucls,
@@ -130,53 +132,57 @@ __global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ tr
   for (int i = threadIdx.x; i < 256; i += blockDim.x)
     reinterpret_cast<uint4 *>(s_tab)[i] = reinterpret_cast<const uint4 *>(trip_tab + (size_t)s0 * 128)[i];
   __syncthreads();
-  const int pos = 4 * threadIdx.x;
+  const int pos = 8 * (threadIdx.x >> 1), sb = 16 * (threadIdx.x & 1);   // first position, first site
   if (pos >= Lg) return;
-  // the four references; padding states (r >= L) read row 0 and are overwritten with MCQ_NOSLOT below
-  unsigned w[4][8];
-  unsigned padmask = 0;                             // byte k = 0xFF when position pos + k is padding
-  size_t roff[4];
+  // the eight references; padding states (r >= L) read row 0 and are overwritten with MCQ_NOSLOT below
+  unsigned w[8][4];
+  unsigned pad0 = 0, pad1 = 0;                      // byte k = 0xFF when position pos + k (+4) is padding
+  int refs[8];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < 8; k++) {
     const int r = g_state_of(pos + k, lg2);
     int ref = 0;
     if (r < L) {
       ref = closest[(size_t)q * L + r];
       if ((unsigned)ref >= (unsigned)N) { ref = 0; *err = 2; }   // reported by mcq_ctx_upload_static
-    } else padmask |= 0xFFu << (8 * k);
-    roff[k] = (size_t)ref * Sp + s0;
-    const uint4 *src = reinterpret_cast<const uint4 *>(trip_pad + roff[k]);
-    const uint4 a = src[0], b = src[1];
+    } else if (k < 4) pad0 |= 0xFFu << (8 * k);
+    else pad1 |= 0xFFu << (8 * (k - 4));
+    refs[k] = ref;
+    const uint4 a = *reinterpret_cast<const uint4 *>(trip_pad + (size_t)ref * Sp + s0 + sb);
     w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
-    w[k][4] = b.x; w[k][5] = b.y; w[k][6] = b.z; w[k][7] = b.w;
   }
-  const unsigned padfill = padmask & (MCQ_NOSLOT * 0x01010101u);
-  uint8_t *dst = G + ((size_t)q * S + s0) * Lg + pos;
-  const int nrow = min(32, S - s0);
+  const unsigned fill0 = pad0 & (MCQ_NOSLOT * 0x01010101u), fill1 = pad1 & (MCQ_NOSLOT * 0x01010101u);
+  uint8_t *dst = G + ((size_t)q * S + s0 + sb) * Lg + pos;
+  const int nrow = min(16, S - s0 - sb);            // rows of this half inside the genome (may be <= 0)
+  const uint8_t *tbase = s_tab + sb * 128;
   unsigned worst = 0;
 #pragma unroll
-  for (int i = 0; i < 32; i++) {
-    const uint8_t *tb = s_tab + i * 128;
-    const unsigned b0 = tb[__byte_perm(w[0][i >> 2], 0, 0x4440 + (i & 3))];
-    const unsigned b1 = tb[__byte_perm(w[1][i >> 2], 0, 0x4440 + (i & 3))];
-    const unsigned b2 = tb[__byte_perm(w[2][i >> 2], 0, 0x4440 + (i & 3))];
-    const unsigned b3 = tb[__byte_perm(w[3][i >> 2], 0, 0x4440 + (i & 3))];
-    unsigned word = __byte_perm(b0 | (b1 << 8), b2 | (b3 << 8), 0x5410);
-    word = (word & ~padmask) | padfill;
-    worst |= word;
-    if (i < nrow) *reinterpret_cast<unsigned *>(dst + (size_t)i * Lg) = word;
+  for (int i = 0; i < 16; i++) {
+    const uint8_t *tb = tbase + i * 128;
+    unsigned b[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) b[k] = tb[__byte_perm(w[k][i >> 2], 0, 0x4440 + (i & 3))];
+    unsigned lo = __byte_perm(b[0] | (b[1] << 8), b[2] | (b[3] << 8), 0x5410);
+    unsigned hi = __byte_perm(b[4] | (b[5] << 8), b[6] | (b[7] << 8), 0x5410);
+    lo = (lo & ~pad0) | fill0;
+    hi = (hi & ~pad1) | fill1;
+    worst |= lo | hi;
+    if (i < nrow) *reinterpret_cast<uint2 *>(dst + (size_t)i * Lg) = make_uint2(lo, hi);
   }
   // every real slot value is below 0x80, MCQ_NEEDS_CONS is not: bit 7 of the OR says whether any occurred
   if (worst & 0x80808080u) {
     // triplet_to_codon (amino_acids.c:50-66): unknown bases take the query's local consensus
 #pragma unroll 1
     for (int i = 0; i < nrow; i++) {
-      const int s = s0 + i;
+      const int s = s0 + sb + i;
 #pragma unroll 1
-      for (int k = 0; k < 4; k++) {
-        if ((padmask >> (8 * k)) & 1) continue;
-        const unsigned tt = (uint8_t)trip_pad[roff[k] + i];
-        if (s_tab[i * 128 + tt] != MCQ_NEEDS_CONS) continue;
+      for (int k = 0; k < 8; k++) {
+        if (((k < 4 ? pad0 >> (8 * k) : pad1 >> (8 * (k - 4))) & 1) != 0) continue;
+        int ref = 0;                                  // (refs[] indexed by a loop variable would go to local memory)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) if (kk == k) ref = refs[kk];
+        const unsigned tt = (uint8_t)trip_pad[(size_t)ref * Sp + s];
+        if (s_tab[(sb + i) * 128 + tt] != MCQ_NEEDS_CONS) continue;
         const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
         int d0 = tt / 25, d1 = (tt / 5) % 5, d2 = tt % 5;
         if (d0 == 4) d0 = cn[0];
