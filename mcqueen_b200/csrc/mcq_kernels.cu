@@ -418,14 +418,6 @@ cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double
 // asynchronous global->shared copies (LDGSTS): a warp stages the codon-slot row G[q][s][.] and the
 // emission row of the sites ahead of the one it is computing
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -479,12 +471,6 @@ cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, int q0, int n
 // ------------------------------------------------------------------------------------------
 static_assert(MCQ_RING == 4, "the unrolled site loops assume a ring of four slots");
 
-__device__ __forceinline__ void cp_async16_sh(unsigned sa, const void *gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8_sh(unsigned sa, const void *gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
 
 // predicated forms: straight-line code, no branch around the copy
 __device__ __forceinline__ void cp_async16_if(unsigned sa, const void *gmem, bool p) {
