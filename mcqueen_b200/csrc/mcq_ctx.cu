@@ -582,6 +582,12 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     KScope ks(c, MCQ_K_GATHER);
     CK(mcq_launch_gather_prepare(c->st_trip, c->st_trip_pad, c->st_slot_of, c->st_trip_tab, S, N, c->stream));
   }
+  // new data: nothing of F or B is valid until the next evaluation (marked before any chunk is released to a
+  // pipelined evaluation, which sets the F marks of the queries it sweeps)
+  c->fv_h.assign(Q, -1);
+  c->bv_h.assign(Q, S);
+  CK(mcq_launch_set_valid(c->fv, c->bv, Q, H, -1, S, nullptr, 0, c->stream));
+  c->launches++;
   // chunks of at least opt_chunk_queries queries: smaller ones leave the kernels behind them short of warps
   const int nchunk = std::max(1, std::min(kUploadChunks, Q / std::max(1, c->opt_chunk_queries)));
   const McqStatic st_all = make_static(c);
@@ -605,11 +611,6 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   }
   c->hla_h.resize((size_t)Q * H);
   for (size_t i = 0; i < c->hla_h.size(); i++) c->hla_h[i] = hla_types[i] == '1';
-  // new data: nothing of F or B is valid until the next mcq_ctx_init_state
-  c->fv_h.assign(Q, -1);
-  c->bv_h.assign(Q, S);
-  CK(mcq_launch_set_valid(c->fv, c->bv, Q, H, -1, S, nullptr, 0, c->stream));
-  c->launches++;
   c->have_state = false;
   c->have_fwd = false;
   c->has_pending = false;
