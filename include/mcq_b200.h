@@ -203,7 +203,10 @@ enum {
                               have been DMA'd (they may be reused); the device-side set-up runs on, chunk
                               by chunk, and the next mcq_ctx_full_llk evaluates each chunk of queries as
                               soon as it is ready, under the set-up of the next one.  A closest_refs entry
-                              out of range is then reported by that evaluation, not by the upload. */
+                              out of range is then reported by that evaluation, not by the upload.
+                              2: the upload does not wait for the DMAs either (the cudaMemcpyAsync contract:
+                              the caller keeps its page-locked buffers unchanged until the next
+                              mcq_ctx_full_llk, evaluation or mcq_ctx_synchronize has returned). */
   MCQ_OPT_UPLOAD_CHUNK_QUERIES = 5 /* default 1250: mcq_ctx_upload_static transfers and sets up the per-query
                               data in up to 8 chunks of at least this many queries (one chunk = no
                               pipelining; smaller chunks starve the kernels that follow them). */

@@ -96,6 +96,7 @@ struct mcq_ctx {
   // MCQ_OPT_ASYNC_UPLOAD: mcq_ctx_upload_static returns once the DMAs are done; the chunks' gathers are
   // still running on the main stream, ev_ready[k] marks chunk k complete, and the next mcq_ctx_full_llk
   // evaluates chunk by chunk on stream3 behind them (pipe_n chunks, queries pipe_q[k] .. pipe_q[k+1]-1)
+  cudaStream_t stream_p = nullptr;  // parameters travelling beside an asynchronous upload
   cudaStream_t stream3 = nullptr;   // the pipelined evaluation: stream3 and pipe_st[] in turn
   cudaStream_t pipe_st[kPipeStreams - 1] = {nullptr};
   cudaEvent_t ev_ps[kPipeStreams - 1] = {nullptr};
@@ -297,6 +298,7 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithFlags(&c->stream_p, cudaStreamNonBlocking));
     for (int i = 0; i < kPipeStreams - 1; i++) {
       CK(cudaStreamCreateWithPriority(&c->pipe_st[i], cudaStreamNonBlocking, hi));
       CK(cudaEventCreateWithFlags(&c->ev_ps[i], cudaEventDisableTiming));
@@ -361,6 +363,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   if (c->ev_static) cudaEventDestroy(c->ev_static);
   if (c->ev_pipe) cudaEventDestroy(c->ev_pipe);
   if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
+  if (c->stream_p) { cudaStreamSynchronize(c->stream_p); cudaStreamDestroy(c->stream_p); }
   for (int i = 0; i < kPipeStreams - 1; i++) {
     if (c->pipe_st[i]) { cudaStreamSynchronize(c->pipe_st[i]); cudaStreamDestroy(c->pipe_st[i]); }
     if (c->ev_ps[i]) cudaEventDestroy(c->ev_ps[i]);
@@ -415,6 +418,8 @@ extern "C" int mcq_ctx_timer_stop(mcq_ctx *c, float *ms) {
 extern "C" int mcq_ctx_synchronize(mcq_ctx *c) {
   REQUIRE(c, "null context");
   CK(cudaSetDevice(c->d.device));
+  CK(cudaStreamSynchronize(c->stream2));      // the DMAs of an asynchronous upload
+  CK(cudaStreamSynchronize(c->stream_p));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -622,9 +627,10 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     c->launches++;
   }
   if (c->opt_async_upload) {
-    // the caller's buffers are free once the DMAs are done; the gathers run on, the range check of
-    // closest_refs is reported by the next evaluation (its reduction publishes the device flag)
-    CK(cudaStreamSynchronize(c->stream2));
+    // the caller's buffers are free once the DMAs are done (mode 1 waits for that, mode 2 leaves it to the
+    // next evaluation, which cannot finish before them); the gathers run on, the range check of closest_refs
+    // is reported by the next evaluation (its reduction publishes the device flag)
+    if (c->opt_async_upload == 1) CK(cudaStreamSynchronize(c->stream2));
     c->pipe_n = nchunk;
     c->have_static = true;
     return 0;
@@ -649,12 +655,13 @@ extern "C" int mcq_ctx_set_params(mcq_ctx *c, const mcq_params *p) {
   CK(cudaSetDevice(c->d.device));
   const size_t S = c->d.num_sites, H = c->d.num_hla_types;
   c->m.mu = p->mu; c->m.kappa = p->kappa; c->m.phi = p->phi;
-  // With an asynchronous upload in flight the main stream is busy gathering: the parameters then travel on
-  // the copy stream and the pipelined evaluation waits for ev_params.
-  cudaStream_t pst = c->pipe_n > 0 ? c->stream2 : c->stream;
+  // With an asynchronous upload in flight the main stream is busy gathering and the copy stream busy with the
+  // upload's DMAs: the parameters then travel on a stream of their own and the pipelined evaluation waits for
+  // ev_params.
+  cudaStream_t pst = c->pipe_n > 0 ? c->stream_p : c->stream;
   c->params_on_copy_stream = c->pipe_n > 0;
-  if (c->pipe_n > 0) CK(cudaStreamSynchronize(c->stream2));
-  else CK(cudaStreamSynchronize(c->stream));     // the staging block may still feed an earlier copy
+  if (c->pipe_n > 0) CK(cudaEventSynchronize(c->ev_params));   // the staging block may still feed the last such copy
+  else CK(cudaStreamSynchronize(c->stream));                    // ... or an earlier copy on the main stream
   double *h = c->h_pblock;
   double *h_prior = h, *h_R = h_prior + 64, *h_omega = h_R + S, *h_rev = h_omega + S, *h_esc = h_rev + S,
          *h_rate = h_esc + H * S;
@@ -683,7 +690,7 @@ extern "C" int mcq_ctx_set_params(mcq_ctx *c, const mcq_params *p) {
   }
   // no host wait: the copy is ordered before every later kernel on the context's stream
   if (c->params_on_copy_stream) {
-    CK(cudaEventRecord(c->ev_params, c->stream2));
+    CK(cudaEventRecord(c->ev_params, c->stream_p));
     CK(cudaStreamWaitEvent(c->stream, c->ev_params, 0));      // everything later on the main stream sees them too
   }
   c->have_params = true;

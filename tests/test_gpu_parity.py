@@ -350,6 +350,22 @@ def test_async_upload_pipelined_evaluation(api, name, over):
         ctx.set_params(**prm)
         assert ctx.full_llk(True) == want
         assert np.array_equal(ctx.query_llk(), per_q)
+    ctx.set_option(api.OPT_ASYNC_UPLOAD, 2)              # not even the DMAs are waited for (page-locked buffers)
+    pinned = [np.ascontiguousarray(a) for a in up[:5]]
+    for a in pinned:
+        api.host_register(a)
+    for _ in range(3):
+        ctx.upload_static(*pinned, *up[5:])
+        ctx.set_params(**prm)
+        assert ctx.full_llk(True) == want
+        assert np.array_equal(ctx.query_llk(), per_q)
+    ctx.upload_static(*pinned, *up[5:])
+    ctx.set_params(**prm)
+    assert abs(ctx.init_state() - want) <= 1e-15 * abs(want)      # another consumer of a queued upload
+    ctx.synchronize()
+    for a in pinned:
+        api.host_unregister(a)
+    ctx.set_option(api.OPT_ASYNC_UPLOAD, 1)
     ctx.set_option(api.OPT_UPLOAD_CHUNK_QUERIES, 1250)   # the default: one chunk at this size, no pipelining
     ctx.upload_static(*up)
     ctx.set_params(**prm)
