@@ -808,7 +808,11 @@ static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream
 static int wait_slot(mcq_ctx *c, unsigned long long want, cudaStream_t st) {
   volatile unsigned long long *seq = &c->h_slot->seq;
   for (unsigned spins = 1; *seq != want; spins++) {
+#if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
     if ((spins & 0x3FFF) == 0) {
       const cudaError_t e = cudaStreamQuery(st);
       if (e == cudaSuccess) {
