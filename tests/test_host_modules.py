@@ -206,3 +206,25 @@ def test_state_json_round_trip(host, tmp_path):
             wa, wb = snapshot(a.contents, S)[0], snapshot(b.contents, S)[0]
             assert [(s, n) for s, n, _ in wa] == [(s, n) for s, n, _ in wb]
             assert np.allclose([c for _, _, c in wa], [c for _, _, c in wb], rtol=1e-5)
+
+
+def test_fasta_and_hla_csv_readers(host, tmp_path):
+    """load_data.c:66-157 restated: multi-line records, CR/LF, blank lines; the 0/1 table with a header line and one
+    leading label column."""
+    fa = tmp_path / "a.fasta"
+    fa.write_text(">r1 some text\nTTTCAG\nGG-\n\n>r2\r\nacgtnn\r\n>r3\n>r4\nA\n")
+    seqs = C.POINTER(C.c_char_p)()
+    host.mcq_load_fasta.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_char_p))]
+    n = host.mcq_load_fasta(str(fa).encode(), C.byref(seqs))
+    assert n == 4
+    assert [seqs[i] for i in range(n)] == [b"TTTCAGGG-", b"acgtnn", b"", b"A"]
+    csv = tmp_path / "h.csv"
+    csv.write_text('"","A01","A02","B07"\nq1,0,1,0\nq2, 1 ,1,1\nq3,0,0,0\nq4,1,0,1\n')
+    rows = C.POINTER(C.c_char_p)()
+    host.mcq_load_hla_csv.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_char_p)), C.c_int]
+    types = host.mcq_load_hla_csv(str(csv).encode(), C.byref(rows), 3)
+    assert types == 3
+    assert [rows[i] for i in range(3)] == [b"010", b"111", b"000"]
+    d = tmp_path / "x" / "y" / "z"
+    host.mcq_mkpath.argtypes = [C.c_char_p]
+    assert host.mcq_mkpath(str(d).encode()) == 1 and d.is_dir()
