@@ -259,6 +259,11 @@ int mcq_ctx_attach_peers(mcq_ctx *ctx, int nranks, int rank, const unsigned char
 int mcq_comm_unique_id(unsigned char id[128]);
 int mcq_ctx_attach_comm(mcq_ctx *ctx, int nranks, int rank, const unsigned char id[128]);
 
+/* Sum of one double per rank over the attached ranks, added in rank order (identical bits on every
+ * rank); identity without peers.  The same exchange the likelihood totals use, for what the host chain
+ * has to decide collectively (mcq_dmodel's wall-clock limit: rank 0's clock decides for everyone). */
+int mcq_ctx_exchange_sum(mcq_ctx *ctx, double *value);
+
 /* Substitution class of the codon pair (c1,c2), codons numbered base-4 over T,C,A,G: 0 none or
  * multi-step, 1 non-synonymous transition, 2 non-synonymous transversion, 3 synonymous transition,
  * 4 synonymous transversion - the content of NS_TS / NS_TV / S_TS / S_TV (constants.c:424-688). */

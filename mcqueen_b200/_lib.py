@@ -74,6 +74,7 @@ SYMBOLS = {
     "mcq_ctx_attach_peers": (C.c_int, [_V, C.c_int, C.c_int, _V]),
     "mcq_comm_unique_id": (C.c_int, [_V]),
     "mcq_ctx_attach_comm": (C.c_int, [_V, C.c_int, C.c_int, _V]),
+    "mcq_ctx_exchange_sum": (C.c_int, [_V, c_double_p]),
     "mcq_codon_class": (C.c_int, [C.c_int, C.c_int]),
     "mcq_closest_batch": (C.c_int, [C.c_int, _V, C.c_size_t, C.c_int, _V, C.c_size_t, C.c_int, C.c_int,
                                     C.c_int, C.c_int, _V]),

@@ -324,6 +324,12 @@ class Context:
         flat = (C.c_ubyte * (64 * nranks)).from_buffer_copy(b"".join(handles))
         check(self.lib.mcq_ctx_attach_peers(self._h, nranks, rank, C.cast(flat, C.c_void_p)))
 
+    def exchange_sum(self, value):
+        """Sum of one double per rank over the attached ranks (rank order; identity without peers)."""
+        v = C.c_double(value)
+        check(self.lib.mcq_ctx_exchange_sum(self._h, C.byref(v)))
+        return v.value
+
     def attach_comm(self, nranks, rank, unique_id: bytes):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         check(self.lib.mcq_ctx_attach_comm(self._h, nranks, rank, C.cast(buf, C.c_void_p)))

@@ -1,37 +1,65 @@
-"""Builds libmcq_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds libmcq_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Every source becomes an object under mcqueen_b200/build/ (compiled in parallel, re-compiled only when
+it or a header changed), the objects are linked into mcqueen_b200/libmcq_b200.so."""
 from __future__ import annotations
 
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmcq_b200.so")
-SOURCES = ["mcq_kernels.cu", "mcq_ctx.cu", "mcq_dropin.cu", "mcq_closest.cu", "mcq_tables.cpp"]
+SOURCES = ["mcq_kernels.cu", "mcq_sweeps.cu", "mcq_ctx.cu", "mcq_dropin.cu", "mcq_closest.cu", "mcq_tables.cpp"]
 # -fmad=false: the reference is compiled without FMA contraction; with it
 # off the emission rows are bit-identical to the reference's.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
-              "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+              "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(os.path.dirname(HERE), "include", "mcq_b200.h"))
+    return hs
+
+
+def _sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "mcq_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return _stale(LIB, [os.path.join(CSRC, s) for s in _sources()] + _headers())
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = _headers()
+    objs, jobs = [], []
+    for s in _sources():
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s.rsplit(".", 1)[0] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + hdrs):
+            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        for r in ex.map(lambda cmd: subprocess.run(cmd, capture_output=not verbose, text=True), jobs):
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed: " + " ".join(r.args) + "\n" + (r.stdout or "") + (r.stderr or ""))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -470,7 +470,8 @@ void tie_shuffle_and_take(const int *lt_sorted, int n_lt, const int *eq_group, l
   const int M = (int)win.size();
   for (int i = 0; i < M; i++) {
     const double u = (i + 1) * ((double)random() / (double)RAND_MAX);
-    const int j = (int)u;
+    int j = (int)u;
+    if (j > i) j = i;        // random() == RAND_MAX: the reference swaps with element i+1, past the window (UB)
     std::swap(win[i], win[j]);
   }
   memcpy(out + lo, win.data(), (size_t)(n - lo) * sizeof(int));

@@ -128,7 +128,7 @@ struct mcq_ctx {
   // emission rows: shared table + per-query consensus values, current and proposal ("tmp") sets
   double *tab = nullptr, *atab = nullptr, *ec = nullptr, *ac = nullptr;
   double *tab_t = nullptr, *atab_t = nullptr, *ec_t = nullptr, *ac_t = nullptr;
-  double *llk_cur = nullptr, *llk_prop = nullptr, *d_sum = nullptr;
+  double *llk_cur = nullptr, *llk_prop = nullptr, *d_sum = nullptr, *d_xchg = nullptr;
   int *fv = nullptr, *bv = nullptr;   // per query: F valid up to fv, B valid from bv (lazy refills)
   double *h_sum = nullptr;   // pinned
   double *pblock = nullptr, *h_pblock = nullptr;   // parameter block (device) and its pinned staging copy
@@ -316,7 +316,7 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   CK(cudaMallocHost((void **)&c->h_pblock, c->pblock_n * sizeof(double)));
   c->m.prior = c->pblock; c->m.R = c->m.prior + 64; c->m.omega = c->m.R + S; c->m.rev = c->m.omega + S;
   c->m.esc = c->m.rev + S; c->m.rate_out = c->m.esc + H * S;
-  ALLOC(c->llk_cur, Q); ALLOC(c->llk_prop, Q); ALLOC(c->d_sum, 1);
+  ALLOC(c->llk_cur, Q); ALLOC(c->llk_prop, Q); ALLOC(c->d_sum, 1); ALLOC(c->d_xchg, 1);
   ALLOC(c->fv, Q); ALLOC(c->bv, Q);
   CK(cudaMallocHost((void **)&c->h_sum, sizeof(double)));
   CK(cudaMallocHost((void **)&c->h_err, sizeof(int)));
@@ -338,7 +338,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   void *ptrs[] = {c->desc, c->rowdesc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->pblock,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
-                  c->llk_cur, c->llk_prop, c->d_sum, c->fv, c->bv, c->sel, c->st_trip, c->st_trip_pad, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
+                  c->llk_cur, c->llk_prop, c->d_sum, c->d_xchg, c->fv, c->bv, c->sel, c->st_trip, c->st_trip_pad, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
   for (void *p : ptrs)
     if (p && !(p == (void *)c->st_trip && c->trip_in_mailbox)) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
@@ -559,11 +559,13 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   // gather of chunk k runs under the transfer of chunk k+1.  The '0'/'1' characters of hla_types are turned
   // into 0/1 and closest_refs is range-checked on the device.
   CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
-  CK(cudaMemcpyAsync(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventRecord(c->ev_fork, c->stream));                 // the copy stream starts behind earlier work
-  CK(cudaEventRecord(c->ev_static, c->stream));               // ... and so does a pipelined evaluation
   CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  // every DMA out of a caller's buffer runs on the copy stream: MCQ_OPT_ASYNC_UPLOAD = 1 returns once that
+  // stream has drained, and the caller may then reuse all of its buffers
+  CK(cudaMemcpyAsync(c->cons_codon, consensus_codons, S, cudaMemcpyHostToDevice, c->stream2));
+  CK(cudaMemcpyAsync(c->st_slot_of, slot_of.data(), (size_t)S * 64, cudaMemcpyHostToDevice, c->stream2));
+  CK(cudaEventRecord(c->ev_static, c->stream2));              // a pipelined evaluation starts behind the small tables
   const bool shared_panel = c->have_peers && c->trip_in_mailbox && c->opt_shared_panel && c->box.nranks > 1;
   if (shared_panel) {
     // every rank DMAs one slice of the panel rows from the host; the others arrive from the peers' copies
@@ -838,15 +840,16 @@ static int slot_error(mcq_ctx *c) {
   }
 }
 
-static int reduce_llk(mcq_ctx *c, const double *per_query, double *out, cudaStream_t st = nullptr) {
+static int reduce_llk(mcq_ctx *c, const double *per_query, double *out, cudaStream_t st = nullptr, int n = -1) {
   if (st == nullptr) st = c->stream;
+  if (n < 0) n = c->d.num_query;
   const unsigned long long want = ++c->eval_seq;
   if (c->have_peers) {
     // shard total + NVLink mailbox exchange in one kernel
     {
       KScope ks(c, MCQ_K_SUM);
       c->step++;
-      CK(mcq_launch_sum_exchange(per_query, c->d.num_query, c->d_sum, &c->box, c->step, c->d_err, c->d_slot, want, st));
+      CK(mcq_launch_sum_exchange(per_query, n, c->d_sum, &c->box, c->step, c->d_err, c->d_slot, want, st));
     }
     if (wait_slot(c, want, st)) return 1;
     if (slot_error(c)) return 1;
@@ -855,7 +858,7 @@ static int reduce_llk(mcq_ctx *c, const double *per_query, double *out, cudaStre
   }
   {
     KScope ks(c, MCQ_K_SUM);
-    CK(mcq_launch_sum(per_query, c->d.num_query, c->d_sum, c->comm ? nullptr : c->d_slot, want, c->d_err, st));
+    CK(mcq_launch_sum(per_query, n, c->d_sum, c->comm ? nullptr : c->d_slot, want, c->d_err, st));
   }
   if (c->comm) {
     int r = g_nccl.AllReduce(c->d_sum, c->d_sum, 1, kNcclDouble, kNcclSum, c->comm, st);
@@ -871,6 +874,17 @@ static int reduce_llk(mcq_ctx *c, const double *per_query, double *out, cudaStre
   if (slot_error(c)) return 1;
   if (out) *out = c->h_slot->value;
   return 0;
+}
+
+// One double per rank, summed over the attached ranks in rank order (the same bits everywhere): the
+// exchange of the likelihood totals, offered to the host chain for what it must decide collectively.
+extern "C" int mcq_ctx_exchange_sum(mcq_ctx *c, double *value) {
+  REQUIRE(c && value, "null argument");
+  CK(cudaSetDevice(c->d.device));
+  *c->h_sum = *value;
+  CK(cudaMemcpyAsync(c->d_xchg, c->h_sum, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->launches = 0;
+  return reduce_llk(c, c->d_xchg, value, nullptr, 1);
 }
 
 #define READY(c)                                                                   \

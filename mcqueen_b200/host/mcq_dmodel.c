@@ -486,8 +486,20 @@ int main(int argc, char **argv)
   /* the two random streams (dmodel.c:391-392); --seed / MCQ_SEED make a run reproducible */
   if(opt_seed < 0 && getenv("MCQ_SEED")) opt_seed = atol(getenv("MCQ_SEED"));
   if(opt_gsl_seed < 0 && getenv("MCQ_GSL_SEED")) opt_gsl_seed = atol(getenv("MCQ_GSL_SEED"));
-  mcq_seed_libc(opt_seed >= 0 ? (unsigned)opt_seed : (unsigned)time(NULL));
-  mcq_mt_seed(opt_gsl_seed >= 0 ? (unsigned long)opt_gsl_seed : (unsigned long)((double)time(NULL) * getpid()));
+  {
+    /* clock-derived seeds differ between processes: with several ranks rank 0 draws them and hands them
+     * over before anybody makes a draw, so that every rank runs the same chain */
+    unsigned long seeds[2];
+    seeds[0] = opt_seed >= 0 ? (unsigned long)opt_seed : (unsigned long)(unsigned)time(NULL);
+    seeds[1] = opt_gsl_seed >= 0 ? (unsigned long)opt_gsl_seed : (unsigned long)((double)time(NULL) * getpid());
+    if(world > 1) {
+      if(rank == 0) blob_put("seed", 0, (const unsigned char *)seeds, sizeof(seeds));
+      else blob_get("seed", 0, (unsigned char *)seeds, sizeof(seeds));
+    }
+    mcq_seed_libc((unsigned)seeds[0]);
+    mcq_mt_seed(seeds[1]);
+    if(rank == 0) printf("seeds: %lu %lu\n", seeds[0], seeds[1]);
+  }
 
   if(!mcq_mkpath(out_dir)) mcq_die("Cannot create output dir: %s", out_dir);
   char stamp[64], path[PATH_MAX];
@@ -674,6 +686,13 @@ int main(int argc, char **argv)
       if(!opt_nccl || rank == 0) unlink(mine);
     }
   }
+  if(world > 1) {
+    /* the seed hand-over file: every rank has read it once the first exchange is through */
+    double one = 1;
+    CHECK(mcq_ctx_exchange_sum(c.ctx, &one));
+    if((int)one != world) mcq_die("rank exchange returned %f for %d ranks", one, world);
+    if(rank == 0) { char f[PATH_MAX]; blob_path(f, sizeof(f), "seed", 0); unlink(f); }
+  }
   if(resume_path != NULL) printf("Likelihood from loaded .json file: %f.\n", resume_llk);
 
   /* move weights (dmodel.c:915-962) */
@@ -703,7 +722,7 @@ int main(int argc, char **argv)
   struct timespec ts0, ts1;
   clock_gettime(CLOCK_MONOTONIC, &ts0);
   time_t t_start = time(NULL);
-  int hours_passed = 1, sample_i = 1, chain_i;
+  int hours_passed = 1, sample_i = 1, chain_i, hours = 0;
   for(chain_i = 0; chain_i < chain_length; chain_i++, sample_i++) {
     int pick = mcq_rand_lim(total);
     int move = pick < rec ? 0 : pick < sel ? 1 : pick < esc_ms ? 2 : pick < rev_ms ? 3 : pick < esc_gr ? 4 :
@@ -735,7 +754,14 @@ int main(int argc, char **argv)
     }
 
     /* end of chain / wall-clock limit / hourly interim state (dmodel.c:1203-1235) */
-    int hours = (int)(difftime(time(NULL), t_start) / 3600);
+    /* with several ranks the clock of rank 0 decides for everyone (checked every 256 steps and on the
+     * last step of the chain): the ranks stop at the same step and write the same state */
+    if(world == 1) hours = (int)(difftime(time(NULL), t_start) / 3600);
+    else if((chain_i & 255) == 255 || (runtime_set && chain_i == chain_length - 1)) {
+      double h0 = rank == 0 ? floor(difftime(time(NULL), t_start) / 3600) : 0;
+      CHECK(mcq_ctx_exchange_sum(c.ctx, &h0));
+      hours = (int)h0;
+    }
     bool last = false;
     if(runtime_set) {
       if(hours >= runtime_hours) last = true;
