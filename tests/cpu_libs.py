@@ -190,3 +190,19 @@ def full_state(chk, p, c2c=None, A=None):
         chk.backward(p, q, c2c[q], p.R, B[q], Bn[q], S - 1)
         llk[q] = chk.site_llk(p, F[q], Fn[q], None, None, S - 1)
     return dict(c2c=c2c, A=A, F=F, B=B, Fn=Fn, Bn=Bn, llk=llk)
+
+
+def reference_consensus_subset(refs, closest):
+    """generate_consensus_subset (amino_acids.c:118-141) of the compiled reference, as base codes."""
+    from mcqueen_b200 import genetics as gen
+    lib = C.CDLL(REF_SO)
+    N, nb = refs.shape
+    rows = [C.create_string_buffer(bytes(refs[r]), nb + 1) for r in range(N)]
+    seqs = (C.c_char_p * N)(*[C.cast(b, C.c_char_p) for b in rows])
+    out = np.zeros((closest.shape[0], nb), np.int8)
+    buf = C.create_string_buffer(nb + 1)
+    for q in range(closest.shape[0]):
+        cl = np.ascontiguousarray(closest[q], np.int32)
+        lib.generate_consensus_subset(seqs, C.c_int(cl.size), C.c_int(nb), buf, cl.ctypes.data_as(C.c_void_p))
+        out[q] = gen.base_codes(np.frombuffer(buf.raw[:nb], np.uint8))
+    return out

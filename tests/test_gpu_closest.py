@@ -112,3 +112,22 @@ def test_consensus_batch_matches_host_rule(api):
         codes = gen.base_codes(refs)
         want = np.stack([prep.majority_codes(codes[closest[q]]) for q in range(25)])
         assert np.array_equal(got, want), L
+
+
+@pytest.mark.parametrize("S,N,Q,L", [(40, 200, 25, 17), (40, 200, 25, 199), (171, 700, 9, 100), (500, 300, 12, 1),
+                                     (43, 2100, 70, 500)])
+def test_consensus_batch_matches_reference_generate_consensus_subset(api, S, N, Q, L):
+    """k_consensus against the reference's own generate_consensus_subset (amino_acids.c:118-141, called per
+    query at dmodel.c:664-681): unknown bases, lower case, ties, positions where no reference has a base."""
+    if not cpu_libs.have_ref():
+        pytest.skip("oracle/_ref/libmcq_ref.so not present")
+    d = _data(S=S, N=N, Q=Q)
+    refs = d["ref_seqs"].copy()
+    refs[::7, 3] = ord("-"); refs[5, :] = ord("N"); refs[9, 10:20] = np.frombuffer(b"acgtacgtac", np.uint8)
+    refs[:, 7] = ord("N")                                   # nobody has a base here: 'T' (code 0)
+    refs[: N // 2, 11] = ord("C"); refs[N // 2:, 11] = ord("A")   # engineered near-ties
+    rng = np.random.default_rng(L)
+    closest = np.stack([rng.choice(N, L, replace=False) for _ in range(Q)]).astype(np.int32)
+    want = cpu_libs.reference_consensus_subset(refs, closest)
+    got = api.consensus_batch(refs, closest)
+    assert np.array_equal(got, want)

@@ -301,6 +301,34 @@ def test_contract_tolerance_on_c2_slice(api):
     ctx.close()
 
 
+@pytest.mark.parametrize("sparse", [0, 1])
+def test_c5_shape_state_and_proposals(api, sparse):
+    """The shape of BASELINE config 5 (3000 codons, L=200 -> ragged rows of 208 in the four-word kernels; 8 queries
+    so that the CPU side finishes in seconds): initial state, every proposal kind, accepts and the owed refills
+    they leave behind, against the CPU chain."""
+    p = make_problem("toy", S=3000, N=600, Q=8, L=200, H=8, gaps=True)
+    cpu = CpuState(checker(), p)
+    ctx = api.Context.from_problem(p)
+    ctx.set_option(api.OPT_SPARSE_ESC, sparse)
+    llk = ctx.init_state()
+    assert abs(llk - cpu.llk) <= RTOL_LLK * abs(cpu.llk)
+    assert rel(ctx.query_llk(), cpu.llk_q) < RTOL_LLK
+    assert_state_matches(ctx, cpu, [0, p.Q - 1])
+    rng = np.random.default_rng(5)
+    moves = _moves(p, rng) + [dict(kind=REV, start=2900, end=2999, value0=0.8),
+                              dict(kind=ESC, start=1400, end=1650, hla=3, split=1500, value0=1.4, value1=0.7),
+                              dict(kind=REC, start=1, value0=0.03)]
+    for i, mv in enumerate(moves):
+        want, got = cpu.propose(**mv), ctx.propose(**mv)
+        assert abs(got - want) <= (1e-11 if sparse else RTOL_LLK) * abs(want), (i, mv, got, want)
+        if i % 3 != 2:
+            cpu.accept(); ctx.accept()
+        else:
+            cpu.reject(); ctx.reject()
+    assert_state_matches(ctx, cpu, [0, 3, p.Q - 1])
+    ctx.close()
+
+
 def test_reupload_invalidates_the_state(api):
     """New static data makes F and B meaningless: proposals are refused until a state exists again
     (mcq_ctx_init_state, or mcq_ctx_full_llk + mcq_ctx_backward_fill), and that state matches the oracle."""

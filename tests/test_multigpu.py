@@ -1,6 +1,8 @@
-"""Two ranks on two GPUs (run with `gpurun --gpus 2`; skipped on a single-GPU box): the sharded
-evaluation with the NVLink peer exchange and with the NCCL all-reduce both equal the single-GPU total,
-and proposals / accepts stay in lock step."""
+"""Two ranks: the sharded evaluation with the peer-mailbox exchange and with the NCCL all-reduce both equal the
+single-GPU total, and proposals / accepts stay in lock step.  With two GPUs (`gpurun --gpus 2`) each rank has its
+own; on a single-GPU box the peer-mailbox variant still runs, both ranks time-sharing device 0 (the mailboxes are
+CUDA IPC mappings either way), and only the NCCL variant - which refuses two ranks on one device - is skipped.
+Also the driver: two ranks of mcq_dmodel started WITHOUT seeds run one and the same chain."""
 import os
 import sys
 
@@ -23,7 +25,8 @@ def _worker(rank, world, port, kind, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     p = make_problem("toy")
     q0, q1 = p.Q * rank // world, p.Q * (rank + 1) // world
-    ctx = api.Context.from_problem(p, device=rank, q0=q0, q1=q1)
+    import torch
+    ctx = api.Context.from_problem(p, device=rank % torch.cuda.device_count(), q0=q0, q1=q1)
     if kind == "peer":
         handles = [None] * world
         dist.all_gather_object(handles, ctx.peer_handle())
@@ -60,8 +63,8 @@ def _worker(rank, world, port, kind, out):
 @pytest.mark.parametrize("kind", ["peer", "nccl"])
 def test_two_gpu_exchange(tmp_path, kind):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if torch.cuda.device_count() < 2 and kind == "nccl":
+        pytest.skip("NCCL needs one GPU per rank")
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from mcqueen_b200 import api
@@ -82,3 +85,39 @@ def test_two_gpu_exchange(tmp_path, kind):
     want.append(ctx.full_llk(False))
     ctx.close()
     assert np.allclose(got[0], want, rtol=1e-12, atol=0)
+
+
+def test_two_rank_driver_without_seeds_runs_one_chain(tmp_path):
+    """mcq_dmodel under two ranks with clock-derived seeds: rank 0 hands its seeds over, so both ranks print the
+    same counters and the same final log-likelihood - the ones a single rank gets from those seeds."""
+    import re
+    import subprocess
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from chain_files import make_chain_inputs
+    driver = os.path.join(ROOT, "mcqueen_b200", "host", "mcq_dmodel")
+    if not os.path.exists(driver):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(driver)])
+    paths, L, _ = make_chain_inputs(str(tmp_path / "in"), "toy")
+    args = ["-H", paths["hla"], "-l", str(L), "-n", "400", "-s", "50", paths["ref"], paths["query"]]
+    ndev = torch.cuda.device_count()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r % ndev), MASTER_PORT="29655")
+        env.pop("MCQ_SEED", None); env.pop("MCQ_GSL_SEED", None)
+        procs.append(subprocess.Popen([driver] + args + [str(tmp_path / f"out{r}")], env=env, text=True,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs[0][-1500:] + outs[1][-1500:]
+
+    def tail(o):
+        return o[o.index("Proposed"):o.index("MCMC loop")], float(re.search(r"final log-likelihood: (\S+)", o).group(1))
+
+    assert tail(outs[0]) == tail(outs[1])
+    a, b = re.search(r"seeds: (\d+) (\d+)", outs[0]).groups()
+    one = subprocess.run([driver, "--seed", a, "--gsl_seed", b] + args + [str(tmp_path / "single")],
+                         capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stdout[-1500:] + one.stderr[-1500:]
+    c1, l1 = tail(one.stdout)
+    c2, l2 = tail(outs[0])
+    assert c1 == c2 and abs(l1 - l2) <= 1e-11 * abs(l1)

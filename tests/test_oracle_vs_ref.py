@@ -140,3 +140,19 @@ def test_mu_rescale_matches_mutation_move(libs):
                            cpu_libs.cp(p.query_codons), C.c_double(p.mu), C.c_double(mu_new), C.c_double(p.phi),
                            cpu_libs.dp(p.prior))
     assert np.array_equal(tc2c, want_c2c) and np.array_equal(tA, want_A)
+
+
+def test_host_majority_rule_matches_generate_consensus_subset():
+    """prep.majority_codes (the host mirror used to build problems) against the reference's
+    generate_consensus_subset (amino_acids.c:118-141): ties, unknown bases, empty columns."""
+    from mcqueen_b200 import genetics as gen, prep, synth
+    d = synth.make_dataset(seed=3, S=30, N=120, Q=4, H=2, ref_unknown_frac=0.2)
+    refs = d["ref_seqs"].copy()
+    refs[:, 5] = ord("N"); refs[:60, 8] = ord("G"); refs[60:, 8] = ord("C"); refs[3, :9] = np.frombuffer(b"acgtnACGT", np.uint8)
+    rng = np.random.default_rng(0)
+    for L in (1, 2, 60, 119):
+        closest = np.stack([rng.choice(120, L, replace=False) for _ in range(6)]).astype(np.int32)
+        want = cpu_libs.reference_consensus_subset(refs, closest)
+        codes = gen.base_codes(refs)
+        got = np.stack([prep.majority_codes(codes[closest[q]]) for q in range(6)])
+        assert np.array_equal(got, want), L
