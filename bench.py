@@ -10,7 +10,13 @@ cross-GPU sum - what dmodel does at start-up and what mutation_move re-does per 
 
 N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...`;
 queries are sharded over ranks (strong scaling: BASELINE.json names one fixed workload "sharded
-1/2/4/8"), the only exchange is the library's one-double NCCL all-reduce per evaluation.
+1/2/4/8"), the only exchange is one double per rank per evaluation: NVLink stores into the peers'
+mailboxes inside the reduction kernel (MCQ_BENCH_COMM=peer, the default) or one ncclAllReduce
+(MCQ_BENCH_COMM=nccl); the one that is not the headline is timed beside it (`exchange_comparison`).
+The problem is the same at every N (closest-L lists of the whole workload, one tie-shuffle stream):
+`llk_matches_single_gpu` checks the total against the recorded one-GPU value and a sample of
+queries bit for bit against a one-GPU re-evaluation.  The dmodel MCMC steps/s are measured at
+every N as well (one driver process per rank).
 """
 from __future__ import annotations
 
@@ -51,38 +57,46 @@ def make_data(name):
     return synth.make_dataset(seed=SEED, self_reference=name in synth.SELF_REFERENCE, **cfg)
 
 
-def build_shard(name, q0, q1, device_index, use_gpu_closest=True):
-    """Problem restricted to queries q0..q1-1 (references are shared by every shard)."""
+def build_shard(name, q0, q1, device_index):
+    """Problem restricted to queries q0..q1-1 (references are shared by every shard).
+
+    The closest-L lists are those of the WHOLE workload: the reference shuffles boundary ties with one libc
+    random() stream consumed in global query order (closest_seqs.c:57-64, called per query from
+    dmodel.c:356-387), so every rank selects for all queries from the same seed - as mcq_dmodel does - and keeps
+    its shard.  The problem is then the same at every number of GPUs."""
     from mcqueen_b200 import api
     cfg = workload_dims(name)
     L = cfg["L"]
     t0 = time.time()
     data = make_data(name)
-    refs, qs, hla = data["ref_seqs"], np.ascontiguousarray(data["query_seqs"][q0:q1]), data["hla"][q0:q1]
-    t1 = time.time()
+    refs, qs_all = data["ref_seqs"], data["query_seqs"]
+    qs, hla = np.ascontiguousarray(qs_all[q0:q1]), data["hla"][q0:q1]
     import ctypes
     # CUDA context creation and module load happen on the first call: keep them out of the closest-L wall time
     api.closest_batch(refs[:max(2 * L, 64)], qs[:2], min(L, 8), device=device_index)
     t1 = time.time()
     ctypes.CDLL("libc.so.6").srandom(SEED & 0x7fffffff)
-    closest = api.closest_batch(refs, qs, L, skip_first=name in synth.SELF_REFERENCE, device=device_index)
+    closest_all = api.closest_batch(refs, qs_all, L, skip_first=name in synth.SELF_REFERENCE, device=device_index)
     t2 = time.time()
     ham_ms, sel_ms = api.closest_last_timing()
+    closest = np.ascontiguousarray(closest_all[q0:q1])
     cons_q = api.consensus_batch(refs, closest, device=device_index)
     p = prep.build_problem(refs, qs, hla, closest, cons_q=cons_q)
     prep.random_parameters(p, seed=1)
     t3 = time.time()
-    log(f"[bench] data {t1 - t0:.1f}s  closest-L(GPU) {t2 - t1:.1f}s  prep {t3 - t2:.1f}s  "
+    log(f"[bench] data {t1 - t0:.1f}s  closest-L(GPU, all {qs_all.shape[0]} queries) {t2 - t1:.1f}s  prep {t3 - t2:.1f}s  "
         f"Q={p.Q} S={p.S} L={p.L} N={p.N} H={p.H}")
     p.closest_seconds = t2 - t1
+    p.full = dict(refs=refs, queries=qs_all, hla=data["hla"], closest=closest_all)
     nb = refs.shape[1]
+    nq = qs_all.shape[0]
     p.closest_stats = {
-        "shape": f"{refs.shape[0]} refs x {qs.shape[0]} queries x {nb} nt, L={L} (BASELINE config 3 when the workload is C4)",
+        "shape": f"{refs.shape[0]} refs x {nq} queries x {nb} nt, L={L} (BASELINE config 3 when the workload is C4)",
         "hamming_kernel_ms": ham_ms, "select_kernels_ms": sel_ms, "wall_seconds_incl_transfers_and_tie_shuffle": t2 - t1,
-        "nt_compares_per_s": refs.shape[0] * qs.shape[0] * nb / (ham_ms * 1e-3) if ham_ms > 0 else None,
+        "nt_compares_per_s": refs.shape[0] * nq * nb / (ham_ms * 1e-3) if ham_ms > 0 else None,
         # one 64-bit POPC word per 64 nt per pair: B200 issues 16 POPC.32 lanes/clk/SM
-        "popc_word_ops_per_s": refs.shape[0] * qs.shape[0] * ((nb + 63) // 64) / (ham_ms * 1e-3) if ham_ms > 0 else None,
-        "queries_per_s": qs.shape[0] / (t2 - t1)}
+        "popc_word_ops_per_s": refs.shape[0] * nq * ((nb + 63) // 64) / (ham_ms * 1e-3) if ham_ms > 0 else None,
+        "queries_per_s": nq / (t2 - t1)}
     return p
 
 
@@ -157,7 +171,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the reference's own code (oracle/_ref/ref_bench), host threads over query shards
 # ------------------------------------------------------------------------------------------------
-def write_ref_problem(p, path, nq):
+def write_ref_problem(p, path, nq, seqs=None):
+    """The problem file oracle/ref_bench.c reads; seqs = (ref_seqs, query_seqs) ASCII adds the section its
+    closest-L mode needs."""
     nq = min(nq, p.Q)
     with open(path, "wb") as f:
         np.array([p.S, p.N, nq, p.L, p.H], np.int32).tofile(f)
@@ -171,11 +187,26 @@ def write_ref_problem(p, path, nq):
         p.ns_ts_sum.astype(np.int32).tofile(f); p.ns_tv_sum.astype(np.int32).tofile(f)
         p.R.tofile(f); p.omega.tofile(f); np.ascontiguousarray(p.esc).tofile(f)
         np.ascontiguousarray(p.rev).tofile(f); p.rate_out_of_codons().tofile(f)
+        if seqs is not None:
+            refs, qs = seqs
+            nb = refs.shape[1]
+            np.array([nb], np.int32).tofile(f)
+            for a in (refs, qs[:nq]):
+                z = np.zeros((a.shape[0], nb + 1), np.uint8); z[:, :nb] = a; z.tofile(f)
     return nq
 
 
-def run_ref_bench(p, threads, seconds, path=None, total_queries=None):
-    """Times the reference on a bounded sample; returns (cells/s, description dict)."""
+REF_MODES = {0: "create_codon_to_codon_HLA + initialise_F_numerical_recipes + llk per query",
+             2: "update_B_numerical_recipes (update = S-1) alone",
+             3: "window proposal: update_F_numerical_recipes over S/6 sites + sum_r tmp_F*B",
+             4: "one-column proposal: update_F_numerical_recipes at one site + sum_r tmp_F*B",
+             5: "closest-L: hamming_distance_considering_unknown + closest_sequences per query"}
+CPU_SAMPLE_QUERIES = 200      # time >= 200 queries of the large shapes, scale linearly in Q
+
+
+def run_ref_bench(p, threads, seconds, path=None, total_queries=None, mode=0, seqs=None):
+    """Times the reference's own objects on a bounded sample; returns (units/s, description dict).  Units are
+    cells (nt-compares in mode 5)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
     if not os.path.exists(exe):
         return None, {"error": "oracle/_ref/ref_bench missing"}
@@ -183,23 +214,53 @@ def run_ref_bench(p, threads, seconds, path=None, total_queries=None):
     if own:
         fd, path = tempfile.mkstemp(suffix=".bin")
         os.close(fd)
-    nq = write_ref_problem(p, path, max(threads * 4, 64))
+        write_ref_problem(p, path, max(CPU_SAMPLE_QUERIES, threads * 4), seqs)
+    nq = min(p.Q, max(CPU_SAMPLE_QUERIES, threads * 4))
+    if mode == 5:
+        nq = min(nq, max(threads, 16))      # 0.36 s per query per core: one query per thread is a sample already
 
     def once(reps):
-        out = subprocess.run([exe, path, str(threads), str(nq), "0", str(reps)], capture_output=True, text=True,
+        out = subprocess.run([exe, path, str(threads), str(nq), str(mode), str(reps)], capture_output=True, text=True,
                              check=True).stdout
         return json.loads(out.strip().splitlines()[-1])
 
     probe = once(1)
-    reps = max(1, int(seconds / max(probe["seconds"], 1e-3)))
+    reps = max(1, int(seconds / max(probe["wall_seconds"], 1e-3)))
     res = once(reps) if reps > 1 else probe
     if own:
         os.unlink(path)
-    desc = dict(kind="reference", cores=threads, value=res["cells_per_s"], unit=UNIT,
-                sample=f"{nq} of {total_queries or p.Q} queries x {reps} repeats ({res['seconds']:.1f} s): "
-                       f"create_codon_to_codon_HLA + initialise_F_numerical_recipes + llk per query, "
-                       f"reference objects built -O3 (oracle/Makefile), {threads} host threads over query shards")
+    desc = dict(kind="reference", cores=threads, value=res["cells_per_s"], unit=UNIT if mode != 5 else "nt-compares/s",
+                sample=f"{nq} of {total_queries or p.Q} queries x {reps} repeats ({res['wall_seconds']:.1f} s): "
+                       f"{REF_MODES[mode]}, reference objects built -O3 (oracle/Makefile), {threads} host "
+                       f"thread{'s' if threads > 1 else ''} over query shards" +
+                       ("; every thread re-runs its ~%d queries, so its working set (one F matrix) stays in cache: "
+                        "generous to the CPU" % max(1, nq // threads) if reps > 1 and mode == 0 else ""))
     return res["cells_per_s"], desc
+
+
+def cpu_baseline_suite(p, seconds, seqs, total_queries):
+    """the headline region on all host cores and on one core, plus backward / window /
+    column / closest-L, every one the reference's own objects on a sample of the same workload."""
+    ncpu = os.cpu_count() or 1
+    fd, path = tempfile.mkstemp(suffix=".bin")
+    os.close(fd)
+    try:
+        write_ref_problem(p, path, max(CPU_SAMPLE_QUERIES, ncpu * 4), seqs)
+        v, desc = run_ref_bench(p, ncpu, seconds, path, total_queries)
+        if v is None:
+            return {"value": None, "unit": UNIT, "cores": ncpu, "kind": "reference", "sample": desc["error"]}
+        other = {}
+        v1, d1 = run_ref_bench(p, 1, min(4.0, seconds), path, total_queries)
+        other["one_core"] = {"value": v1, "unit": UNIT, "cores": 1, "sample": d1["sample"]}
+        for key, mode in (("backward_fill", 2), ("window_proposal", 3), ("single_site_proposal", 4), ("closest_L", 5)):
+            if mode == 5 and seqs is None:
+                continue
+            vm, dm = run_ref_bench(p, ncpu, min(3.0, seconds), path, total_queries, mode=mode)
+            other[key] = {"value": vm, "unit": dm["unit"], "cores": ncpu, "sample": dm["sample"]}
+        desc["other_regions"] = other
+        return desc
+    finally:
+        os.unlink(path)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -207,32 +268,52 @@ def run_ref_bench(p, threads, seconds, path=None, total_queries=None):
 # to the reference dmodel on the host CPU, same files, same seeds, default move mix with annealing
 # ------------------------------------------------------------------------------------------------
 def mcmc_steps_per_s(workload, steps, ref_steps=12,
-                     variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]), ("gpu_sparse_esc", ["--sparse_esc"]))):
+                     variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]), ("gpu_sparse_esc", ["--sparse_esc"])),
+                     rank=0, world=1, dist=None):
+    """Runs the C driver (one process per rank, started by every bench rank with its own RANK / LOCAL_RANK) on
+    files written by rank 0; rank 0 returns the figures, the others None."""
     import re
     import shutil
+    import uuid
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from chain_files import make_chain_inputs
     driver = os.path.join(ROOT, "mcqueen_b200", "host", "mcq_dmodel")
     if not os.path.exists(driver):
         return {"error": "mcqueen_b200/host/mcq_dmodel not built"}
-    tmp = tempfile.mkdtemp(prefix="mcq_mcmc_")
-    out = {"workload": workload, "steps": steps,
+    box = [None, None]
+    if rank == 0:
+        box = [tempfile.mkdtemp(prefix="mcq_mcmc_"), uuid.uuid4().hex[:12]]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    tmp, tag = box
+    out = {"workload": workload, "steps": steps, "n_gpus": world,
            "variants": "gpu = driver defaults (escape-window proposals re-evaluate carriers only when the shard is "
                        "large enough to be bound by bytes); dense_esc = every query, as the reference; eager_refill = "
                        "dense_esc with the reference's refill after every accept"}
     try:
-        paths, L, _ = make_chain_inputs(os.path.join(tmp, "in"), workload, seed=SEED, query_model="dsim")
+        paths = L = None
+        if rank == 0:
+            paths, L, _ = make_chain_inputs(os.path.join(tmp, "in"), workload, seed=SEED, query_model="dsim")
+        if world > 1:
+            pl = [paths, L]
+            dist.broadcast_object_list(pl, src=0)
+            paths, L = pl
         out["data"] = "queries drawn from the model itself (dsim recipe, mcqueen_b200/synth.py)"
         base = ["-H", paths["hla"], "-l", str(L), "-s", "1000000", paths["ref"], paths["query"]]
-        for key, extra in variants:
+        for i, (key, extra) in enumerate(variants):
+            env = dict(os.environ, MCQ_RUN_TAG=f"{tag}{i}")
             r = subprocess.run([driver, "--seed", "1", "--gsl_seed", "1", "-n", str(steps)] + extra + base +
-                               [os.path.join(tmp, key)], capture_output=True, text=True)
+                               [os.path.join(tmp, f"{key}_r{rank}")], capture_output=True, text=True, env=env)
             m = re.search(r"MCMC loop: (\d+) steps in ([0-9.]+) s = ([0-9.]+) steps/s", r.stdout)
             out[key + "_steps_per_s"] = float(m.group(3)) if m else None
+            m2 = re.search(r"final log-likelihood: (\S+)", r.stdout)
+            out[key + "_final_llk"] = float(m2.group(1)) if m2 else None
             if not m:
                 out[key + "_error"] = (r.stdout + r.stderr)[-300:]
+            if world > 1:
+                dist.barrier()
         ref = os.path.join(ROOT, "oracle", "_ref", "dmodel_ref")
-        if os.path.exists(ref) and ref_steps > 0:
+        if rank == 0 and os.path.exists(ref) and ref_steps > 0:
             env = dict(os.environ, MCQ_SEED="1", MCQ_GSL_SEED="1")
             t = []
             for n in (1, 1 + ref_steps):     # the difference removes the start-up (closest-L, initial F/B)
@@ -244,8 +325,11 @@ def mcmc_steps_per_s(workload, steps, ref_steps=12,
             out["reference_cpu"] = f"unmodified reference dmodel, 1 core, {ref_steps} steps after start-up " \
                                    f"({t[0]:.1f} s start-up incl. closest-L and initial F/B)"
     finally:
-        shutil.rmtree(tmp, ignore_errors=True)
-    return out
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return out if rank == 0 else None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -285,6 +369,7 @@ def main():
         vals = []
         desc = None
         per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+        write_ref_problem(p, path, p.Q)
         for i in range(args.warmup + args.steps):
             v, desc = run_ref_bench(p, ncpu, per_step, path, total_queries=Qtot)
             if v is None:
@@ -311,9 +396,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the McQueen path has no CPU fallback")
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL's INFO log (communicator size, transports) is part of the record; it goes to stderr so that stdout
+        # stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("gloo", rank=rank, world_size=world)
     dev = local_rank
     # the clock sampler starts before the set-up: nvidia-smi needs a second or two before its first line
@@ -324,14 +411,15 @@ def main():
     p = build_shard(args.workload, q0, q1, dev)
     ctx = api.Context.from_problem(p, device=dev)
     comm_kind = os.environ.get("MCQ_BENCH_COMM", "peer") if world > 1 else "none"
-    if comm_kind == "peer":       # shard totals exchanged by NVLink peer stores inside the reduction kernel
+    if world > 1:
+        # both exchanges are attached: the headline runs on `comm_kind`, the other one is timed beside it
         handles = [None] * world
         dist.all_gather_object(handles, ctx.peer_handle())
         ctx.attach_peers(world, rank, handles)
-    elif comm_kind == "nccl":     # one ncclAllReduce of one double
         ids = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.attach_comm(world, rank, ids[0])
+        ctx.set_option(api.OPT_EXCHANGE, 1 if comm_kind == "nccl" else 0)
     log(f"[bench] rank {rank}: context holds {ctx.device_bytes() / 2**30:.1f} GiB")
 
     def barrier():
@@ -376,6 +464,57 @@ def main():
     clocks = clk.summary(mark0, mark1)
     assert abs(llk - llk0) <= 1e-12 * abs(llk0), (llk, llk0)
 
+    # ---- the other exchange of the shard totals, timed beside the headline (same steps, same problem):
+    # north_star names one NCCL all-reduce, the default is the peer-mailbox store fused into the reduction kernel
+    exchange_cmp = None
+    if world > 1:
+        other = "nccl" if comm_kind == "peer" else "peer"
+        ctx.set_option(api.OPT_EXCHANGE, 1 if other == "nccl" else 0)
+        for _ in range(3):
+            ctx.full_llk(True)
+        barrier()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            llk_other = ctx.full_llk(True)
+        ms_other = ctx.timer_stop()
+        barrier()
+        ctx.set_option(api.OPT_EXCHANGE, 1 if comm_kind == "nccl" else 0)
+        assert abs(llk_other - llk0) <= 1e-12 * abs(llk0), (llk_other, llk0)
+        exchange_cmp = (other, ms_other, llk_other)
+
+    # ---- the sharded evaluation IS the single-GPU evaluation: (a) the total against the value recorded from a
+    # one-GPU run of this workload (profiles/llk_single_gpu.json), (b) a sample of queries spread over all shards,
+    # re-evaluated in a one-GPU context of their own on rank 0, against the shards' per-query values bit for bit
+    per_q_all = [ctx.query_llk()]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_q_all[0])
+        per_q_all = gathered
+    identity = None
+    if rank == 0:
+        per_q_all = np.concatenate(per_q_all)
+        sample = np.unique(np.linspace(0, Qtot - 1, min(Qtot, CPU_SAMPLE_QUERIES)).astype(np.int64))
+        f = p.full
+        ps = prep.build_problem(f["refs"], np.ascontiguousarray(f["queries"][sample]), f["hla"][sample],
+                                np.ascontiguousarray(f["closest"][sample]),
+                                cons_q=api.consensus_batch(f["refs"], np.ascontiguousarray(f["closest"][sample]), device=dev))
+        prep.random_parameters(ps, seed=1)
+        cs = api.Context.from_problem(ps, device=dev)
+        cs.full_llk(True)
+        per_s = cs.query_llk()
+        cs.close()
+        identity = {"sample_queries": int(sample.size), "sample_bit_identical": bool(np.array_equal(per_s, per_q_all[sample])),
+                    "sample_max_rel_diff": float(np.max(np.abs(per_s - per_q_all[sample]) / np.abs(per_s)))}
+        rec_path = os.path.join(ROOT, "profiles", "llk_single_gpu.json")
+        rec = json.load(open(rec_path)).get(args.workload) if os.path.exists(rec_path) else None
+        if rec is not None and rec.get("seed") == SEED:
+            identity["single_gpu_llk"] = rec["llk"]
+            identity["total_rel_diff"] = abs(llk0 - rec["llk"]) / abs(rec["llk"])
+            identity["total_matches"] = bool(identity["total_rel_diff"] <= 1e-12)
+        log(f"[bench] sharded == single-GPU: {identity}")
+    seqs_sample = (p.full["refs"], np.ascontiguousarray(p.full["queries"][q0:q0 + 1024]))
+    p.full = None
+
     # ---- e2e: everything from (pinned) host buffers every step, per-query results back
     host_arrays = [p.ref_triplets, p.closest_refs, p.cons_query_nucls, p.query_codons, p.hla]
     for a in host_arrays:
@@ -383,7 +522,7 @@ def main():
     rate_out = p.rate_out_of_codons()
     # per rank; with the peer exchange attached each rank DMAs 1/world of the reference panel and reads the
     # rest from its peers over NVLink (MCQ_OPT_SHARED_PANEL)
-    panel_share = p.ref_triplets.nbytes // world if comm_kind == "peer" else p.ref_triplets.nbytes
+    panel_share = p.ref_triplets.nbytes // world
     h2d = panel_share + sum(a.nbytes for a in host_arrays[1:]) + p.consensus_codons.nbytes + \
         p.n_site_codons.nbytes + p.site_codons.nbytes + 8 * (64 + 2 * S + 64 * S + H * S + S)
     d2h = 8 * p.Q + 8
@@ -467,7 +606,8 @@ def main():
         ctx.enable_timing(0)
 
     # ---- gather over ranks (max time)
-    stats = np.array([ms_dev, t_wall, ms_e2e_dev, t_e2e, fwd_ms / max(fwd_n, 1)], np.float64)
+    stats = np.array([ms_dev, t_wall, ms_e2e_dev, t_e2e, fwd_ms / max(fwd_n, 1),
+                      exchange_cmp[1] if exchange_cmp else 0.0], np.float64)
     per_rank = [stats.tolist()]
     if world > 1:
         gathered = [None] * world
@@ -480,6 +620,7 @@ def main():
     ms_step_wall = stats[1] / args.steps
     ms_e2e = max(stats[2], stats[3]) / args.steps
     fwd_ms_avg = stats[4]
+    ms_other_max = stats[5]
 
     if rank == 0:
         total_cells = Qtot * S * L
@@ -492,12 +633,14 @@ def main():
         bytes_per_cell = 9.0 + 520.0 / L
         alg_bytes = bytes_per_cell * p.Q * S * L
         achieved = alg_bytes / (fwd_ms_avg * 1e-3) / 1e9
-        traffic = None
+        traffic = traffic_src = None
         tpath = os.path.join(ROOT, "profiles", "forward_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("workload") == args.workload and tj.get("queries_per_gpu") == p.Q:
                 traffic = tj["dram_bytes_per_launch"]
+                traffic_src = "recorded, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one " \
+                              "k_forward launch of this shape under ncu --set full (" + tj.get("source", "profiles/") + ")"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -510,9 +653,10 @@ def main():
                     "what": "mcq_ctx_upload_static + mcq_ctx_set_params + mcq_ctx_full_llk + per-query llk "
                             "read-back, all inputs from pinned host buffers every step, MCQ_OPT_ASYNC_UPLOAD=2: the calls queue "
                             "the DMAs and the evaluation follows them and the device-side set-up chunk by chunk (bytes per rank" +
-                            ("; the reference panel is DMA'd in 1/N slices and completed over NVLink)" if world > 1 and comm_kind == "peer" else ")")},
+                            ("; the reference panel is DMA'd in 1/N slices and completed over NVLink)" if world > 1 else ")")},
             "roofline": {"bound": "hbm", "kernel": "k_forward", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": bytes_per_cell, "launch_ms": fwd_ms_avg,
                          "cells_per_launch": p.Q * S * L},
             "ms_per_step_wall": ms_step_wall, "llk": llk0, "extras": extras,
@@ -521,19 +665,35 @@ def main():
             "kernel_share": {"forward_ms_per_step": fwd_ms / max(args.steps, 1),
                              "emission_ms_per_step": emi_ms},
         }
-        if world == 1 and not args.no_mcmc:
-            ctx.close()          # frees the C4 context before the driver allocates its own
-            line["mcmc"] = mcmc_steps_per_s("C2", args.mcmc_steps)
-            # the same driver at the headline shape (no CPU side: the reference would need hours)
-            line["mcmc_c4"] = mcmc_steps_per_s(args.workload, 600, ref_steps=0,
-                                               variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]),
-                                                         ("gpu_sparse_esc", ["--sparse_esc"]),
-                                                         ("gpu_eager_refill", ["--dense_esc", "--eager_refill"])))
+        line["llk_matches_single_gpu"] = bool(identity.get("total_matches", False) and identity["sample_bit_identical"])
+        line["single_gpu_identity"] = identity
+        if exchange_cmp is not None:
+            other, ms_other, llk_other = exchange_cmp
+            line["exchange_comparison"] = {
+                "headline": comm_kind, "other": other, "other_ms_per_step": ms_other_max / args.steps,
+                "other_value": total_cells / (ms_other_max / args.steps * 1e-3), "other_llk": llk_other,
+                "nccl_nranks": world,
+                "what": "the same K steps with the shard totals exchanged the other way (peer = NVLink stores into the "
+                        "peers' mailboxes inside the reduction kernel; nccl = k_sum + one ncclAllReduce of one double + "
+                        "publish kernel); NCCL's INFO log of this communicator is on stderr"}
         if world == 1 and args.cpu_seconds > 0:
-            ncpu = os.cpu_count() or 1
-            v, desc = run_ref_bench(p, ncpu, args.cpu_seconds)
-            line["cpu_baseline"] = desc if v is not None else {"value": None, "unit": UNIT, "cores": ncpu,
-                                                               "kind": "reference", "sample": desc["error"]}
+            line["cpu_baseline"] = cpu_baseline_suite(p, args.cpu_seconds, seqs_sample, Qtot)
+    # ---- dmodel MCMC steps/s (the second half of the metric) at this number of GPUs: every rank starts the
+    # driver for its GPU once the bench context has released the memory
+    if not args.no_mcmc:
+        ctx.close()
+        mc = mcmc_steps_per_s("C2", args.mcmc_steps, ref_steps=12 if world == 1 else 0, rank=rank, world=world,
+                              dist=dist if world > 1 else None,
+                              variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]), ("gpu_sparse_esc", ["--sparse_esc"]))
+                              if world == 1 else (("gpu", []),))
+        mc4 = mcmc_steps_per_s(args.workload, 600, ref_steps=0, rank=rank, world=world, dist=dist if world > 1 else None,
+                               variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]),
+                                         ("gpu_sparse_esc", ["--sparse_esc"]),
+                                         ("gpu_eager_refill", ["--dense_esc", "--eager_refill"])) if world == 1 else
+                               (("gpu", []), ("gpu_dense_esc", ["--dense_esc"])))
+        if rank == 0:
+            line["mcmc"], line["mcmc_c4"] = mc, mc4
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -543,31 +703,30 @@ def main():
 
 
 def build_problem_cpu(name, ncpu):
-    """Reference arm only: a problem for ref_bench without needing the exact closest-L lists of the
-    full workload (the CPU sample covers a few hundred queries).  Closest lists come from the GPU
-    library when a device is present, else from the oracle on the sampled queries."""
+    """Reference arm only: a problem for ref_bench on a sample of the workload's queries, built WITHOUT the product
+    library: distances and closest-L lists come from the compiled reference (oracle/_ref/libmcq_ref.so, else the C
+    oracle), Hamming rows over host threads, the tie shuffles in query order."""
+    from concurrent.futures import ThreadPoolExecutor
     cfg = workload_dims(name)
     L = cfg["L"]
     data = make_data(name)
-    nq = min(cfg["Q"], max(ncpu * 4, 64))
+    nq = min(cfg["Q"], max(CPU_SAMPLE_QUERIES, ncpu * 4))
     refs, qs, hla = data["ref_seqs"], np.ascontiguousarray(data["query_seqs"][:nq]), data["hla"][:nq]
-    import ctypes
-    ctypes.CDLL("libc.so.6").srandom(SEED & 0x7fffffff)
-    closest = None
-    try:
-        import torch
-        if torch.cuda.is_available():
-            from mcqueen_b200 import api
-            closest = api.closest_batch(refs, qs, L)
-    except Exception:
-        closest = None
-    if closest is None:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import cpu_libs
-        orc = cpu_libs.Checker("ref" if cpu_libs.have_ref() else "oracle")
-        closest = np.stack([orc.closest(orc.hamming(refs, qs[q]), L) for q in range(nq)])
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_libs
+    orc = cpu_libs.Checker("ref" if cpu_libs.have_ref() else "oracle")
+    skip = name in synth.SELF_REFERENCE
+    cpu_libs.srandom(SEED & 0x7fffffff)
+    closest = np.zeros((nq, L), np.int32)
+    with ThreadPoolExecutor(max_workers=ncpu) as ex:      # ctypes releases the GIL: one Hamming row per thread
+        for q0 in range(0, nq, 4 * ncpu):
+            rows = list(ex.map(lambda q: orc.hamming(refs, qs[q]), range(q0, min(nq, q0 + 4 * ncpu))))
+            for i, ham in enumerate(rows):
+                c = orc.closest(ham, L + 1 if skip else L)
+                closest[q0 + i] = c[1:] if skip else c
     p = prep.build_problem(refs, qs, hla, closest)
     prep.random_parameters(p, seed=1)
+    p.seqs = (refs, qs)
     return p
 
 

@@ -207,6 +207,8 @@ enum {
                               2: the upload does not wait for the DMAs either (the cudaMemcpyAsync contract:
                               the caller keeps its page-locked buffers unchanged until the next
                               mcq_ctx_full_llk, evaluation or mcq_ctx_synchronize has returned). */
+  MCQ_OPT_EXCHANGE = 6,     /* which exchange carries the shard totals when both are attached: 0 (default) the
+                              peer mailboxes, 1 the NCCL all-reduce */
   MCQ_OPT_UPLOAD_CHUNK_QUERIES = 5 /* default 1250: mcq_ctx_upload_static transfers and sets up the per-query
                               data in up to 8 chunks of at least this many queries (one chunk = no
                               pipelining; smaller chunks starve the kernels that follow them). */

@@ -26,6 +26,7 @@ OPT_LAZY_REFILL = 2
 OPT_SHARED_PANEL = 3
 OPT_ASYNC_UPLOAD = 4
 OPT_UPLOAD_CHUNK_QUERIES = 5
+OPT_EXCHANGE = 6
 K_GATHER, K_EMISSION, K_FORWARD, K_BACKWARD, K_COMMIT, K_SUM = range(6)
 
 

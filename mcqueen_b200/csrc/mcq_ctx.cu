@@ -175,6 +175,7 @@ struct mcq_ctx {
   const int8_t *peer_trip[16] = {nullptr};
   unsigned long long bar_seq = 0;
   int opt_shared_panel = 1;         // MCQ_OPT_SHARED_PANEL
+  int opt_exchange = 0;             // MCQ_OPT_EXCHANGE
   void *peer_map[16] = {nullptr};   // IPC mappings of the peers' mailboxes
   bool have_peers = false;
   unsigned long long step = 0;
@@ -444,6 +445,7 @@ extern "C" int mcq_ctx_set_option(mcq_ctx *c, int option, int value) {
   if (option == MCQ_OPT_SPARSE_ESC) { c->opt_sparse_esc = value; return 0; }
   if (option == MCQ_OPT_SHARED_PANEL) { c->opt_shared_panel = value; return 0; }
   if (option == MCQ_OPT_ASYNC_UPLOAD) { c->opt_async_upload = value; return 0; }
+  if (option == MCQ_OPT_EXCHANGE) { c->opt_exchange = value; return 0; }
   if (option == MCQ_OPT_UPLOAD_CHUNK_QUERIES) {
     REQUIRE(value >= 1, "chunk size must be positive");
     c->opt_chunk_queries = value;
@@ -844,7 +846,7 @@ static int reduce_llk(mcq_ctx *c, const double *per_query, double *out, cudaStre
   if (st == nullptr) st = c->stream;
   if (n < 0) n = c->d.num_query;
   const unsigned long long want = ++c->eval_seq;
-  if (c->have_peers) {
+  if (c->have_peers && !(c->opt_exchange == 1 && c->comm)) {
     // shard total + NVLink mailbox exchange in one kernel
     {
       KScope ks(c, MCQ_K_SUM);
@@ -863,11 +865,12 @@ static int reduce_llk(mcq_ctx *c, const double *per_query, double *out, cudaStre
   if (c->comm) {
     int r = g_nccl.AllReduce(c->d_sum, c->d_sum, 1, kNcclDouble, kNcclSum, c->comm, st);
     if (r != 0) return mcq_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce failed");
-    CK(cudaMemcpyAsync(c->h_sum, c->d_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    REQUIRE(*c->h_err == 0, "device error flag set (closest_refs out of range in the last mcq_ctx_upload_static?)");
-    if (out) *out = *c->h_sum;
+    // the reduced value reaches the host through the mapped slot, as on the other paths (no copy + stream wait)
+    CK(mcq_launch_sum(c->d_sum, 1, c->d_sum, c->d_slot, want, c->d_err, st));
+    c->launches++;
+    if (wait_slot(c, want, st)) return 1;
+    if (slot_error(c)) return 1;
+    if (out) *out = c->h_slot->value;
     return 0;
   }
   if (wait_slot(c, want, st)) return 1;

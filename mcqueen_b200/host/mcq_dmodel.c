@@ -446,8 +446,11 @@ static void blob_path(char *path, size_t n, const char *tag, int r)
 {
   /* the launcher's pid is common to the ranks of one launch and differs between launches, so files a
    * crashed earlier run left behind are never picked up */
-  snprintf(path, n, "/tmp/mcq_%s_%s_%s_%ld_%d", tag, getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0",
-           getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : "run", (long)getppid(), r);
+  const char *run = getenv("MCQ_RUN_TAG");      /* ranks started by different parents name their launch themselves */
+  char ppid[32];
+  snprintf(ppid, sizeof(ppid), "%ld", (long)getppid());
+  snprintf(path, n, "/tmp/mcq_%s_%s_%s_%s_%d", tag, getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0",
+           getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : "run", run ? run : ppid, r);
 }
 
 static void blob_put(const char *tag, int r, const unsigned char *data, size_t len)
