@@ -395,12 +395,16 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the McQueen path has no CPU fallback")
+    # stdout carries the one JSON line and nothing else: whatever the libraries print there (NCCL writes its log
+    # to stdout) is sent to stderr, the line goes out through a duplicate of the original descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL's INFO log (communicator size, transports) is part of the record; it goes to stderr so that stdout
-        # stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's INFO log (communicator size, transports) is part of the record (it lands on stderr, see below)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("gloo", rank=rank, world_size=world)
     dev = local_rank
     # the clock sampler starts before the set-up: nvidia-smi needs a second or two before its first line
@@ -694,7 +698,7 @@ def main():
         if rank == 0:
             line["mcmc"], line["mcmc_c4"] = mc, mc4
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
