@@ -209,6 +209,17 @@ enum {
                               mcq_ctx_full_llk, evaluation or mcq_ctx_synchronize has returned). */
   MCQ_OPT_EXCHANGE = 6,     /* which exchange carries the shard totals when both are attached: 0 (default) the
                               peer mailboxes, 1 the NCCL all-reduce */
+  MCQ_OPT_WARPS_PER_QUERY = 7, /* 0: the sweeps run one warp per query (bound by the HBM when the GPU holds many
+                              queries).  W = 1, 2, 4 or 8 (NJ/2 or NJ for NJ = ceil(closest_n/64) groups of 64 copy
+                              states): a block of W consumer warps + one warp that stages the rows owns a query,
+                              which shortens the dependent instruction stream per site - for GPUs that hold few
+                              queries.  Set it before mcq_ctx_init_state: the grouping of the per-site sums, and
+                              with it the last bits of every value, follows the choice. */
+  MCQ_OPT_PIPELINE_MAX_QUERIES = 8, /* a sweep launch that runs at most this many queries (the shard, or the carriers
+                              of one HLA type) uses the software-pipelined kernels: with few warps per SM a sweep
+                              costs the length of one warp's dependent chain per site, and there the look-ups of
+                              the next site travel under the butterfly of the current one.  Same bits either way.
+                              Default: see mcq_ctx.cu (measured cross-over); 0 = never. */
   MCQ_OPT_UPLOAD_CHUNK_QUERIES = 5 /* default 1250: mcq_ctx_upload_static transfers and sets up the per-query
                               data in up to 8 chunks of at least this many queries (one chunk = no
                               pipelining; smaller chunks starve the kernels that follow them). */

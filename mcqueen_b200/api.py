@@ -27,6 +27,8 @@ OPT_SHARED_PANEL = 3
 OPT_ASYNC_UPLOAD = 4
 OPT_UPLOAD_CHUNK_QUERIES = 5
 OPT_EXCHANGE = 6
+OPT_WARPS_PER_QUERY = 7
+OPT_PIPELINE_MAX_QUERIES = 8
 K_GATHER, K_EMISSION, K_FORWARD, K_BACKWARD, K_COMMIT, K_SUM = range(6)
 
 

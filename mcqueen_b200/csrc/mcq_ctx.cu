@@ -176,6 +176,9 @@ struct mcq_ctx {
   unsigned long long bar_seq = 0;
   int opt_shared_panel = 1;         // MCQ_OPT_SHARED_PANEL
   int opt_exchange = 0;             // MCQ_OPT_EXCHANGE
+  int pipe_max = 0;                 // launches that run at most this many queries use the pipelined sweep kernels
+  std::vector<int> carriers;        // queries carrying each HLA type (host count)
+  int wpq = 0;                      // MCQ_OPT_WARPS_PER_QUERY: 0 = the one-warp sweeps, else consumer warps per query
   void *peer_map[16] = {nullptr};   // IPC mappings of the peers' mailboxes
   bool have_peers = false;
   unsigned long long step = 0;
@@ -284,6 +287,7 @@ extern "C" int mcq_ctx_create(mcq_ctx **out, const mcq_dims *dims) {
   c->Lg = 64;
   while (c->Lg < c->Ls) c->Lg *= 2;   // 64 * NJ, NJ in {1,2,4,8,16}
   c->logBIG = log(MCQ_BIG);   // the host libm value the reference itself uses (mcmc_moves.c:223)
+  if (getenv("MCQ_PIPE_MAX")) c->pipe_max = atoi(getenv("MCQ_PIPE_MAX"));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -446,6 +450,15 @@ extern "C" int mcq_ctx_set_option(mcq_ctx *c, int option, int value) {
   if (option == MCQ_OPT_SHARED_PANEL) { c->opt_shared_panel = value; return 0; }
   if (option == MCQ_OPT_ASYNC_UPLOAD) { c->opt_async_upload = value; return 0; }
   if (option == MCQ_OPT_EXCHANGE) { c->opt_exchange = value; return 0; }
+  if (option == MCQ_OPT_PIPELINE_MAX_QUERIES) { c->pipe_max = value; return 0; }
+  if (option == MCQ_OPT_WARPS_PER_QUERY) {
+    REQUIRE(value == 0 || mcq_mw_supported(c->Lg / 64, value), "this number of warps per query is not built for this closest_n");
+    // the grouping of the per-site column sum changes with it: F, B and the cached per-query values of one state
+    // must all come from one grouping
+    REQUIRE(!c->have_state || value == c->wpq, "set MCQ_OPT_WARPS_PER_QUERY before mcq_ctx_init_state");
+    c->wpq = value;
+    return 0;
+  }
   if (option == MCQ_OPT_UPLOAD_CHUNK_QUERIES) {
     REQUIRE(value >= 1, "chunk size must be positive");
     c->opt_chunk_queries = value;
@@ -620,6 +633,9 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
   }
   c->hla_h.resize((size_t)Q * H);
   for (size_t i = 0; i < c->hla_h.size(); i++) c->hla_h[i] = hla_types[i] == '1';
+  c->carriers.assign(H, 0);
+  for (int q = 0; q < Q; q++)
+    for (int h = 0; h < H; h++) c->carriers[h] += c->hla_h[(size_t)q * H + h];
   c->have_state = false;
   c->have_fwd = false;
   c->has_pending = false;
@@ -765,7 +781,7 @@ enum FwdMode {
 static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int start, int end, FwdMode mode, int llk_mode,
                        double *llk_out, int r_site, double r_value, bool sparse, int hla, bool lazy = false,
                        bool mark_end = false, int *tuned_blocks = nullptr) {
-  FwdArgs a;
+  FwdArgs a{};
   a.st = make_static(c);
   a.em.tab = tab; a.em.ec = ec; a.R = c->m.R; a.r_site = r_site; a.r_value = r_value;
   a.em_pre.tab = c->tab; a.em_pre.ec = c->ec;
@@ -779,8 +795,12 @@ static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int star
   a.B = c->B; a.Bn = c->Bn; a.llk_out = llk_out; a.llk_keep = c->llk_cur;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
   a.logBIG = c->logBIG;
+  a.pipe = (sparse ? c->carriers[hla] : c->d.num_query) <= c->pipe_max;
   KScope ks(c, MCQ_K_FORWARD);
-  if (tuned_blocks != nullptr) CK(mcq_tune_forward(a, c->stream, tuned_blocks, nullptr));
+  if (c->wpq > 0) {
+    if (tuned_blocks != nullptr) *tuned_blocks = 0;      // (the residency sweep is for the one-warp kernels)
+    CK(mcq_launch_forward_mw(a, c->wpq, c->stream));
+  } else if (tuned_blocks != nullptr) CK(mcq_tune_forward(a, c->stream, tuned_blocks, nullptr));
   else CK(mcq_launch_forward(a, c->stream));
   return 0;
 }
@@ -790,19 +810,24 @@ static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int star
 static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream_t stream = nullptr,
                         bool lazy = false, int bottom = 0, int *tuned_blocks = nullptr) {
   if (stream == nullptr) stream = c->stream;
-  BwdArgs a;
+  BwdArgs a{};
   a.st = make_static(c);
   a.em.tab = c->tab; a.em.ec = c->ec; a.R = c->m.R; a.B = c->B; a.Bn = c->Bn; a.update = update;
   a.bottom = bottom; a.bv = lazy ? c->bv : nullptr;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
+  a.pipe = (sparse ? c->carriers[hla] : c->d.num_query) <= c->pipe_max;
   if (stream != c->stream) {          // beside the main stream: counted, not bracketed
     c->launches++;
     c->k_n[MCQ_K_BACKWARD]++;
-    CK(mcq_launch_backward(a, stream));
+    if (c->wpq > 0) CK(mcq_launch_backward_mw(a, c->wpq, stream));
+    else CK(mcq_launch_backward(a, stream));
     return 0;
   }
   KScope ks(c, MCQ_K_BACKWARD);
-  if (tuned_blocks != nullptr) CK(mcq_tune_backward(a, c->stream, tuned_blocks, nullptr));
+  if (c->wpq > 0) {
+    if (tuned_blocks != nullptr) *tuned_blocks = 0;
+    CK(mcq_launch_backward_mw(a, c->wpq, c->stream));
+  } else if (tuned_blocks != nullptr) CK(mcq_tune_backward(a, c->stream, tuned_blocks, nullptr));
   else CK(mcq_launch_backward(a, c->stream));
   return 0;
 }
@@ -992,7 +1017,7 @@ static int full_llk_pipelined(mcq_ctx *c, int with_emission, double *llk) {
       c->launches++; c->k_n[MCQ_K_EMISSION]++;
       CK(mcq_launch_emission_cons(e, st));
     }
-    FwdArgs a;
+    FwdArgs a{};
     a.st = v;
     a.em.tab = c->tab; a.em.ec = c->ec + q0 * S; a.em_pre = a.em; a.R = c->m.R; a.r_site = -1; a.r_value = 0.0;
     a.fv = nullptr; a.mark_fv = c->fv + q0;
@@ -1001,8 +1026,10 @@ static int full_llk_pipelined(mcq_ctx *c, int with_emission, double *llk) {
     a.in_place = 1; a.no_store = 0; a.start = 0; a.end = S - 1; a.llk_mode = 2;
     a.B = c->B + q0 * S * Ls; a.Bn = c->Bn + q0 * S; a.llk_out = c->llk_cur + q0; a.llk_keep = c->llk_cur + q0;
     a.active = nullptr; a.active_hla = 0; a.logBIG = c->logBIG;
+    a.pipe = 0;
     c->launches++; c->k_n[MCQ_K_FORWARD]++;
-    CK(mcq_launch_forward(a, st));
+    if (c->wpq > 0) CK(mcq_launch_forward_mw(a, c->wpq, st));
+    else CK(mcq_launch_forward(a, st));
   }
   for (int &m : c->fv_h) m = S - 1;
   c->pipe_n = 0;
@@ -1131,6 +1158,7 @@ static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const Mcq
   d.llk_out = c->llk_prop; d.llk_keep = c->llk_cur;
   d.active = sparse ? c->hla : nullptr; d.active_hla = ov.hla;
   d.logBIG = c->logBIG;
+  d.wpq = c->wpq;
   {
     KScope ks(c, MCQ_K_SUM);
     CK(mcq_launch_dot(d, c->stream));

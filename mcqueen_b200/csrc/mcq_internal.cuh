@@ -99,6 +99,7 @@ struct FwdArgs {
   const uint8_t *active;     // [Q][H] carrier table or null
   int active_hla;            // column of `active` to test
   double logBIG;
+  int pipe;                  // 1: few queries in flight - launch the variant with the shorter per-site chain (same bits)
 };
 
 struct BwdArgs {
@@ -110,6 +111,7 @@ struct BwdArgs {
   int bottom;                // last column to compute (0 = down to the first site)
   int *bv;                   // [Q] first valid column of B per query (S = none); nullptr = use `update`
   const uint8_t *active; int active_hla;
+  int pipe;                  // as FwdArgs::pipe
 };
 
 struct DotArgs {             // per-query log-likelihood from a proposal column and the backward column
@@ -123,6 +125,7 @@ struct DotArgs {             // per-query log-likelihood from a proposal column 
   const double *llk_keep;
   const uint8_t *active; int active_hla;
   double logBIG;
+  int wpq;                          // consumer warps per query of the sweeps (0: one warp): fixes the summation order
 };
 
 struct EmisArgs {
@@ -153,6 +156,11 @@ cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
 // this kernel with this many queries; the launch itself must be repeatable (same inputs, same outputs)
 cudaError_t mcq_tune_forward(const FwdArgs &a, cudaStream_t stream, int *best_blocks, float *best_ms);
 cudaError_t mcq_tune_backward(const BwdArgs &a, cudaStream_t stream, int *best_blocks, float *best_ms);
+// the same sweeps with W consumer warps (+ one producer warp) per query (mcq_sweeps.cu); mcq_mw_supported says
+// which (NJ = Lg/64, W) pairs are built
+bool mcq_mw_supported(int NJ, int W);
+cudaError_t mcq_launch_forward_mw(const FwdArgs &a, int W, cudaStream_t stream);
+cudaError_t mcq_launch_backward_mw(const BwdArgs &a, int W, cudaStream_t stream);
 cudaError_t mcq_launch_dot(const DotArgs &a, cudaStream_t stream);
 // fv[q] := f, bv[q] := b for the queries selected by (active, hla) (all when active == nullptr); a
 // negative value leaves that array untouched

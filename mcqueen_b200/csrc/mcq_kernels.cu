@@ -16,6 +16,7 @@
 #include <mutex>
 #include <unordered_map>
 #include "mcq_internal.cuh"
+#include "mcq_sweep_common.cuh"
 #include "../../include/mcq_b200.h"
 
 // ------------------------------------------------------------------------------------------
@@ -57,12 +58,6 @@ __device__ __forceinline__ double ns_rate(double kappa, int c1, int c2) {
 __device__ __forceinline__ double s_rate(double kappa, int c1, int c2) {
   uint8_t c = d_cls[c1 * 64 + c2];
   return c == 3 ? kappa : (c == 4 ? 1.0 : 0.0);
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -414,28 +409,6 @@ cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double
   return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------------
-// asynchronous global->shared copies (LDGSTS): a warp stages the codon-slot row G[q][s][.] and the
-// emission row of the sites ahead of the one it is computing
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-#define MCQ_PF 3                 // sites staged ahead of the one being computed
-#define MCQ_RING (MCQ_PF + 1)    // ring slots per warp
-#ifndef MCQ_WPB
-#define MCQ_WPB 1                // warps (= queries) per block: small blocks balance best over the SMs
-#endif
-#define MCQ_ES 67                // doubles per staged row: emission slots 0..64, a constant 0 at MCQ_NOSLOT, R[s]
-#define MCQ_RSLOT 66             // where the site's recombination probability travels
-
-// What a warp needs to stage the emission row of (query, site) is one word of the static table rowdesc:
-// bits 0..24 the offset of row (s, to(q,s)) in TAB, bits 25..31 the entries per row K_s (0 = nothing to
-// stage, also used for sites outside the range).  The words are fetched MCQ_RING sites ahead of their use.
-#define MCQ_RD_SHIFT 25
-#define MCQ_RD_MASK 0x1FFFFFFu
-
 __global__ void __launch_bounds__(256) k_rowdesc(const McqStatic st, uint32_t *__restrict__ out, int q0, int nq) {
   const size_t i0 = (size_t)q0 * st.S, n = i0 + (size_t)nq * st.S;
   for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -472,62 +445,6 @@ cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, int q0, int n
 static_assert(MCQ_RING == 4, "the unrolled site loops assume a ring of four slots");
 
 
-// predicated forms: straight-line code, no branch around the copy
-__device__ __forceinline__ void cp_async16_if(unsigned sa, const void *gmem, bool p) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n"
-               ::"r"(sa), "l"(gmem), "r"((int)p) : "memory");
-}
-__device__ __forceinline__ void cp_async8_if(unsigned sa, const void *gmem, bool p) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}\n"
-               ::"r"(sa), "l"(gmem), "r"((int)p) : "memory");
-}
-
-// Stage the rows of one site into ring slot KS (a constant): one commit group per call, empty when the
-// site lies outside the range (its descriptor word is then 0 as well).  g_sh / e_sh: shared-window addresses
-// of the rings, already offset by this lane's 16 / 8 bytes; gsrc = the site's G row, tabl = the emission
-// table, both offset by this lane's share; ecp = the query's consensus-row value of the site (lane 0 copies
-// it), Rp = the site's recombination probability (lane 1).
-template <int NJ, int KS>
-__device__ __forceinline__ void stage_k(unsigned g_sh, unsigned e_sh, bool valid, unsigned rd,
-                                        const double *__restrict__ tabl, const double *__restrict__ ecp, bool has_ec,
-                                        const double *__restrict__ Rp, const uint8_t *__restrict__ gsrc, int lane) {
-#pragma unroll
-  for (int i = 0; i < (NJ + 7) / 8; i++)
-    cp_async16_if(g_sh + KS * (64 * NJ) + 512 * i, gsrc + 512 * i, valid && (lane + 32 * i) * 16 < 64 * NJ);
-  const int kr = (int)(rd >> MCQ_RD_SHIFT);   // at most 64 entries: two predicated copies, no loop
-  const double *row = tabl + (rd & MCQ_RD_MASK);
-  const unsigned ed = e_sh + (KS * MCQ_ES + 1) * 8;
-  cp_async8_if(ed, row, lane < kr);
-  cp_async8_if(ed + 256, row + 32, lane + 32 < kr);
-  // lane 0: the consensus-row value into slot 0; lane 1: R[s] into MCQ_RSLOT
-  const bool l0 = lane == 0;
-  cp_async8_if(l0 ? ed - 8 : ed + (MCQ_RSLOT - 2) * 8, l0 ? ecp : Rp, valid && (l0 ? has_ec : lane == 1));
-  cp_async_commit();
-}
-
-// emission of the state whose slot is byte `b` of word w, from the staged row at `row`
-__device__ __forceinline__ double emis_at(const double *row, unsigned w, int b) {
-  const unsigned slot = __byte_perm(w, 0, 0x4440 + b);
-  return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(row) + (slot << 3));
-}
-
-// the 2*NJ slot bytes a lane owns at one site, from ring slot K of the staged G rows (gl = this lane's
-// bytes in slot 0)
-template <int NJ, int K>
-__device__ __forceinline__ void load_slots(const uint8_t *gl, unsigned (&w)[(2 * NJ + 3) / 4]) {
-  const uint8_t *p = gl + K * (64 * NJ);
-  if constexpr (NJ == 1) w[0] = *reinterpret_cast<const uint16_t *>(p);
-  else if constexpr (NJ == 2) w[0] = *reinterpret_cast<const uint32_t *>(p);
-  else if constexpr (NJ == 4) { const uint2 v = *reinterpret_cast<const uint2 *>(p); w[0] = v.x; w[1] = v.y; }
-  else {
-#pragma unroll
-    for (int i = 0; i < NJ / 8; i++) {
-      const uint4 v = reinterpret_cast<const uint4 *>(p)[i];
-      w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-    }
-  }
-}
-
 template <int NJ>
 struct FwdWarp {              // what one warp carries from site to site
   double p0[NJ], p1[NJ];      // the running column
@@ -538,10 +455,14 @@ struct FwdWarp {              // what one warp carries from site to site
   // running pointers (advanced once per site, no per-site index arithmetic)
   const uint8_t *gsrc;        // G row of site t (this lane's 16 bytes)
   const uint32_t *rdp;        // descriptor word of site t + MCQ_RING
+  const uint32_t *rdsafe;     // a descriptor word that may always be read (the last site's)
   const double *Rp;           // R of site t
   double *Fs;                 // column of the site being computed in buffer 0 (this lane's states)
   int *Fnp;                   // its rescale counter (output array)
   const uint8_t *selp;        // column selector of site s + MCQ_RING
+  // the pipelined variant only: emissions and recombination probability of the site about to be computed,
+  // fetched while the previous site's butterfly was in flight
+  double e0[NJ], e1[NJ], Rs;
 };
 
 // one site of the recursion, its rows in ring slot K
@@ -559,7 +480,9 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
     // one bump per group
     const int t = w.t + K;
     const unsigned cur = w.rd[KT];
-    w.rd[KT] = (t + MCQ_RING <= a.end) ? w.rdp[K] : 0u;   // consumed four sites from now
+    // consumed four sites from now.  The load is unconditional (beyond the range: the word of the last site, ignored
+    // by stage_k): a select on the loaded VALUE would park the warp on the load's latency right here
+    w.rd[KT] = *((t + MCQ_RING <= a.end) ? w.rdp + K : w.rdsafe);
     const bool pre = PRE && t < a.start;
     const double *eq = pre ? ecq_pre : ecq;
     stage_k<NJ, KT>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.Rp + K,
@@ -610,11 +533,91 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
   }
 }
 
+// ---- the pipelined variant (PIPE).  With few warps on an SM the time of a sweep is the length of ONE warp's
+// dependent chain per site: the branch that closes a site (the rescale decision needs the butterfly's result)
+// keeps everything of the next site - wait for its rows, slot bytes, emission look-ups: two shared-memory
+// round trips - from issuing until the column sum is known.  Here a site is cut in two: its FRONT (wait for the
+// rows, stage the site three ahead, fetch this lane's emissions and R into registers) runs between the cell
+// updates of the previous site and that site's butterfly, so the look-ups travel while the shuffles do.  Same
+// operations on the same values in the same order per cell: the results are bit-identical to fwd_site's.
+template <int NJ, bool PRE, int K>
+__device__ __forceinline__ void fwd_front(const FwdArgs &a, FwdWarp<NJ> &w, int s, const uint8_t *gl, const double *ering,
+                                          unsigned g_sh, unsigned e_sh, const double *tabl, const double *tabl_pre,
+                                          const double *ecq, const double *ecq_pre, int lane) {
+  cp_async_wait<MCQ_PF - 1>();   // rows of site s have landed; the values of site s-1 are in registers already
+  __syncwarp();
+  {
+    constexpr int KT = (K + MCQ_PF) & 3;
+    const int t = w.t + K;
+    const unsigned cur = w.rd[KT];
+    w.rd[KT] = *((t + MCQ_RING <= a.end) ? w.rdp + K : w.rdsafe);
+    const bool pre = PRE && t < a.start;
+    const double *eq = pre ? ecq_pre : ecq;
+    stage_k<NJ, KT>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.Rp + K,
+                    w.gsrc + K * (64 * NJ), lane);
+    if (K == 3) { w.t += 4; w.rdp += 4; w.Rp += 4; w.gsrc += 4 * (64 * NJ); }
+  }
+  unsigned g[(2 * NJ + 3) / 4];
+  load_slots<NJ, K>(gl, g);
+  const double *es = ering + K * MCQ_ES;
+  w.Rs = (s == a.r_site) ? a.r_value : es[MCQ_RSLOT];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    w.e0[j] = emis_at(es, g[j >> 1], (j & 1) * 2);
+    w.e1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+  }
+}
+
+// the cell updates of a site from the registers fwd_front filled; returns this lane's share of the column sum
+template <int NJ>
+__device__ __forceinline__ double fwd_cells(FwdWarp<NJ> &w, double invN) {
+  const double jump = w.tot * (w.Rs * invN);
+  const double stay = 1 - w.Rs;
+  double la = 0.0, lb = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const double v0 = __fma_rn(stay, w.p0[j], jump) * w.e0[j];
+    const double v1 = __fma_rn(stay, w.p1[j], jump) * w.e1[j];
+    w.p0[j] = v0; w.p1[j] = v1;
+    la += v0; lb += v1;
+  }
+  return la + lb;
+}
+
+// butterfly, rescale, store
+template <int NJ, bool FULL, bool PRE, bool STORE, int K>
+__device__ __forceinline__ void fwd_finish(const FwdArgs &a, FwdWarp<NJ> &w, int s, double mine, int lane,
+                                           const bool (&inrow)[NJ], ptrdiff_t delta, bool has_sel, int *Fnc) {
+  w.tot = warp_sum(mine);
+  if (w.tot < MCQ_BIGI) {                       // forward_backward.c:163-167
+    ++w.cnt;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { w.p0[j] *= MCQ_BIG; w.p1[j] *= MCQ_BIG; }
+    w.tot *= MCQ_BIG;
+  }
+  if (STORE) {
+    const bool pre = PRE && s < a.start;
+    const unsigned cur1 = w.sel[K];
+    if (has_sel && s + MCQ_RING <= a.end) w.sel[K] = w.selp[K];
+    const bool into1 = (cur1 != 0) != (!a.in_place && !pre);
+    const size_t row = FULL ? (size_t)(64 * NJ) : (size_t)a.st.Ls;
+    double *__restrict__ Fs = (into1 ? w.Fs + delta : w.Fs) + K * row;
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(w.p0[j], w.p1[j]));
+    if (lane == 0) {
+      if (pre) Fnc[s] = w.cnt;
+      else w.Fnp[K] = w.cnt;
+    }
+    if (K == 3) { w.Fs += 4 * row; w.Fnp += 4; w.selp += 4; }
+  }
+}
+
 // (register caps: the stored sweep at most 120 = 17 one-warp blocks per SM, which NJ = 8 misses by two registers
 // otherwise; the likelihood-only sweep is issue-bound and wants the warps of 96; NJ = 16 and the catch-up
 // variant are exempt)
-template <int NJ, bool FULL, bool PRE, bool STORE>
-__global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE) ? (STORE ? 120 : 96) : 255) k_forward(const FwdArgs a) {
+template <int NJ, bool FULL, bool PRE, bool STORE, bool PIPE>
+__global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE && !PIPE) ? (STORE ? 120 : 96) : 255) k_forward(const FwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
   __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -685,6 +688,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE) ? 
   }
   w.gsrc = Gl + (size_t)w.t * (64 * NJ);
   w.rdp = rdq + w.t + MCQ_RING;
+  w.rdsafe = rdq + a.end;
   w.Rp = a.R + w.t;
   w.Fs = X0 + (size_t)sA * Ls;
   w.Fnp = STORE ? Fno + sA : nullptr;
@@ -731,19 +735,43 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE) ? 
     w.tot = warp_sum(loc);
   }
 
+  if constexpr (!PIPE) {
 #define MCQ_FWD_SITE(K, SITE)                                                                             \
   fwd_site<NJ, FULL, PRE, STORE, K>(a, w, SITE, gl, ering, g_sh, e_sh, tabl, tabl_pre, ecq, ecq_pre, lane, \
                                     inrow, invN, delta, has_sel, Fnc)
-  for (int s = sA; s <= a.end; s += 4) {
-    MCQ_FWD_SITE(0, s);
-    if (s + 1 > a.end) break;
-    MCQ_FWD_SITE(1, s + 1);
-    if (s + 2 > a.end) break;
-    MCQ_FWD_SITE(2, s + 2);
-    if (s + 3 > a.end) break;
-    MCQ_FWD_SITE(3, s + 3);
-  }
+    for (int s = sA; s <= a.end; s += 4) {
+      MCQ_FWD_SITE(0, s);
+      if (s + 1 > a.end) break;
+      MCQ_FWD_SITE(1, s + 1);
+      if (s + 2 > a.end) break;
+      MCQ_FWD_SITE(2, s + 2);
+      if (s + 3 > a.end) break;
+      MCQ_FWD_SITE(3, s + 3);
+    }
 #undef MCQ_FWD_SITE
+  } else {
+    // cells of site s | front of site s+1 | butterfly, rescale, store of site s
+#define MCQ_FWD_FRONT(K, SITE) \
+  fwd_front<NJ, PRE, K>(a, w, SITE, gl, ering, g_sh, e_sh, tabl, tabl_pre, ecq, ecq_pre, lane)
+#define MCQ_FWD_SITE(K, KN, SITE)                                                       \
+  {                                                                                     \
+    const double mine = fwd_cells<NJ>(w, invN);                                         \
+    if ((SITE) + 1 <= a.end) MCQ_FWD_FRONT(KN, (SITE) + 1);                             \
+    fwd_finish<NJ, FULL, PRE, STORE, K>(a, w, SITE, mine, lane, inrow, delta, has_sel, Fnc); \
+  }
+    if (sA <= a.end) MCQ_FWD_FRONT(0, sA);
+    for (int s = sA; s <= a.end; s += 4) {
+      MCQ_FWD_SITE(0, 1, s);
+      if (s + 1 > a.end) break;
+      MCQ_FWD_SITE(1, 2, s + 1);
+      if (s + 2 > a.end) break;
+      MCQ_FWD_SITE(2, 3, s + 2);
+      if (s + 3 > a.end) break;
+      MCQ_FWD_SITE(3, 0, s + 3);
+    }
+#undef MCQ_FWD_SITE
+#undef MCQ_FWD_FRONT
+  }
   cp_async_wait<0>();
   if (caught_up && lane == 0) a.fv[q] = a.start - 1;
   if (a.mark_fv != nullptr && lane == 0) a.mark_fv[q] = a.end;
@@ -863,8 +891,14 @@ static cudaError_t launch_forward_nj(const FwdArgs &a, cudaStream_t stream, bool
   const unsigned blocks = (unsigned)((a.st.Q + MCQ_WPB - 1) / MCQ_WPB);
   const bool full = a.st.Ls == 64 * NJ;
   void (*kernel)(const FwdArgs);
-  if (a.fv != nullptr) kernel = full ? k_forward<NJ, true, true, STORE> : k_forward<NJ, false, true, STORE>;
-  else kernel = full ? k_forward<NJ, true, false, STORE> : k_forward<NJ, false, false, STORE>;
+  if (a.pipe && !tune) {     // few queries in flight: the variant with the shorter per-site chain (same bits)
+    if (a.fv != nullptr) kernel = full ? k_forward<NJ, true, true, STORE, true> : k_forward<NJ, false, true, STORE, true>;
+    else kernel = full ? k_forward<NJ, true, false, STORE, true> : k_forward<NJ, false, false, STORE, true>;
+    kernel<<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
+  if (a.fv != nullptr) kernel = full ? k_forward<NJ, true, true, STORE, false> : k_forward<NJ, false, true, STORE, false>;
+  else kernel = full ? k_forward<NJ, true, false, STORE, false> : k_forward<NJ, false, false, STORE, false>;
   if (tune)
     return tune_residency((const void *)kernel, blocks, stream,
                           [&](int smem) { kernel<<<blocks, 32 * MCQ_WPB, smem, stream>>>(a); }, best_blocks, best_ms);
@@ -916,10 +950,12 @@ struct BwdWarp {
   unsigned rd[MCQ_RING];      // descriptor words of sites t .. t-3 (entry = ring slot of the site)
   const uint8_t *gsrc;        // G row of site t (this lane's 16 bytes)
   const uint32_t *rdp;        // descriptor word of site t - MCQ_RING
+  const uint32_t *rdsafe;     // a descriptor word that may always be read (the bottom site's)
   const double *ecp;          // consensus-row value of site t (unused when the rows carry none)
   const double *Rp;           // R of site t
   double *Bs;                 // output column of the site being computed
   int *Bnp;
+  double n0[NJ], n1[NJ], Rs;  // the pipelined variant only: emissions and R of the site about to be computed
 };
 
 // stage site w.t into ring slot (K + MCQ_PF) & 3 and fetch the descriptor word needed four sites on
@@ -931,7 +967,7 @@ __device__ __forceinline__ void bwd_stage(const BwdArgs &a, BwdWarp<NJ> &w, unsi
   constexpr int KT = (K + MCQ_PF) & 3;
   const int t = w.t - K;
   const unsigned cur = w.rd[KT];
-  w.rd[KT] = (t - MCQ_RING >= bottom) ? *(w.rdp - K) : 0u;
+  w.rd[KT] = *((t - MCQ_RING >= bottom) ? w.rdp - K : w.rdsafe);   // (unconditional load: see fwd_site)
   stage_k<NJ, KT>(g_sh, e_sh, t >= bottom, cur, tabl, w.ecp - K, a.em.ec != nullptr, w.Rp - K,
                   w.gsrc - K * (64 * NJ), lane);
   if (K == 3) { w.t -= 4; w.rdp -= 4; w.ecp -= 4; w.Rp -= 4; w.gsrc -= 4 * (64 * NJ); }
@@ -989,7 +1025,72 @@ __device__ __forceinline__ void bwd_site(const BwdArgs &a, BwdWarp<NJ> &w, const
   if (K == 0) { w.Bs -= 4 * row; w.Bnp -= 4; }
 }
 
-template <int NJ, bool FULL>
+// ---- the pipelined variant (see fwd_front): the front of column s-1 runs between the cell updates of column s
+// and its butterfly.  Bit-identical to bwd_site.
+template <int NJ, int K>
+__device__ __forceinline__ void bwd_front(const BwdArgs &a, BwdWarp<NJ> &w, const uint8_t *gl, const double *ering,
+                                          unsigned g_sh, unsigned e_sh, const double *tabl, int bottom, int lane) {
+  cp_async_wait<MCQ_PF - 1>();
+  __syncwarp();
+  bwd_stage<NJ, K>(a, w, g_sh, e_sh, tabl, bottom, lane);
+  unsigned g[(2 * NJ + 3) / 4];
+  load_slots<NJ, K>(gl, g);
+  const double *es = ering + K * MCQ_ES;
+  w.Rs = es[MCQ_RSLOT];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    w.n0[j] = emis_at(es, g[j >> 1], (j & 1) * 2);
+    w.n1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+  }
+}
+
+// cell updates of one column from the registers bwd_front filled; lane sums in locv / locy
+template <int NJ>
+__device__ __forceinline__ void bwd_cells(BwdWarp<NJ> &w, const double (&m0)[NJ], const double (&m1)[NJ], double invN,
+                                          double &locv, double &locy) {
+  const double Rn = w.Rnext;
+  w.Rnext = w.Rs;
+  const double jump = w.sx * (Rn * invN);
+  const double stay = 1 - Rn;
+  double v_a = 0.0, y_a = 0.0, v_b = 0.0, y_b = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const double v0 = __fma_rn(stay * w.b0[j], w.e0[j], jump) * m0[j];
+    const double v1 = __fma_rn(stay * w.b1[j], w.e1[j], jump) * m1[j];
+    w.b0[j] = v0; w.b1[j] = v1;
+    v_a += v0; v_b += v1;
+    y_a = __fma_rn(v0, w.n0[j], y_a); y_b = __fma_rn(v1, w.n1[j], y_b);
+    w.e0[j] = w.n0[j]; w.e1[j] = w.n1[j];
+  }
+  locv = v_a + v_b; locy = y_a + y_b;
+}
+
+template <int NJ, bool FULL, int K>
+__device__ __forceinline__ void bwd_finish(const BwdArgs &a, BwdWarp<NJ> &w, double locv, double locy, int lane,
+                                           const bool (&inrow)[NJ]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    locv += __shfl_xor_sync(0xffffffffu, locv, o);
+    locy += __shfl_xor_sync(0xffffffffu, locy, o);
+  }
+  w.sx = locy;
+  if (locv < MCQ_BIGI) {                        // forward_backward.c:236-242
+    ++w.cnt;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { w.b0[j] *= MCQ_BIG; w.b1[j] *= MCQ_BIG; }
+    w.sx *= MCQ_BIG;
+  }
+  constexpr int J = (K + 3) & 3;
+  const size_t row = FULL ? (size_t)(64 * NJ) : (size_t)a.st.Ls;
+  double *__restrict__ Bs = w.Bs - J * row;
+#pragma unroll
+  for (int j = 0; j < NJ; j++)
+    if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(Bs + 64 * j), make_double2(w.b0[j], w.b1[j]));
+  if (lane == 0) *(w.Bnp - J) = w.cnt;
+  if (K == 0) { w.Bs -= 4 * row; w.Bnp -= 4; }
+}
+
+template <int NJ, bool FULL, bool PIPE>
 __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
   __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
@@ -1073,6 +1174,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   }
   w.gsrc = Gl + (ptrdiff_t)w.t * (64 * NJ);
   w.rdp = rdq + (w.t - MCQ_RING);
+  w.rdsafe = rdq + bottom;
   w.ecp = ecq + w.t;
   w.Rp = a.R + w.t;
   w.Bs = Bq + (size_t)s * Ls;
@@ -1097,18 +1199,42 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
     w.Rnext = es[MCQ_RSLOT];                    // R[s+1]
   }
 
+  if constexpr (!PIPE) {
 #define MCQ_BWD_SITE(K) \
   bwd_site<NJ, FULL, K>(a, w, gl, ering, g_sh, e_sh, tabl, bottom, lane, inrow, m0, m1, invN)
-  for (; s >= bottom; s -= 4) {
-    MCQ_BWD_SITE(1);
-    if (s - 1 < bottom) break;
-    MCQ_BWD_SITE(2);
-    if (s - 2 < bottom) break;
-    MCQ_BWD_SITE(3);
-    if (s - 3 < bottom) break;
-    MCQ_BWD_SITE(0);
-  }
+    for (; s >= bottom; s -= 4) {
+      MCQ_BWD_SITE(1);
+      if (s - 1 < bottom) break;
+      MCQ_BWD_SITE(2);
+      if (s - 2 < bottom) break;
+      MCQ_BWD_SITE(3);
+      if (s - 3 < bottom) break;
+      MCQ_BWD_SITE(0);
+    }
 #undef MCQ_BWD_SITE
+  } else {
+    // cells of column s | front of column s-1 | butterfly, rescale, store of column s
+#define MCQ_BWD_FRONT(K) bwd_front<NJ, K>(a, w, gl, ering, g_sh, e_sh, tabl, bottom, lane)
+#define MCQ_BWD_SITE(K, KN, COL)                                       \
+  {                                                                    \
+    double locv, locy;                                                 \
+    bwd_cells<NJ>(w, m0, m1, invN, locv, locy);                        \
+    if ((COL) - 1 >= bottom) MCQ_BWD_FRONT(KN);                        \
+    bwd_finish<NJ, FULL, K>(a, w, locv, locy, lane, inrow);            \
+  }
+    MCQ_BWD_FRONT(1);
+    for (; s >= bottom; s -= 4) {
+      MCQ_BWD_SITE(1, 2, s);
+      if (s - 1 < bottom) break;
+      MCQ_BWD_SITE(2, 3, s - 1);
+      if (s - 2 < bottom) break;
+      MCQ_BWD_SITE(3, 0, s - 2);
+      if (s - 3 < bottom) break;
+      MCQ_BWD_SITE(0, 1, s - 3);
+    }
+#undef MCQ_BWD_SITE
+#undef MCQ_BWD_FRONT
+  }
   cp_async_wait<0>();
   if (a.bv != nullptr && lane == 0) a.bv[q] = bottom;
 }
@@ -1116,7 +1242,12 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
 template <int NJ>
 static cudaError_t launch_backward_nj(const BwdArgs &a, cudaStream_t stream, bool tune, int *best_blocks, float *best_ms) {
   const unsigned blocks = (unsigned)((a.st.Q + MCQ_WPB - 1) / MCQ_WPB);
-  void (*kernel)(const BwdArgs) = (a.st.Ls == 64 * NJ) ? k_backward<NJ, true> : k_backward<NJ, false>;
+  if (a.pipe && !tune) {
+    void (*kp)(const BwdArgs) = (a.st.Ls == 64 * NJ) ? k_backward<NJ, true, true> : k_backward<NJ, false, true>;
+    kp<<<blocks, 32 * MCQ_WPB, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
+  void (*kernel)(const BwdArgs) = (a.st.Ls == 64 * NJ) ? k_backward<NJ, true, false> : k_backward<NJ, false, false>;
   if (tune)
     return tune_residency((const void *)kernel, blocks, stream,
                           [&](int smem) { kernel<<<blocks, 32 * MCQ_WPB, smem, stream>>>(a); }, best_blocks, best_ms);
@@ -1161,12 +1292,31 @@ __global__ void __launch_bounds__(128) k_dot(const DotArgs a) {
   const double *Tq = (a.sel != nullptr && a.sel[(size_t)q * S + a.site] != 0) ? a.F : a.T;
   const double2 *__restrict__ t = reinterpret_cast<const double2 *>(Tq + col);
   const double2 *__restrict__ b = reinterpret_cast<const double2 *>(a.B + col);
-  double loc = 0.0;          // the same lane mapping and order as the epilogue of k_forward
-  for (int i = lane; i < Ls / 2; i += 32) {
-    const double2 x = t[i], y = b[i];
-    loc += x.x * y.x; loc += x.y * y.y;
+  double dot;
+  if (a.wpq <= 0) {
+    double loc = 0.0;        // the same lane mapping and order as the epilogue of k_forward
+    for (int i = lane; i < Ls / 2; i += 32) {
+      const double2 x = t[i], y = b[i];
+      loc += x.x * y.x; loc += x.y * y.y;
+    }
+    dot = warp_sum(loc);
+  } else {
+    // ... and of k_forward_mw: the 64-state groups of one consumer warp first, then the warps in order
+    const int njw = (a.st.Lg / 64) / a.wpq;
+    dot = 0.0;
+    for (int w = 0; w < a.wpq; w++) {
+      double loc = 0.0;
+      for (int j = w * njw; j < (w + 1) * njw; j++) {
+        const int i = lane + 32 * j;
+        if (i < Ls / 2) {
+          const double2 x = t[i], y = b[i];
+          loc += x.x * y.x; loc += x.y * y.y;
+        }
+      }
+      const double part = warp_sum(loc);
+      dot = (w == 0) ? part : dot + part;
+    }
   }
-  const double dot = warp_sum(loc);
   if (lane == 0)
     a.llk_out[q] = log(dot) - (a.Tn[(size_t)q * S + a.site] + a.Bn[(size_t)q * S + a.site]) * a.logBIG;
 }

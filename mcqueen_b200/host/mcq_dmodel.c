@@ -352,7 +352,7 @@ static const char *ref_path, *query_path, *out_dir, *hla_path, *cons_path;
 static bool separate_reference_set = true, no_hla = false, no_rev = false, no_rec = false, no_anneal = false;
 static int opt_sparse = -1;   /* -1 auto, 0 dense, 1 sparse */
 static bool opt_sample_prior = false, runtime_set = false, states_set = false, opt_nccl = false,
-            opt_eager = false;
+            opt_eager = false, opt_profile = false;
 static int opt_omega_prior = MCQ_PRIOR_EXPONENTIAL, opt_esc_prior = MCQ_PRIOR_LOG_NORMAL;
 static int opt_rev_prior = MCQ_PRIOR_LOG_NORMAL, opt_device = -1;
 static long opt_seed = -1, opt_gsl_seed = -1;
@@ -368,7 +368,8 @@ static void usage(void)
           "  -v/-e/-w omega prior gamma/log-normal/uniform   -g/-k/-f escape prior gamma/normal/flat\n"
           "  -a/-d/-u reversion prior gamma/normal/flat   -b sample the prior   -z no simulated annealing\n"
           "  --seed N --gsl_seed N (default: clock)  --device D  --sparse_esc | --dense_esc  --trace FILE  --nccl\n"
-          "  --eager_refill  refill F and B at every accept (the reference's schedule) instead of when next read\n");
+          "  --eager_refill  refill F and B at every accept (the reference's schedule) instead of when next read\n"
+          "  --profile  wall time per kind of move at the end of the run\n");
   exit(EXIT_FAILURE);
 }
 
@@ -390,6 +391,7 @@ static void parse(int argc, char **argv)
       {"gsl_seed", required_argument, NULL, 1002}, {"device", required_argument, NULL, 1003},
       {"sparse_esc", no_argument, NULL, 1004}, {"trace", required_argument, NULL, 1005},
       {"nccl", no_argument, NULL, 1006}, {"eager_refill", no_argument, NULL, 1007}, {"dense_esc", no_argument, NULL, 1008},
+      {"profile", no_argument, NULL, 1009},
       {NULL, 0, NULL, 0}};
   int o;
   while((o = getopt_long(argc, argv, "H:n:s:t:c:r:l:qijovewgkfadubz", lo, NULL)) != -1) {
@@ -424,6 +426,7 @@ static void parse(int argc, char **argv)
       case 1005: trace_path = optarg; break;
       case 1006: opt_nccl = true; break;
       case 1007: opt_eager = true; break;
+      case 1009: opt_profile = true; break;
       default: usage();
     }
   }
@@ -726,6 +729,8 @@ int main(int argc, char **argv)
   clock_gettime(CLOCK_MONOTONIC, &ts0);
   time_t t_start = time(NULL);
   int hours_passed = 1, sample_i = 1, chain_i, hours = 0;
+  double prof_s[9] = {0};
+  long prof_n[9] = {0};
   for(chain_i = 0; chain_i < chain_length; chain_i++, sample_i++) {
     int pick = mcq_rand_lim(total);
     int move = pick < rec ? 0 : pick < sel ? 1 : pick < esc_ms ? 2 : pick < rev_ms ? 3 : pick < esc_gr ? 4 :
@@ -748,12 +753,19 @@ int main(int argc, char **argv)
       }
     }
 
+    struct timespec tm0, tm1;
+    if(opt_profile) clock_gettime(CLOCK_MONOTONIC, &tm0);
     switch(move) {
       case 0: move_recombination(&c, temperature); break;
       case 1: move_selection(&c, temperature); break;
       case 8: move_mutation(&c, temperature); break;
       default:
         move_window(&c, temperature, (move & 1) != 0, move <= 3 ? ACT_MERGE_OR_SPLIT : move <= 5 ? ACT_GROW : ACT_COEFF);
+    }
+    if(opt_profile) {
+      clock_gettime(CLOCK_MONOTONIC, &tm1);
+      prof_s[move] += (tm1.tv_sec - tm0.tv_sec) + 1e-9 * (tm1.tv_nsec - tm0.tv_nsec);
+      prof_n[move]++;
     }
 
     /* end of chain / wall-clock limit / hourly interim state (dmodel.c:1203-1235) */
@@ -795,6 +807,13 @@ int main(int argc, char **argv)
     double sec = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
     int done = chain_i < chain_length ? chain_i + 1 : chain_i;
     printf("MCMC loop: %d steps in %.6f s = %.3f steps/s\n", done, sec, done / sec);
+  }
+  if(opt_profile) {
+    static const char *names[9] = {"recombination", "selection", "esc merge/split", "rev merge/split", "esc grow",
+                                   "rev grow", "esc coeff", "rev coeff", "mutation"};
+    for(int m = 0; m < 9; m++)
+      if(prof_n[m]) printf("profile: %-16s %7ld moves %10.3f ms total %9.1f us each\n", names[m], prof_n[m],
+                           prof_s[m] * 1e3, prof_s[m] / prof_n[m] * 1e6);
   }
   printf("final log-likelihood: %.10f\n", c.llk);
   printf("time taken: %.2f\n", difftime(time(NULL), t_start));
