@@ -356,14 +356,15 @@ static bool opt_sample_prior = false, runtime_set = false, states_set = false, o
 static int opt_omega_prior = MCQ_PRIOR_EXPONENTIAL, opt_esc_prior = MCQ_PRIOR_LOG_NORMAL;
 static int opt_rev_prior = MCQ_PRIOR_LOG_NORMAL, opt_device = -1;
 static long opt_seed = -1, opt_gsl_seed = -1;
-static const char *trace_path = NULL, *resume_path = NULL;
+static const char *trace_path = NULL, *resume_path = NULL, *params_path = NULL, *mosaic_path = NULL;
 
 static void usage(void)
 {
   fprintf(stderr,
           "usage: mcq_dmodel [options] <ref_seqs.fasta> <query.fasta> <outdir>\n"
           "  -H <HLA.csv>  -n <chain length>  -s <sample every>  -t <hours>  -c <consensus.fasta>  -l <closest L>\n"
-          "  -r <state.json> resume from a saved state\n"
+          "  -r <state.json> resume from a saved state  -p <parameters.json> kappa, phi, codon priors\n"
+          "  -m <mosaic.json> closest-L lists from the true mosaics of a simulation\n"
           "  -q self-reference mode  -i no HLA inference  -j no reversion inference  -o no recombination\n"
           "  -v/-e/-w omega prior gamma/log-normal/uniform   -g/-k/-f escape prior gamma/normal/flat\n"
           "  -a/-d/-u reversion prior gamma/normal/flat   -b sample the prior   -z no simulated annealing\n"
@@ -379,7 +380,8 @@ static void parse(int argc, char **argv)
       {"HLA_inference", required_argument, NULL, 'H'}, {"chain_length", required_argument, NULL, 'n'},
       {"sample_every", required_argument, NULL, 's'}, {"runtime_hours", required_argument, NULL, 't'},
       {"consensus_fasta", required_argument, NULL, 'c'}, {"closest_n", required_argument, NULL, 'l'},
-      {"resume_json", required_argument, NULL, 'r'},
+      {"resume_json", required_argument, NULL, 'r'}, {"parameters_json", required_argument, NULL, 'p'},
+      {"true_mosaic_fasta", required_argument, NULL, 'm'},
       {"separate_reference_fasta", no_argument, NULL, 'q'}, {"no_HLA_inference", no_argument, NULL, 'i'},
       {"no_rev_inference", no_argument, NULL, 'j'}, {"no_recombination_inference", no_argument, NULL, 'o'},
       {"omega_gamma", no_argument, NULL, 'v'}, {"omega_log_normal", no_argument, NULL, 'e'},
@@ -394,7 +396,7 @@ static void parse(int argc, char **argv)
       {"profile", no_argument, NULL, 1009},
       {NULL, 0, NULL, 0}};
   int o;
-  while((o = getopt_long(argc, argv, "H:n:s:t:c:r:l:qijovewgkfadubz", lo, NULL)) != -1) {
+  while((o = getopt_long(argc, argv, "H:n:s:t:c:r:p:m:l:qijovewgkfadubz", lo, NULL)) != -1) {
     switch(o) {
       case 'H': hla_path = optarg; break;
       case 'n': chain_length = atoi(optarg); states_set = true; break;
@@ -402,6 +404,8 @@ static void parse(int argc, char **argv)
       case 't': runtime_hours = atoi(optarg); runtime_set = true; break;
       case 'c': cons_path = optarg; break;
       case 'r': resume_path = optarg; break;
+      case 'p': params_path = optarg; break;
+      case 'm': mosaic_path = optarg; break;
       case 'l': closest_n = atoi(optarg); break;
       case 'q': separate_reference_set = false; break;
       case 'i': no_hla = true; break;
@@ -561,7 +565,10 @@ int main(int argc, char **argv)
     for(int q = 0; q < Qall; q++) { hla_rows[q] = malloc(2); hla_rows[q][0] = '0'; hla_rows[q][1] = '\0'; }
     H = 1;
   }
-  const double kappa = MCQ_KAPPA, phi = MCQ_PHI;
+  /* the fixed viral parameters; dmodel -p replaces them (dmodel.c:461-463) */
+  double kappa = MCQ_KAPPA, phi = MCQ_PHI, prior[64];
+  memcpy(prior, mcq_prior_c1, sizeof(prior));
+  if(params_path != NULL) mcq_load_fixed_parameters_json(params_path, &kappa, &phi, prior);
   printf("kappa:%f\nphi:%f\n", kappa, phi);
   double lambda_rec = 1 / (-log(1 - MCQ_P_REC) * N);
   printf("lambda_rec:%f\n", lambda_rec);
@@ -582,6 +589,33 @@ int main(int argc, char **argv)
   printf("Example - closest references to query sequence 1:\n");
   for(int r = 0; r < closest_n; r++) printf("%i ", closest_all[r]);
   printf("\n");
+
+  if(mosaic_path != NULL) {
+    /* dmodel -m (dmodel.c:505-558): every query's list becomes the closest relatives of the references it was
+     * truly copied from, floor(L/k) of each and one more for the last L mod k of them.  Draws (the permutation,
+     * then the tie shuffles of every selection) are made in the reference's order, one selection at a time
+     * through the library's one-query symbols. */
+    int *which = malloc(sizeof(int) * (size_t)Qall * S), *num = malloc(sizeof(int) * Qall);
+    int *tmp_hamming = malloc(sizeof(int) * N), *sel = malloc(sizeof(int) * (closest_n + 1));
+    mcq_load_true_mosaics_json(mosaic_path, Qall, S, which, num);
+    for(int q = 0; q < Qall; q++) {
+      int *w = which + (size_t)q * S, k = num[q];
+      if(k <= 0) mcq_die("mosaic of query %i is empty", q);
+      for(int i = 0; i < k; i++) {                /* knuth_perm, util.c:103-112 */
+        int j = (int)mcq_rand_lim(i + 1), t = w[i];
+        w[i] = w[j]; w[j] = t;
+      }
+      int each = closest_n / k, remain = closest_n % k, m_total = 0;
+      for(int r = 0; r < k; r++) {
+        int n = r < k - remain ? each : each + 1;
+        if(w[r] < 0 || w[r] >= N) mcq_die("mosaic of query %i names reference %i", q, w[r]);
+        hamming_distance_considering_unknown(ref_seqs, ref_seqs[w[r]], N, (int)nb, tmp_hamming);
+        closest_sequences(N, tmp_hamming, n, sel);
+        for(int m = 0; m < n; m++) closest_all[(size_t)q * closest_n + m_total++] = sel[m];
+      }
+    }
+    free(which); free(num); free(tmp_hamming); free(sel);
+  }
 
   /* parameters and windows (dmodel.c:564-642) */
   Chain c;
@@ -642,8 +676,7 @@ int main(int argc, char **argv)
   }
   free(rev_all);
 
-  double prior[64], acc = 0;
-  memcpy(prior, mcq_prior_c1, sizeof(prior));
+  double acc = 0;
   for(int i = 0; i < 63; i++) acc += prior[i];
   prior[63] = 1 - acc;                                     /* dmodel.c:867-869 */
   double *rate_out = malloc(sizeof(double) * 64 * S);     /* dmodel.c:836-849 */

@@ -1,4 +1,5 @@
 #include <ctype.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
@@ -32,6 +33,31 @@ static char *parse_string(JIn *in)
   s[n] = '\0';
   in->p++;
   return s;
+}
+
+/* Numbers are converted the way the reference's JSON library does it (cJSON.c:96-115: the digits accumulated in a
+ * double, times pow(10, exponent)), not with strtod: the two differ in the last bit for most decimal fractions,
+ * and a chain resumed from a state file (-r) or run with a parameter file (-p) must start from the very doubles
+ * the reference would read. */
+static double parse_number(JIn *in)
+{
+  const char *p = in->p;
+  double mant = 0, sign = 1;
+  int frac_digits = 0, expo = 0, expo_sign = 1;
+  if(*p == '-') { sign = -1; p++; }
+  while(isdigit((unsigned char)*p)) mant = mant * 10.0 + (*p++ - '0');
+  if(*p == '.' && isdigit((unsigned char)p[1])) {
+    p++;
+    while(isdigit((unsigned char)*p)) { mant = mant * 10.0 + (*p++ - '0'); frac_digits++; }
+  }
+  if(*p == 'e' || *p == 'E') {
+    p++;
+    if(*p == '+') p++;
+    else if(*p == '-') { expo_sign = -1; p++; }
+    while(isdigit((unsigned char)*p)) expo = expo * 10 + (*p++ - '0');
+  }
+  in->p = p;
+  return sign * mant * pow(10.0, (double)(-frac_digits + expo * expo_sign));
 }
 
 static JNode *parse_value(JIn *in)
@@ -68,10 +94,8 @@ static JNode *parse_value(JIn *in)
     n->type = J_STR;
     n->str = parse_string(in);
   } else if(c == '-' || isdigit((unsigned char)c)) {
-    char *end;
     n->type = J_NUM;
-    n->num = strtod(in->p, &end);
-    in->p = end;
+    n->num = parse_number(in);
   } else if(!strncmp(in->p, "true", 4)) { n->type = J_BOOL; n->num = 1; in->p += 4; }
   else if(!strncmp(in->p, "false", 5)) { n->type = J_BOOL; in->p += 5; }
   else if(!strncmp(in->p, "null", 4)) { n->type = J_NULL; in->p += 4; }
@@ -181,6 +205,54 @@ void mcq_load_state_json(const char *path, double *llk, double *mu, double *R, d
     if(i != closest_n) mcq_die("Mismatch in closest N.");
   }
   if(q != num_query) mcq_die("Mismatch in number of queries: [%i vs %i].", q, num_query);
+  jfree(root);
+  free(text);
+}
+
+/* load_fixed_parameters_from_json, load_from_json.c:248-295: kappa, phi and the 64 codon priors */
+void mcq_load_fixed_parameters_json(const char *path, double *kappa, double *phi, double *codon_prior)
+{
+  char *text = slurp(path);
+  JIn in = {text};
+  JNode *root = parse_value(&in);
+  *kappa = member(root, "kappa", J_NUM, "parameters")->num;
+  *phi = member(root, "phi", J_NUM, "parameters")->num;
+  const JNode *codons = member(root, "codons", J_ARR, "parameters");
+  if(codons->child == NULL) mcq_die("json: No 'codons' object.");
+  int c = 0;
+  for(const JNode *cd = codons->child; cd; cd = cd->next, c++) {
+    if(c >= 64) mcq_die("Mismatch in number of codon types: more than 64.");
+    codon_prior[c] = member(cd, "codon_prior", J_NUM, "codon")->num;
+    printf("codon_prior[%i]:%f\n", c, codon_prior[c]);
+  }
+  if(c != 64) mcq_die("Mismatch in number of codon types: [%i vs %i].", 64, c);
+  jfree(root);
+  free(text);
+}
+
+/* load_closest_n_from_json, load_from_json.c:178-246: per simulated query the references it was copied from */
+void mcq_load_true_mosaics_json(const char *path, int num_query, int num_sites, int *which_seqs, int *num_seqs)
+{
+  char *text = slurp(path);
+  JIn in = {text};
+  JNode *root = parse_value(&in);
+  const JNode *sims = member(root, "true_sequences", J_ARR, "root");
+  if(sims->child == NULL) mcq_die("json: No sequences in file.");
+  printf("num sims: %i\n", num_query);
+  int q = 0;
+  for(const JNode *sim = sims->child; sim; sim = sim->next, q++) {
+    if(q >= num_query) mcq_die("json: more mosaics than query sequences [%i].", num_query);
+    (void)member(sim, "number", J_NUM, "mosaic");
+    int n = 0;
+    for(const JNode *e = member(sim, "closest_n", J_ARR, "mosaic")->child; e; e = e->next, n++) {
+      if(n >= num_sites) mcq_die("json: num_seqs too big.");
+      if(e->type != J_NUM) mcq_die("json: No 'num_seqs' object.");
+      which_seqs[(size_t)q * num_sites + n] = (int)e->num;
+    }
+    num_seqs[q] = n;
+  }
+  if(q != num_query) mcq_die("json: %i mosaics for %i query sequences.", q, num_query);
+  printf("We got %i simulated sequence mosaics\n", q - 1);
   jfree(root);
   free(text);
 }

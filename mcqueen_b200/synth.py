@@ -16,7 +16,8 @@ import numpy as np
 
 from . import genetics as gen
 
-__all__ = ["make_dataset", "CONFIGS", "dsim_rows", "dsim_queries"]
+__all__ = ["make_dataset", "CONFIGS", "dsim_rows", "dsim_queries", "dsim_simulate_in_reference_order",
+           "write_simulation_parameters_json", "load_simulation_parameters_json"]
 
 # the named shapes of BASELINE.json / SURVEY.md §8
 CONFIGS = {
@@ -106,6 +107,110 @@ def dsim_queries(rng, ref_codons, consensus_codons, hla, omega, R, esc, rev, mu,
         u = rng.random((q1 - q0, S, 1)) * cdf[..., -1:]
         out[q0:q1] = np.minimum((u > cdf).sum(-1), 63).astype(np.int8)
     return out, copy_from
+
+
+def dsim_simulate_in_reference_order(ref_codons, consensus_codons, omega, R, esc, rev, mu, hla_prevalences, ploidy,
+                                     n_HLA, proportion_no_hla, num_sims, uniform=None, kappa=gen.KAPPA, phi=gen.PHI,
+                                     prior=None):
+    """simulate_sequences (simulate_sequences_sim.c:154-300) restated draw for draw: the HLA profile of every
+    simulated query (one discrete_sampling_dist draw per gene copy, util.c:519-533), the queries without HLA
+    information, the copied reference per codon (a switch with probability R[s]), and one codon per site drawn from
+    the cumulative emission distribution (bfind_pos, :139-152).  ``uniform()`` returns random()/RAND_MAX of the
+    libc stream the reference draws from (default: this process's libc), so that the same seed gives the reference's
+    own output.  Returns (hla (num_sims,H) u8 '0'/'1', copy_from (num_sims,S) i32, sequences (num_sims,S) i32)."""
+    if uniform is None:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6")
+        libc.random.restype = ctypes.c_long
+        rand_max = 2147483647.0
+
+        def uniform():
+            return libc.random() / rand_max
+    N, S = ref_codons.shape
+    H = int(sum(n_HLA))
+    prev = np.asarray(hla_prevalences, float)
+    hla = np.full((num_sims, H), ord("0"), np.uint8)
+    for i in range(num_sims):
+        base = 0
+        for ng in n_HLA:
+            for _ in range(ploidy):
+                u = 1 * uniform()
+                cur, b = prev[base], 0
+                for k in range(ng):
+                    if u < cur:
+                        break
+                    b += 1
+                    cur += prev[base + k + 1] if base + k + 1 < prev.size else 0.0
+                hla[i, base + b] = ord("1")
+            base += ng
+    for i in range(num_sims):
+        if 1 * uniform() < proportion_no_hla:
+            hla[i, :] = ord("0")
+    copy_from = np.zeros((num_sims, S), np.int32)
+    for i in range(num_sims):
+        copy_from[i, 0] = int(N * uniform())
+        for s in range(1, S):
+            if 1 * uniform() < R[s]:
+                copy_from[i, s] = int(N * uniform())
+            else:
+                copy_from[i, s] = copy_from[i, s - 1]
+    frm = ref_codons[copy_from, np.arange(S)[None, :]].astype(np.int64)
+    esc_prod = np.ones((num_sims, S))
+    for h in range(H):          # product in HLA order, as the reference multiplies
+        esc_prod = np.where((hla[:, h] == ord("1"))[:, None], esc_prod * esc[h][None, :], esc_prod)
+    rows = dsim_rows(frm, np.asarray(consensus_codons)[None, :], omega[None, :], esc_prod, rev[None, :], mu, N,
+                     kappa=kappa, phi=phi, prior=prior)
+    cdf = np.cumsum(rows, axis=-1)
+    seqs = np.zeros((num_sims, S), np.int32)
+    for i in range(num_sims):
+        for s in range(S):
+            where = 1 * uniform()
+            j = 0
+            for c in range(64):
+                if where > cdf[i, s, c]:
+                    j += 1
+                else:
+                    break
+            seqs[i, s] = j
+    return hla, copy_from, seqs
+
+
+def write_simulation_parameters_json(path, kappa, mu, omega, R, reversion, hla_profiles, hla_prevalences, n_HLA, ploidy):
+    """The parameter file dsim reads (load_lengths_for_simulation_from_json / load_parameters_for_simulation_from_json,
+    load_from_json.c:297-443): scalars, the HLA prevalences and gene sizes, and per site omega, R, the reversion
+    coefficient and one escape coefficient per HLA type."""
+    import json
+    omega, R, reversion = (np.asarray(x, float) for x in (omega, R, reversion))
+    prof = np.asarray(hla_profiles, float)            # (total_n_HLA, S)
+    doc = {"kappa": float(kappa), "mu": float(mu), "codon_sequence_length": int(omega.size),
+           "total_n_HLA": int(prof.shape[0]), "ploidy": int(ploidy), "n_genes": len(n_HLA),
+           "HLA_prevalences": [float(x) for x in hla_prevalences], "n_HLA": [int(x) for x in n_HLA],
+           "sites": [{"omega": float(omega[s]), "R": float(R[s]), "reversion": float(reversion[s]),
+                      "HLA": [float(x) for x in prof[:, s]]} for s in range(omega.size)]}
+    with open(path, "w") as f:
+        json.dump(doc, f)
+
+
+def load_simulation_parameters_json(path):
+    """Reads the file above, with the reference's consistency checks (gene sizes add up to total_n_HLA, one entry
+    per site)."""
+    import gzip
+    import json
+    with open(path, "rb") as f:
+        raw = f.read()
+    doc = json.loads(gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw)
+    S, H = int(doc["codon_sequence_length"]), int(doc["total_n_HLA"])
+    n_HLA = [int(x) for x in doc["n_HLA"]]
+    if sum(n_HLA) != H or len(n_HLA) != int(doc["n_genes"]):
+        raise ValueError(f"Mismatch in the number of HLA types: [{sum(n_HLA)} vs {H}].")
+    if len(doc["sites"]) != S:
+        raise ValueError(f"Mismatch in sequence length: [{len(doc['sites'])} vs {S}].")
+    sites = doc["sites"]
+    return dict(kappa=float(doc["kappa"]), mu=float(doc["mu"]), ploidy=int(doc["ploidy"]), n_HLA=n_HLA,
+                hla_prevalences=np.array(doc["HLA_prevalences"], float),
+                omega=np.array([s["omega"] for s in sites], float), R=np.array([s["R"] for s in sites], float),
+                reversion=np.array([s["reversion"] for s in sites], float),
+                hla_profiles=np.array([s["HLA"] for s in sites], float).T.copy())
 
 
 def make_dataset(seed=20261019, S=100, N=200, Q=50, H=4, n_clades=None,

@@ -228,3 +228,28 @@ def test_fasta_and_hla_csv_readers(host, tmp_path):
     d = tmp_path / "x" / "y" / "z"
     host.mcq_mkpath.argtypes = [C.c_char_p]
     assert host.mcq_mkpath(str(d).encode()) == 1 and d.is_dir()
+
+
+def test_parameter_json_reads_the_doubles_the_reference_reads(host, tmp_path):
+    """dmodel -p: kappa, phi and the codon priors come out of the file as exactly the doubles the reference's JSON
+    library produces (digits times pow(10, exponent), cJSON.c:96-115 - not the correctly rounded strtod value), for
+    plain decimals, long fractions and exponents alike (load_from_json.c:248-295)."""
+    refsim = os.path.join(ROOT, "oracle", "_ref", "libmcq_refsim.so")
+    if not os.path.exists(refsim):
+        pytest.skip("oracle/_ref/libmcq_refsim.so not built")
+    ref = C.CDLL(refsim)
+    rng = np.random.default_rng(9)
+    texts = ["0.1", "7.595744", "1e-05", "3.08971e-06", "0.9482171", "12345.678901234567", "2.5E+3", "0.000117409", "-0.5"]
+    texts += [repr(float(x)) for x in rng.random(64 - len(texts)) * 10.0 ** rng.integers(-8, 3, 64 - len(texts))]
+    path = str(tmp_path / "p.json")
+    with open(path, "w") as f:
+        f.write('{"kappa": 7.595744, "phi": 0.9482171,\n "codons": [' +
+                ", ".join('{"codon": %d, "codon_prior": %s}' % (i, t) for i, t in enumerate(texts)) + "]}\n")
+    ours, theirs = np.zeros(64), np.zeros(64)
+    k = [C.c_double(), C.c_double()]
+    p = [C.c_double(), C.c_double()]
+    host.mcq_load_fixed_parameters_json(path.encode(), C.byref(k[0]), C.byref(p[0]), ours.ctypes.data_as(C.c_void_p))
+    ref.load_fixed_parameters_from_json(path.encode(), C.byref(k[1]), C.byref(p[1]), theirs.ctypes.data_as(C.c_void_p))
+    assert k[0].value == k[1].value and p[0].value == p[1].value
+    assert np.array_equal(ours, theirs)
+    assert any(float(t) != v for t, v in zip(texts, theirs))      # the point: these are not all strtod's values

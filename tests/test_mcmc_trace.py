@@ -120,3 +120,65 @@ def test_resume_from_saved_state_matches_reference(tmp_path):
     assert abs(ours_init - ref_init) <= 1e-9 * abs(ref_init)
     a, b = read_trace(t_ours), read_trace(t_ref)
     assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def _trace_pair(tmp_path, extra_args, paths, L, steps="300", seed="4"):
+    args = extra_args + ["-H", paths["hla"], "-l", str(L), "-n", steps, "-s", "50", paths["ref"], paths["query"]]
+    t_ours, t_ref = str(tmp_path / "ours.trace"), str(tmp_path / "ref.trace")
+    o = run([DRIVER, "--seed", seed, "--gsl_seed", seed, "--trace", t_ours] + args + [str(tmp_path / "ours")])
+    r = run([cpu_libs.REF_DMODEL] + args + [str(tmp_path / "ref")],
+            env={"MCQ_SEED": seed, "MCQ_GSL_SEED": seed, "MCQ_TRACE": t_ref})
+    pat = r"Total log-likelihood using initialise F: (-?[0-9]+\.[0-9]+)"
+    return (read_trace(t_ours), float(re.search(pat, o).group(1)), o), (read_trace(t_ref), float(re.search(pat, r).group(1)), r)
+
+
+def test_parameters_json_matches_reference(tmp_path):
+    """dmodel -p (load_from_json.c:248-295): kappa, phi and the codon priors from a file - same initial
+    likelihood and the same decisions as the reference given the same file."""
+    import json
+    if not (cpu_libs.have_ref() and os.path.exists(cpu_libs.REF_DMODEL)):
+        pytest.skip("oracle/_ref/dmodel_ref not present")
+    from mcqueen_b200 import genetics as gen
+    paths, L, _ = make_chain_inputs(str(tmp_path / "in"), "toy")
+    rng = np.random.default_rng(2)
+    prior = gen.PRIOR_C1 * np.exp(rng.normal(0, 0.3, 64))
+    prior /= prior.sum()
+    pj = str(tmp_path / "params.json")
+    json.dump({"kappa": 5.25, "phi": 0.9, "codons": [{"codon": i, "codon_prior": float(x)} for i, x in enumerate(prior)]},
+              open(pj, "w"))
+    (a, ia, out), (b, ib, _) = _trace_pair(tmp_path, ["-p", pj], paths, L)
+    assert "kappa:5.25" in out and "phi:0.9" in out
+    assert abs(ia - ib) <= 1e-9 * abs(ib)
+    assert a.shape == b.shape and np.array_equal(a, b)
+    # ... and the file changed something: the default parameters give another likelihood
+    (_, i0, _), _ = _trace_pair(tmp_path, [], paths, L, steps="1")
+    assert abs(i0 - ia) > 1e-6 * abs(ia)
+
+
+def test_true_mosaic_mode_matches_reference(tmp_path):
+    """dmodel -m (dmodel.c:505-558): the closest-L lists are rebuilt from the references each query was truly
+    copied from; the permutation and every tie shuffle draw from the shared stream in the reference's order."""
+    import json
+    if not (cpu_libs.have_ref() and os.path.exists(cpu_libs.REF_DMODEL)):
+        pytest.skip("oracle/_ref/dmodel_ref not present")
+    paths, L, d = make_chain_inputs(str(tmp_path / "in"), "toy", Q=20)
+    sims = []
+    for q in range(20):
+        seen = []
+        for r in d["parents"][q]:
+            if int(r) not in seen:
+                seen.append(int(r))
+        sims.append({"number": q, "closest_n": seen[:L]})
+    mj = str(tmp_path / "mosaic.json")
+    json.dump({"true_sequences": sims}, open(mj, "w"))
+    (a, ia, out), (b, ib, rout) = _trace_pair(tmp_path, ["-m", mj], paths, L)
+    assert abs(ia - ib) <= 1e-9 * abs(ib)
+    assert a.shape == b.shape and np.array_equal(a, b)
+    # the saved closest-L lists are the mosaic ones, identical in both final states
+    lists = []
+    for name in ("ours", "ref"):
+        st = json.load(open(newest(str(tmp_path / name), "_final_state.json")))
+        lists.append([qq["closest_n"] for qq in st["query"]])
+    assert lists[0] == lists[1]
+    for q in range(20):
+        assert set(sims[q]["closest_n"]) <= set(lists[0][q]) or len(sims[q]["closest_n"]) > L
