@@ -57,13 +57,14 @@ def make_data(name):
     return synth.make_dataset(seed=SEED, self_reference=name in synth.SELF_REFERENCE, **cfg)
 
 
-def build_shard(name, q0, q1, device_index):
+def build_shard(name, q0, q1, device_index, dist=None, world=1):
     """Problem restricted to queries q0..q1-1 (references are shared by every shard).
 
     The closest-L lists are those of the WHOLE workload: the reference shuffles boundary ties with one libc
     random() stream consumed in global query order (closest_seqs.c:57-64, called per query from
-    dmodel.c:356-387), so every rank selects for all queries from the same seed - as mcq_dmodel does - and keeps
-    its shard.  The problem is then the same at every number of GPUs."""
+    dmodel.c:356-387).  The device part (distances, selection groups) is done for this rank's queries only; the
+    groups of all ranks are exchanged and every rank replays the tie shuffles of all queries from the same seed - as
+    mcq_dmodel does - and keeps its shard.  The problem is then the same at every number of GPUs."""
     from mcqueen_b200 import api
     cfg = workload_dims(name)
     L = cfg["L"]
@@ -71,12 +72,18 @@ def build_shard(name, q0, q1, device_index):
     data = make_data(name)
     refs, qs_all = data["ref_seqs"], data["query_seqs"]
     qs, hla = np.ascontiguousarray(qs_all[q0:q1]), data["hla"][q0:q1]
+    skip = name in synth.SELF_REFERENCE
     import ctypes
     # CUDA context creation and module load happen on the first call: keep them out of the closest-L wall time
     api.closest_batch(refs[:max(2 * L, 64)], qs[:2], min(L, 8), device=device_index)
     t1 = time.time()
+    groups = api.closest_groups(refs, qs, L, skip_first=skip, device=device_index)
+    blocks = [groups]
+    if world > 1:
+        blocks = [None] * world
+        dist.all_gather_object(blocks, groups)
     ctypes.CDLL("libc.so.6").srandom(SEED & 0x7fffffff)
-    closest_all = api.closest_batch(refs, qs_all, L, skip_first=name in synth.SELF_REFERENCE, device=device_index)
+    closest_all = np.concatenate([api.closest_replay(b, L, skip_first=skip) for b in blocks])
     t2 = time.time()
     ham_ms, sel_ms = api.closest_last_timing()
     closest = np.ascontiguousarray(closest_all[q0:q1])
@@ -84,15 +91,18 @@ def build_shard(name, q0, q1, device_index):
     p = prep.build_problem(refs, qs, hla, closest, cons_q=cons_q)
     prep.random_parameters(p, seed=1)
     t3 = time.time()
-    log(f"[bench] data {t1 - t0:.1f}s  closest-L(GPU, all {qs_all.shape[0]} queries) {t2 - t1:.1f}s  prep {t3 - t2:.1f}s  "
+    log(f"[bench] data {t1 - t0:.1f}s  closest-L(GPU: {qs.shape[0]} queries here, tie shuffles of all {qs_all.shape[0]}) {t2 - t1:.2f}s  prep {t3 - t2:.1f}s  "
         f"Q={p.Q} S={p.S} L={p.L} N={p.N} H={p.H}")
     p.closest_seconds = t2 - t1
     p.full = dict(refs=refs, queries=qs_all, hla=data["hla"], closest=closest_all)
     nb = refs.shape[1]
-    nq = qs_all.shape[0]
+    nq = qs.shape[0]
     p.closest_stats = {
-        "shape": f"{refs.shape[0]} refs x {nq} queries x {nb} nt, L={L} (BASELINE config 3 when the workload is C4)",
-        "hamming_kernel_ms": ham_ms, "select_kernels_ms": sel_ms, "wall_seconds_incl_transfers_and_tie_shuffle": t2 - t1,
+        "shape": f"{refs.shape[0]} refs x {nq} queries on this GPU (of {qs_all.shape[0]}) x {nb} nt, L={L} (BASELINE config 3 when the workload is C4)",
+        "hamming_kernel_ms": ham_ms, "select_kernel_ms": sel_ms,
+        "kernel_times": "CUDA events per chunk of queries, summed; chunks alternate between two streams, so the two sums "
+                        "overlap in time (one after the other: profiles/)",
+        "wall_seconds_incl_transfers_exchange_and_tie_shuffles": t2 - t1,
         "nt_compares_per_s": refs.shape[0] * nq * nb / (ham_ms * 1e-3) if ham_ms > 0 else None,
         # one 64-bit POPC word per 64 nt per pair: B200 issues 16 POPC.32 lanes/clk/SM
         "popc_word_ops_per_s": refs.shape[0] * nq * ((nb + 63) // 64) / (ham_ms * 1e-3) if ham_ms > 0 else None,
@@ -412,7 +422,7 @@ def main():
     if rank == 0:
         clk.__enter__()
     q0, q1 = Qtot * rank // world, Qtot * (rank + 1) // world
-    p = build_shard(args.workload, q0, q1, dev)
+    p = build_shard(args.workload, q0, q1, dev, dist=dist if world > 1 else None, world=world)
     ctx = api.Context.from_problem(p, device=dev)
     comm_kind = os.environ.get("MCQ_BENCH_COMM", "peer") if world > 1 else "none"
     if world > 1:

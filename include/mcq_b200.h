@@ -289,6 +289,18 @@ int mcq_codon_class(int c1, int c2);
 int mcq_closest_batch(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
                       const char *query_seqs, size_t query_stride, int num_query,
                       int num_bases, int closest_n, int skip_first, int *closest_refs /*[Q][L]*/);
+/* The same in two steps, for queries sharded over ranks.  mcq_closest_groups does the device part for the given
+ * queries - per query the references closer than the distance T of sorted element closest_n, sorted by (distance,
+ * index), and those at distance T in index order - and returns them as one flat int block (malloc'ed; mcq_free).
+ * mcq_closest_replay does the sequential part for one block: the reference's tie shuffle (closest_seqs.c:57-64)
+ * with libc random(), query after query.  Every rank computes the block of its shard, the blocks are exchanged, and
+ * every rank replays all of them in rank order: the lists are then those of a single-process run. */
+int mcq_closest_groups(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
+                       const char *query_seqs, size_t query_stride, int num_query, int num_bases,
+                       int closest_n, int skip_first, int **groups, size_t *count);
+int mcq_closest_replay(const int *groups, size_t count, int closest_n, int skip_first,
+                       int *closest_refs /*[Q of the block][L]*/, int *num_query /* may be NULL */);
+void mcq_free(void *p);
 /* Per-query consensus of the closest references (generate_consensus_subset over every query,
  * dmodel.c:664-681 / amino_acids.c:118-141): cons_codes[Q][num_bases] receives base codes 0..3
  * (T,C,A,G), i.e. cons_query_nucls.  Reference sequences must still carry their unknown bases. */
@@ -298,6 +310,8 @@ int mcq_consensus_batch(int device, const char *ref_seqs, size_t ref_stride, int
 /* Device time (CUDA events) of the distance kernel and of the two selection kernels in the last
  * mcq_closest_batch / mcq_hamming_batch call of the calling thread. */
 int mcq_closest_last_timing(float *hamming_ms, float *select_ms);
+/* Device time of the consensus kernel in the last mcq_consensus_batch call of the calling thread. */
+int mcq_consensus_last_timing(float *kernel_ms);
 /* Hamming distances only (values as closest_seqs.c:17-48), hamming[Q][N]. */
 int mcq_hamming_batch(int device, const char *ref_seqs, size_t ref_stride, int num_refs,
                       const char *query_seqs, size_t query_stride, int num_query,

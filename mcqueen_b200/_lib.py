@@ -78,7 +78,12 @@ SYMBOLS = {
     "mcq_codon_class": (C.c_int, [C.c_int, C.c_int]),
     "mcq_closest_batch": (C.c_int, [C.c_int, _V, C.c_size_t, C.c_int, _V, C.c_size_t, C.c_int, C.c_int,
                                     C.c_int, C.c_int, _V]),
+    "mcq_closest_groups": (C.c_int, [C.c_int, _V, C.c_size_t, C.c_int, _V, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_size_t)]),
+    "mcq_closest_replay": (C.c_int, [_V, C.c_size_t, C.c_int, C.c_int, _V, c_int_p]),
+    "mcq_free": (None, [_V]),
     "mcq_consensus_batch": (C.c_int, [C.c_int, _V, C.c_size_t, C.c_int, _V, C.c_int, C.c_int, C.c_int, _V]),
+    "mcq_consensus_last_timing": (C.c_int, [C.POINTER(C.c_float)]),
     "mcq_closest_last_timing": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mcq_hamming_batch": (C.c_int, [C.c_int, _V, C.c_size_t, C.c_int, _V, C.c_size_t, C.c_int, C.c_int, _V]),
 }

@@ -133,6 +133,32 @@ def closest_batch(ref_seqs, query_seqs, closest_n, skip_first=False, device=0):
     return out
 
 
+def closest_groups(ref_seqs, query_seqs, closest_n, skip_first=False, device=0):
+    """The device part of closest_batch for the given queries: one flat int32 block of selection groups (to be
+    exchanged between ranks and replayed in rank order with closest_replay)."""
+    lib = _lib.load()
+    ref_seqs, query_seqs = _chars(ref_seqs, "ref_seqs"), _chars(query_seqs, "query_seqs")
+    N, nb = ref_seqs.shape
+    Q = query_seqs.shape[0]
+    ptr, cnt = C.POINTER(C.c_int)(), C.c_size_t()
+    check(lib.mcq_closest_groups(device, _vp(ref_seqs), nb, N, _vp(query_seqs), nb, Q, nb, closest_n,
+                                 1 if skip_first else 0, C.byref(ptr), C.byref(cnt)))
+    try:
+        return np.ctypeslib.as_array(ptr, shape=(cnt.value,)).copy()
+    finally:
+        lib.mcq_free(ptr)
+
+
+def closest_replay(groups, closest_n, skip_first=False):
+    """The sequential part: the reference's tie shuffles with libc random() for the queries of one block."""
+    lib = _lib.load()
+    groups = _req(np.ascontiguousarray(groups, np.int32), np.int32, "groups")
+    out = np.zeros((int(groups[1]), closest_n), np.int32)
+    nq = C.c_int()
+    check(lib.mcq_closest_replay(_vp(groups), groups.size, closest_n, 1 if skip_first else 0, _vp(out), C.byref(nq)))
+    return out
+
+
 def consensus_batch(ref_seqs, closest_refs, device=0):
     """cons_query_nucls (Q, num_bases) int8 codes 0..3: per-query majority base over its closest references
     (dmodel.c:664-681)."""
@@ -144,6 +170,13 @@ def consensus_batch(ref_seqs, closest_refs, device=0):
     out = np.zeros((Q, nb), np.int8)
     check(lib.mcq_consensus_batch(device, _vp(ref_seqs), nb, N, _vp(closest_refs), Q, L, nb, _vp(out)))
     return out
+
+
+def consensus_last_timing():
+    """device ms of the consensus kernel of the last consensus_batch call"""
+    a = C.c_float()
+    check(_lib.load().mcq_consensus_last_timing(C.byref(a)))
+    return a.value
 
 
 def closest_last_timing():

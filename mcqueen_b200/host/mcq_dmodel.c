@@ -487,6 +487,37 @@ static void blob_get(const char *tag, int r, unsigned char *data, size_t len)
   mcq_die("timed out waiting for %s", path);
 }
 
+/* a blob of any length: rank r writes {length, bytes}, the reader allocates */
+static void blob_put_var(const char *tag, int r, const void *data, size_t len)
+{
+  unsigned char *buf = malloc(sizeof(size_t) + len);
+  memcpy(buf, &len, sizeof(size_t));
+  memcpy(buf + sizeof(size_t), data, len);
+  blob_put(tag, r, buf, sizeof(size_t) + len);
+  free(buf);
+}
+
+static void *blob_get_var(const char *tag, int r, size_t *len)
+{
+  char path[PATH_MAX];
+  blob_path(path, sizeof(path), tag, r);
+  for(int tries = 0; tries < 12000; tries++) {
+    FILE *f = fopen(path, "rb");           /* (the file appears complete: written aside and renamed) */
+    if(f) {
+      void *data = NULL;
+      if(fread(len, sizeof(size_t), 1, f) == 1 && (data = malloc(*len ? *len : 1)) != NULL &&
+         fread(data, 1, *len, f) == *len) {
+        fclose(f);
+        return data;
+      }
+      free(data);
+      fclose(f);
+    }
+    usleep(10000);
+  }
+  mcq_die("timed out waiting for %s", path);
+}
+
 int main(int argc, char **argv)
 {
   parse(argc, argv);
@@ -574,17 +605,41 @@ int main(int argc, char **argv)
   printf("lambda_rec:%f\n", lambda_rec);
   printf("Loaded %i sites.\n", S);
 
-  /* closest-L for ALL queries on every rank: the tie shuffles consume the shared random() stream in
-   * query order (closest_seqs.c:57-64), so every rank must replay all of them */
+  /* this rank's shard of the queries */
+  const int q0 = (int)((long long)Qall * rank / world), q1 = (int)((long long)Qall * (rank + 1) / world);
+  const int Q = q1 - q0;
+
+  /* closest-L.  The distances and the selection groups (the references closer than the boundary distance, those
+   * at it) are computed for this rank's queries only; the tie shuffles consume the shared random() stream in
+   * query order (closest_seqs.c:57-64), so the groups of all ranks are exchanged and every rank replays all of
+   * them: the lists are those of a single process. */
   const bool skip_first = !separate_reference_set;
   if((skip_first ? closest_n + 1 : closest_n) > N) mcq_die("closest_n exceeds the number of references");
   int *closest_all = malloc((size_t)Qall * closest_n * sizeof(int));
   {
-    char *rflat = malloc((size_t)N * nb), *qflat = malloc((size_t)Qall * nb);
+    char *rflat = malloc((size_t)N * nb), *qflat = malloc((size_t)(Q ? Q : 1) * nb);
     for(int r = 0; r < N; r++) memcpy(rflat + (size_t)r * nb, ref_seqs[r], nb);
-    for(int q = 0; q < Qall; q++) memcpy(qflat + (size_t)q * nb, query_seqs[q], nb);
-    CHECK(mcq_closest_batch(device, rflat, nb, N, qflat, nb, Qall, (int)nb, closest_n, skip_first, closest_all));
+    for(int q = 0; q < Q; q++) memcpy(qflat + (size_t)q * nb, query_seqs[q0 + q], nb);
+    int *groups = NULL;
+    size_t count = 0;
+    if(Q == 0) mcq_die("more ranks than query sequences");
+    CHECK(mcq_closest_groups(device, rflat, nb, N, qflat, nb, Q, (int)nb, closest_n, skip_first, &groups, &count));
     free(rflat); free(qflat);
+    if(world > 1) blob_put_var("closest", rank, groups, count * sizeof(int));
+    for(int r = 0; r < world; r++) {
+      const int r0 = (int)((long long)Qall * r / world);
+      int *g = groups, nq = 0;
+      size_t cnt = count;
+      if(r != rank) {
+        size_t len = 0;
+        g = blob_get_var("closest", r, &len);
+        cnt = len / sizeof(int);
+      }
+      CHECK(mcq_closest_replay(g, cnt, closest_n, skip_first, closest_all + (size_t)r0 * closest_n, &nq));
+      if(nq != (int)((long long)Qall * (r + 1) / world) - r0) mcq_die("rank %d selected for %d queries", r, nq);
+      if(r != rank) free(g);
+    }
+    mcq_free(groups);
   }
   printf("Example - closest references to query sequence 1:\n");
   for(int r = 0; r < closest_n; r++) printf("%i ", closest_all[r]);
@@ -647,9 +702,6 @@ int main(int argc, char **argv)
     for(int h = 1; h < H; h++) for(int i = 0; i < MCQ_INIT_WINDOWS; i++) c.hw[h].rev->w[i].coeff = 1;
   }
 
-  /* this rank's shard of the queries */
-  const int q0 = (int)((long long)Qall * rank / world), q1 = (int)((long long)Qall * (rank + 1) / world);
-  const int Q = q1 - q0;
   c.Q = Q;
   McqData d;
   mcq_prepare(&d, device, ref_seqs, N, query_seqs + q0, Q, cons_seqs, ncons, hla_rows + q0, H,
@@ -731,6 +783,7 @@ int main(int argc, char **argv)
     CHECK(mcq_ctx_exchange_sum(c.ctx, &one));
     if((int)one != world) mcq_die("rank exchange returned %f for %d ranks", one, world);
     if(rank == 0) { char f[PATH_MAX]; blob_path(f, sizeof(f), "seed", 0); unlink(f); }
+    { char f[PATH_MAX]; blob_path(f, sizeof(f), "closest", rank); unlink(f); }
   }
   if(resume_path != NULL) printf("Likelihood from loaded .json file: %f.\n", resume_llk);
 

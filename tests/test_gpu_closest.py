@@ -131,3 +131,41 @@ def test_consensus_batch_matches_reference_generate_consensus_subset(api, S, N, 
     want = cpu_libs.reference_consensus_subset(refs, closest)
     got = api.consensus_batch(refs, closest)
     assert np.array_equal(got, want)
+
+
+def test_sharded_groups_replayed_in_rank_order_equal_the_single_call(api):
+    """Queries sharded over ranks: every rank's block of selection groups, replayed in rank order from one seed,
+    gives the lists (and the number of draws) of the single-process call - and of the CPU reference."""
+    d = _data(S=100, N=300, Q=41)
+    refs, qs = d["ref_seqs"], d["query_seqs"]
+    for L, skip in ((20, False), (33, True)):
+        cpu_libs.srandom(5)
+        want = api.closest_batch(refs, qs, L, skip_first=skip)
+        after = cpu_libs.libc_random()
+        blocks = [api.closest_groups(refs, np.ascontiguousarray(qs[a:b]), L, skip_first=skip)
+                  for a, b in ((0, 13), (13, 14), (14, 41))]
+        cpu_libs.srandom(5)
+        got = np.concatenate([api.closest_replay(b, L, skip_first=skip) for b in blocks])
+        assert np.array_equal(got, want) and cpu_libs.libc_random() == after
+    with pytest.raises(api._lib.McqError, match="another closest_n"):
+        api.closest_replay(blocks[0], 20)
+
+
+def test_many_boundary_ties_overflow_the_pool_and_are_redone(api):
+    """A panel of near-identical references: the '== T' groups hold almost the whole panel for every query, far
+    more than the pool of a chunk is sized for - the chunk is redone with a pool of the exact size."""
+    rng = np.random.default_rng(1)
+    base = rng.integers(0, 4, 90)
+    N, Q = 40000, 96
+    refs = np.frombuffer(b"TCAG", np.uint8)[np.repeat(base[None], N, 0)].copy()
+    refs[::1000, :2] = ord("N")
+    qs = refs[:Q].copy()
+    qs[:, 7] = ord("-")
+    chk = checker()
+    cpu_libs.srandom(3)
+    want = np.stack([chk.closest(chk.hamming(refs, qs[q]), 50) for q in range(0, Q, 16)])
+    cpu_libs.srandom(3)
+    got = api.closest_batch(refs, np.ascontiguousarray(qs[::16]), 50)
+    assert np.array_equal(got, want)
+    got_all = api.closest_batch(refs, qs, 50)            # 96 x ~40 000 ties > the pool of 2^20 entries
+    assert got_all.shape == (Q, 50) and all(len(set(r)) == 50 for r in got_all)
