@@ -613,6 +613,20 @@ def main():
         extras["window_proposal_cells_per_s"] = p.Q * (w1 - w0 + 1) * L / t * 1e3
         t = timed(lambda: ctx.propose(api.PROP_REC, S // 2, value0=0.02), reps=5)
         extras["single_site_proposal_ms"] = t
+        # the same proposal, every kernel bracketed by its own pair of events (the figure above spans the call: it
+        # ends when the host, having seen the result, records the closing event)
+        ctx.enable_timing(2)
+        ctx.kernel_time(api.K_FORWARD, reset=True)
+        for _ in range(5):
+            ctx.propose(api.PROP_REC, S // 2, value0=0.02)
+        kf, nf = ctx.kernel_time(api.K_FORWARD)
+        ks, ns = ctx.kernel_time(api.K_SUM)
+        extras["single_site_kernels_ms"] = {"column": kf / max(nf, 1), "sum_and_exchange": ks / max(ns, 1)}
+        # 25 L bytes per query move for one column (F in, tmp_F out, B in, 8 B each, + the G row)
+        extras["single_site_roofline_frac"] = 25.0 * L * p.Q / ((kf / max(nf, 1) + ks / max(ns, 1)) * 1e-3) / 1e9 / \
+            (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0)
+        ctx.enable_timing(1)
         ctx.propose(api.PROP_REV, w0, w1, value0=1.1)
         ctx.accept()
         extras["window_accept_ms"] = ctx.last_timing()[0]

@@ -623,7 +623,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     CK(cudaStreamWaitEvent(c->stream, c->ev_chunk[1 + k], 0));
     {
       KScope ks(c, MCQ_K_GATHER);
-      CK(mcq_launch_gather(c->st_trip_pad, c->st_closest + q0 * L, c->st_cons + q0 * 3 * S, c->st_slot_of, c->st_trip_tab,
+      CK(mcq_launch_gather(c->st_trip_pad, c->st_trip, c->st_closest + q0 * L, c->st_cons + q0 * 3 * S, c->st_slot_of,
                            c->G + q0 * S * c->Lg, c->hla + q0 * H, (int)nq, S, L, c->Lg, N, H, c->d_err, c->stream));
     }
     CK(mcq_launch_rowdesc(st_all, c->rowdesc, (int)q0, (int)nq, c->stream));
@@ -797,6 +797,11 @@ static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int star
   a.logBIG = c->logBIG;
   a.pipe = (sparse ? c->carriers[hla] : c->d.num_query) <= c->pipe_max;
   KScope ks(c, MCQ_K_FORWARD);
+  if (c->wpq == 0 && mode == FWD_PROPOSAL && start == end && start > 0 && !lazy && !sparse && llk_mode == 1 &&
+      tuned_blocks == nullptr) {
+    CK(mcq_launch_column(a, c->stream));       // a one-column proposal, nothing owed: the direct kernel
+    return 0;
+  }
   if (c->wpq > 0) {
     if (tuned_blocks != nullptr) *tuned_blocks = 0;      // (the residency sweep is for the one-warp kernels)
     CK(mcq_launch_forward_mw(a, c->wpq, c->stream));

@@ -134,7 +134,7 @@ struct Scratch {
     DK(cudaMemcpyAsync(E, h_E.data(), h_E.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     DK(cudaMemcpyAsync(R, Rh, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, stream));
     DK(mcq_launch_gather_prepare(trip, trip_pad, slot_of, trip_tab, S, L, stream));
-    DK(mcq_launch_gather(trip_pad, closest, cons, slot_of, trip_tab, G, nullptr, 1, S, L, Lg, L, 1, d_err, stream));
+    DK(mcq_launch_gather(trip_pad, trip, closest, cons, slot_of, G, nullptr, 1, S, L, Lg, L, 1, d_err, stream));
   }
 
   // one column host[L][S] (stride S) -> device column

@@ -140,18 +140,21 @@ struct EmisArgs {
 
 // launchers (mcq_kernels.cu); all asynchronous on `stream`, return cudaGetLastError()
 cudaError_t mcq_launch_tables_init();
-// the query-independent tables of the gather: trip_tab [ceil32(S)][128] and trip_pad [N][ceil32(S)] (both scratch)
+// the query-independent tables of the gather: trip_tab [ceil32(S)][128] (triplet -> slot per site) and trip_pad
+// [N][ceil32(S)], the SLOT of every reference codon (both scratch)
 cudaError_t mcq_launch_gather_prepare(const int8_t *ref_triplets, int8_t *trip_pad, const uint8_t *slot_of /*[S][64]*/,
                                       uint8_t *trip_tab, int S, int N, cudaStream_t stream);
-// G rows of Q queries (pointers address the first of them); hla_chars [Q][H] '0'/'1' -> 0/1 in place, or null;
-// err: device flag, 2 = closest out of range
-cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int *closest, const int8_t *cons_nucls,
-                              const uint8_t *slot_of, const uint8_t *trip_tab, uint8_t *G, uint8_t *hla_chars, int Q,
+// G rows of Q queries (pointers address the first of them); trip = ref_triplets on the device (for the triplets with
+// unknown bases); hla_chars [Q][H] '0'/'1' -> 0/1 in place, or null; err: device flag, 2 = closest out of range
+cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int8_t *trip, const int *closest, const int8_t *cons_nucls,
+                              const uint8_t *slot_of, uint8_t *G, uint8_t *hla_chars, int Q,
                               int S, int L, int Lg, int N, int H, int *err, cudaStream_t stream);
 // rowdesc[q][s] for queries q0 .. q0+nq-1 from desc and query_codon (st.rowdesc itself is not read)
 cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, int q0, int nq, cudaStream_t stream);
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
+// a one-column proposal with nothing owed (start == end > 0, all queries): same values as mcq_launch_forward's
+cudaError_t mcq_launch_column(const FwdArgs &a, cudaStream_t stream);
 // time the launch at every residency (blocks per SM) the kernel allows and keep the fastest for launches of
 // this kernel with this many queries; the launch itself must be repeatable (same inputs, same outputs)
 cudaError_t mcq_tune_forward(const FwdArgs &a, cudaStream_t stream, int *best_blocks, float *best_ms);

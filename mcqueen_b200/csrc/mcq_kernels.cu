@@ -91,10 +91,12 @@ __global__ void __launch_bounds__(128) k_trip_table(const uint8_t *__restrict__ 
   trip_tab[(size_t)s * 128 + t] = v;
 }
 
-// ref_triplets[N][S] -> rows of pitch Sp (a multiple of 32, padded with "no state"): every run of 32
-// sites of a reference is then one aligned 32-byte sector that a thread fetches with two 16-byte loads
-__global__ void __launch_bounds__(256) k_pad_rows(const int8_t *__restrict__ src, uint32_t *__restrict__ dst, int N, int S,
-                                                  int Sp) {
+// ref_triplets[N][S] -> the SLOT of every reference codon, rows of pitch Sp (a multiple of 32, padded with "no
+// slot"): the query-independent half of triplet_to_codon is done once per panel cell here instead of once per
+// (query, copy state, site) in the gather, and every run of 32 sites of a reference is one aligned 32-byte sector.
+// Triplets with an unknown base keep MCQ_NEEDS_CONS: they are resolved per query.
+__global__ void __launch_bounds__(256) k_slot_rows(const int8_t *__restrict__ src, const uint8_t *__restrict__ trip_tab,
+                                                   uint32_t *__restrict__ dst, int N, int S, int Sp) {
   const size_t wpr = (size_t)(Sp >> 2), n = (size_t)N * wpr;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t row = i / wpr;
@@ -102,31 +104,30 @@ __global__ void __launch_bounds__(256) k_pad_rows(const int8_t *__restrict__ src
     const int8_t *p = src + row * S + c0;
     uint32_t w = 0;
 #pragma unroll
-    for (int b = 0; b < 4; b++) w |= (uint32_t)(uint8_t)(c0 + b < S ? p[b] : 125) << (8 * b);
+    for (int b = 0; b < 4; b++) {
+      const unsigned v = c0 + b < S ? trip_tab[(size_t)(c0 + b) * 128 + (uint8_t)p[b]] : (unsigned)MCQ_NOSLOT;
+      w |= v << (8 * b);
+    }
     dst[i] = w;
   }
 }
 
 // One block per (query, 32 sites).  A PAIR of lanes owns eight consecutive physical positions of the G rows (=
 // eight copy states): the even lane takes the block's first 16 sites, the odd lane the other 16, so the two
-// 16-byte loads of a pair fall into one aligned 32-byte sector of the reference's (re-pitched) row and a warp
-// instruction touches 16 sectors, not 32 - the kernel is bound by the L1 tag stage.  Each triplet becomes the
-// site's slot through the table in shared memory; per site a lane stores its 8 bytes, the even (odd) lanes of a
-// warp together 128 contiguous bytes of one G row.
-__global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ trip_pad, int Sp,
+// 16-byte loads of a pair fall into one aligned 32-byte sector of the reference's slot row and a warp
+// instruction touches 16 sectors, not 32.  What is left is a byte transpose in registers: per site a lane packs
+// the eight slots of its references and stores its 8 bytes, the even (odd) lanes of a warp together 128
+// contiguous bytes of one G row.
+__global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ slot_rows, int Sp,
+                                                   const int8_t *__restrict__ trip,
                                                    const int *__restrict__ closest,
                                                    const int8_t *__restrict__ cons_nucls,
                                                    const uint8_t *__restrict__ slot_of,
-                                                   const uint8_t *__restrict__ trip_tab,
                                                    uint8_t *__restrict__ G, int S, int L, int Lg, int N,
                                                    int *__restrict__ err) {
-  __shared__ __align__(16) uint8_t s_tab[32 * 128]; // [site of the block][triplet]
   const int q = blockIdx.y;
   const int s0 = blockIdx.x * 32;
   const int lg2 = 31 - __clz(Lg >> 5);              // log2(2 * NJ)
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)
-    reinterpret_cast<uint4 *>(s_tab)[i] = reinterpret_cast<const uint4 *>(trip_tab + (size_t)s0 * 128)[i];
-  __syncthreads();
   const int pos = 8 * (threadIdx.x >> 1), sb = 16 * (threadIdx.x & 1);   // first position, first site
   if (pos >= Lg) return;
   // the eight references; padding states (r >= L) read row 0 and are overwritten with MCQ_NOSLOT below
@@ -143,22 +144,20 @@ __global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ tr
     } else if (k < 4) pad0 |= 0xFFu << (8 * k);
     else pad1 |= 0xFFu << (8 * (k - 4));
     refs[k] = ref;
-    const uint4 a = *reinterpret_cast<const uint4 *>(trip_pad + (size_t)ref * Sp + s0 + sb);
+    const uint4 a = *reinterpret_cast<const uint4 *>(slot_rows + (size_t)ref * Sp + s0 + sb);
     w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
   }
   const unsigned fill0 = pad0 & (MCQ_NOSLOT * 0x01010101u), fill1 = pad1 & (MCQ_NOSLOT * 0x01010101u);
   uint8_t *dst = G + ((size_t)q * S + s0 + sb) * Lg + pos;
   const int nrow = min(16, S - s0 - sb);            // rows of this half inside the genome (may be <= 0)
-  const uint8_t *tbase = s_tab + sb * 128;
   unsigned worst = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
-    const uint8_t *tb = tbase + i * 128;
-    unsigned b[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) b[k] = tb[__byte_perm(w[k][i >> 2], 0, 0x4440 + (i & 3))];
-    unsigned lo = __byte_perm(b[0] | (b[1] << 8), b[2] | (b[3] << 8), 0x5410);
-    unsigned hi = __byte_perm(b[4] | (b[5] << 8), b[6] | (b[7] << 8), 0x5410);
+    // byte (i & 3) of word (i >> 2) of each of the eight rows -> two words
+    const unsigned sel2 = 0x0040u + (i & 3) * 0x0011u;            // {b of x, b of y, 0, 0}
+    const unsigned p01 = __byte_perm(w[0][i >> 2], w[1][i >> 2], sel2), p23 = __byte_perm(w[2][i >> 2], w[3][i >> 2], sel2);
+    const unsigned p45 = __byte_perm(w[4][i >> 2], w[5][i >> 2], sel2), p67 = __byte_perm(w[6][i >> 2], w[7][i >> 2], sel2);
+    unsigned lo = __byte_perm(p01, p23, 0x5410), hi = __byte_perm(p45, p67, 0x5410);
     lo = (lo & ~pad0) | fill0;
     hi = (hi & ~pad1) | fill1;
     worst |= lo | hi;
@@ -176,10 +175,10 @@ __global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ tr
         int ref = 0;                                  // (refs[] indexed by a loop variable would go to local memory)
 #pragma unroll
         for (int kk = 0; kk < 8; kk++) if (kk == k) ref = refs[kk];
-        const unsigned tt = (uint8_t)trip_pad[(size_t)ref * Sp + s];
-        if (s_tab[(sb + i) * 128 + tt] != MCQ_NEEDS_CONS) continue;
-        const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
+        const unsigned tt = (uint8_t)trip[(size_t)ref * S + s];
         int d0 = tt / 25, d1 = (tt / 5) % 5, d2 = tt % 5;
+        if (tt >= 125 || (d0 != 4 && d1 != 4 && d2 != 4)) continue;
+        const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
         if (d0 == 4) d0 = cn[0];
         if (d1 == 4) d1 = cn[1];
         if (d2 == 4) d2 = cn[2];
@@ -203,13 +202,13 @@ cudaError_t mcq_launch_gather_prepare(const int8_t *ref_triplets, int8_t *trip_p
   const size_t words = (size_t)N * (Sp / 4);
   unsigned blocks = (unsigned)((words + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_pad_rows<<<blocks, 256, 0, stream>>>(ref_triplets, reinterpret_cast<uint32_t *>(trip_pad), N, S, Sp);
+  k_slot_rows<<<blocks, 256, 0, stream>>>(ref_triplets, trip_tab, reinterpret_cast<uint32_t *>(trip_pad), N, S, Sp);
   return cudaGetLastError();
 }
 
 // G rows (and the 0/1 HLA flags) of Q queries; the pointers address the first of them
-cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int *closest, const int8_t *cons_nucls,
-                              const uint8_t *slot_of, const uint8_t *trip_tab, uint8_t *G, uint8_t *hla_chars, int Q,
+cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int8_t *trip, const int *closest, const int8_t *cons_nucls,
+                              const uint8_t *slot_of, uint8_t *G, uint8_t *hla_chars, int Q,
                               int S, int L, int Lg, int N, int H, int *err, cudaStream_t stream) {
   const int sblocks = (S + 31) / 32, Sp = sblocks * 32;
   if (hla_chars != nullptr) {
@@ -220,8 +219,8 @@ cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int *closest, const 
   for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
     int nq = Q - q0 < 65535 ? Q - q0 : 65535;
     dim3 grid(sblocks, nq);
-    k_gather<<<grid, threads, 0, stream>>>(trip_pad, Sp, closest + (size_t)q0 * L, cons_nucls + (size_t)q0 * 3 * S,
-                                           slot_of, trip_tab, G + (size_t)q0 * S * Lg, S, L, Lg, N, err);
+    k_gather<<<grid, threads, 0, stream>>>(trip_pad, Sp, trip, closest + (size_t)q0 * L, cons_nucls + (size_t)q0 * 3 * S,
+                                           slot_of, G + (size_t)q0 * S * Lg, S, L, Lg, N, err);
   }
   return cudaGetLastError();
 }
@@ -1324,6 +1323,113 @@ __global__ void __launch_bounds__(128) k_dot(const DotArgs a) {
 cudaError_t mcq_launch_dot(const DotArgs &a, cudaStream_t stream) {
   k_dot<<<(unsigned)(((size_t)a.st.Q * 32 + 127) / 128), 128, 0, stream>>>(a);
   return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K4c: a ONE-COLUMN proposal (recombination_move, selection_move: mcmc_moves.c:213-224, 366-395) when nothing is
+// owed before or behind the column.  The general sweep kernel spends its time here on set-up: descriptor, ring
+// prologue, column load, row wait, each a dependent trip to memory.  Here every load a warp needs - the current
+// column s-1, the backward column s, the slot bytes and the emission row of site s - is issued at once; one
+// warp per query, four queries per block.  Same operations in the same order as k_forward + its epilogue: the
+// per-query values are bit-identical.
+// ------------------------------------------------------------------------------------------
+template <int NJ, bool FULL>
+__global__ void __launch_bounds__(128) k_column(const FwdArgs a) {
+  __shared__ __align__(16) double s_e[4][MCQ_NOSLOT + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q = blockIdx.x * 4 + wid;
+  if (q >= a.st.Q) return;
+  const int S = a.st.S, Ls = a.st.Ls, s = a.start;
+  const size_t qs = (size_t)q * S, qoff = qs * Ls;
+  const unsigned sel0 = a.sel ? a.sel[qs + s - 1] : 0u, selS = a.sel ? a.sel[qs + s] : 0u;
+  const unsigned rd = a.st.rowdesc[qs + s];
+  int cnt = a.Fn_in[qs + s - 1];
+  const int bn = a.Bn[qs + s];
+  const double Rs = (s == a.r_site) ? a.r_value : a.R[s];
+  bool inrow[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) inrow[j] = FULL || (64 * j + 2 * lane < Ls);
+  unsigned g[(2 * NJ + 3) / 4];
+  load_slots<NJ, 0>(a.st.G + (qs + s) * (64 * NJ) + lane * (2 * NJ), g);
+  const double *__restrict__ Fi = (sel0 ? a.Fout : a.Fin) + qoff + (size_t)(s - 1) * Ls + 2 * lane;
+  const double *__restrict__ Bc = a.B + qoff + (size_t)s * Ls + 2 * lane;
+  double p0[NJ], p1[NJ], b0[NJ], b1[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    p0[j] = p1[j] = b0[j] = b1[j] = 0.0;
+    if (inrow[j]) {
+      const double2 v = *reinterpret_cast<const double2 *>(Fi + 64 * j);
+      const double2 b = *reinterpret_cast<const double2 *>(Bc + 64 * j);
+      p0[j] = v.x; p1[j] = v.y; b0[j] = b.x; b1[j] = b.y;
+    }
+  }
+  double *es = s_e[wid];
+  {
+    const int kr = (int)(rd >> MCQ_RD_SHIFT);
+    const double *row = a.em.tab + (rd & MCQ_RD_MASK);
+    if (lane < kr) es[1 + lane] = row[lane];
+    if (lane + 32 < kr) es[33 + lane] = row[lane + 32];
+    if (lane == 0) {
+      es[0] = a.em.ec ? a.em.ec[qs + s] : 0.0;
+      es[MCQ_NOSLOT] = 0.0;
+    }
+  }
+  __syncwarp();
+  double loc = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) { loc += p0[j]; loc += p1[j]; }
+  double tot = warp_sum(loc);
+  const double jump = tot * (Rs * (1.0 / (double)a.st.N));
+  const double stay = 1 - Rs;
+  double la = 0.0, lb = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const double v0 = __fma_rn(stay, p0[j], jump) * emis_at(es, g[j >> 1], (j & 1) * 2);
+    const double v1 = __fma_rn(stay, p1[j], jump) * emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+    p0[j] = v0; p1[j] = v1;
+    la += v0; lb += v1;
+  }
+  tot = warp_sum(la + lb);
+  if (tot < MCQ_BIGI) {                         // forward_backward.c:163-167
+    ++cnt;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { p0[j] *= MCQ_BIG; p1[j] *= MCQ_BIG; }
+  }
+  // the proposal's column goes into the buffer that does not hold the current column s
+  double *__restrict__ Fo = (selS ? const_cast<double *>(a.Fin) : a.Fout) + qoff + (size_t)s * Ls + 2 * lane;
+  double dl = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++)
+    if (inrow[j]) {
+      __stcs(reinterpret_cast<double2 *>(Fo + 64 * j), make_double2(p0[j], p1[j]));
+      dl += p0[j] * b0[j]; dl += p1[j] * b1[j];
+    }
+  const double dot = warp_sum(dl);
+  if (lane == 0) {
+    a.Fn_out[qs + s] = cnt;
+    a.llk_out[q] = log(dot) - (cnt + bn) * a.logBIG;     // mcmc_moves.c:220-223
+  }
+}
+
+template <int NJ>
+static cudaError_t launch_column_nj(const FwdArgs &a, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((a.st.Q + 3) / 4);
+  if (a.st.Ls == 64 * NJ) k_column<NJ, true><<<blocks, 128, 0, stream>>>(a);
+  else k_column<NJ, false><<<blocks, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// a.start == a.end > 0, every query active, columns start-1 of F and start of B current, llk_mode 1
+cudaError_t mcq_launch_column(const FwdArgs &a, cudaStream_t stream) {
+  if (a.start != a.end || a.start <= 0 || a.active != nullptr || a.fv != nullptr || a.llk_mode != 1) return cudaErrorInvalidValue;
+  switch (a.st.Lg / 64) {
+    case 1: return launch_column_nj<1>(a, stream);
+    case 2: return launch_column_nj<2>(a, stream);
+    case 4: return launch_column_nj<4>(a, stream);
+    case 8: return launch_column_nj<8>(a, stream);
+    case 16: return launch_column_nj<16>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_set_valid(int *fv, int *bv, int Q, int H, int f, int b,
