@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k_slot_rows(const int8_t *__restrict__ sr
 // instruction touches 16 sectors, not 32.  What is left is a byte transpose in registers: per site a lane packs
 // the eight slots of its references and stores its 8 bytes, the even (odd) lanes of a warp together 128
 // contiguous bytes of one G row.
-__global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ slot_rows, int Sp,
+__global__ void __launch_bounds__(256, 4) k_gather(const int8_t *__restrict__ slot_rows, int Sp,
                                                    const int8_t *__restrict__ trip,
                                                    const int *__restrict__ closest,
                                                    const int8_t *__restrict__ cons_nucls,
@@ -126,12 +126,10 @@ __global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ sl
                                                    uint8_t *__restrict__ G, int S, int L, int Lg, int N,
                                                    int *__restrict__ err) {
   const int q = blockIdx.y;
-  const int s0 = blockIdx.x * 32;
   const int lg2 = 31 - __clz(Lg >> 5);              // log2(2 * NJ)
   const int pos = 8 * (threadIdx.x >> 1), sb = 16 * (threadIdx.x & 1);   // first position, first site
   if (pos >= Lg) return;
   // the eight references; padding states (r >= L) read row 0 and are overwritten with MCQ_NOSLOT below
-  unsigned w[8][4];
   unsigned pad0 = 0, pad1 = 0;                      // byte k = 0xFF when position pos + k (+4) is padding
   int refs[8];
 #pragma unroll
@@ -144,10 +142,16 @@ __global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ sl
     } else if (k < 4) pad0 |= 0xFFu << (8 * k);
     else pad1 |= 0xFFu << (8 * (k - 4));
     refs[k] = ref;
-    const uint4 a = *reinterpret_cast<const uint4 *>(slot_rows + (size_t)ref * Sp + s0 + sb);
-    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
   }
   const unsigned fill0 = pad0 & (MCQ_NOSLOT * 0x01010101u), fill1 = pad1 & (MCQ_NOSLOT * 0x01010101u);
+  // the block's share of the 32-site blocks (the reference list is fetched once for all of them)
+  for (int s0 = blockIdx.x * 32; s0 < S; s0 += gridDim.x * 32) {
+  unsigned w[8][4];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(slot_rows + (size_t)refs[k] * Sp + s0 + sb);
+    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+  }
   uint8_t *dst = G + ((size_t)q * S + s0 + sb) * Lg + pos;
   const int nrow = min(16, S - s0 - sb);            // rows of this half inside the genome (may be <= 0)
   unsigned worst = 0;
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(256, 2) k_gather(const int8_t *__restrict__ sl
       }
     }
   }
+  }   // site blocks
 }
 
 // '0'/'1' characters (load_data.c:125-157) -> 0/1, in place
@@ -218,7 +223,7 @@ cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int8_t *trip, const 
   const int threads = Lg / 4 < 32 ? 32 : Lg / 4;
   for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
     int nq = Q - q0 < 65535 ? Q - q0 : 65535;
-    dim3 grid(sblocks, nq);
+    dim3 grid((sblocks + 3) / 4, nq);            // four 32-site blocks per thread block
     k_gather<<<grid, threads, 0, stream>>>(trip_pad, Sp, trip, closest + (size_t)q0 * L, cons_nucls + (size_t)q0 * 3 * S,
                                            slot_of, G + (size_t)q0 * S * Lg, S, L, Lg, N, err);
   }
