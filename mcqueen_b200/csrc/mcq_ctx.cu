@@ -1250,28 +1250,25 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
   } else {
     const bool sparse = (ov.kind == MCQ_PROP_ESC) && c->opt_sparse_esc != 0;
     {
+      CommitArgs k{};
+      k.st = st; k.m = c->m; k.ov = ov;
+      k.tab_t = c->tab_t; k.atab_t = c->atab_t; k.ec_t = c->ec_t; k.ac_t = c->ac_t;
+      k.tab = c->tab; k.atab = c->atab; k.ec = c->ec; k.ac = c->ac;
+      if (ov.kind == MCQ_PROP_SEL || ov.kind == MCQ_PROP_REV) {   // shared rows of the range
+        k.t0 = (size_t)c->toff_h[ov.start]; k.t1 = (size_t)c->toff_h[ov.end + 1];
+        k.a0 = (size_t)c->aoff_h[ov.start]; k.a1 = (size_t)c->aoff_h[ov.end + 1];
+      }
+      k.copy_cons = (ov.kind == MCQ_PROP_SEL || ov.kind == MCQ_PROP_ESC) ? 1 : 0;   // per-query consensus values
+      k.sel = c->sel; k.Tn = c->Tn; k.Fn = c->Fn;
+      k.active = sparse ? c->hla : nullptr; k.active_hla = ov.hla;
+      // with lazy refills the refills of mcmc_moves.c:266-279 are owed, not run: the next evaluation completes
+      // what it needs (marks on the device here, mirrored on the host below)
+      k.fv = c->fv; k.bv = c->bv; k.mark = c->opt_lazy ? ov.end : -1;
       KScope ks(c, MCQ_K_COMMIT);
-      CK(mcq_launch_commit_params(st, c->m, ov, c->stream));
-    }
-    if (ov.kind == MCQ_PROP_SEL || ov.kind == MCQ_PROP_REV) {   // shared rows of the range
-      const size_t t0 = (size_t)c->toff_h[ov.start], t1 = (size_t)c->toff_h[ov.end + 1];
-      const size_t a0 = (size_t)c->aoff_h[ov.start], a1 = (size_t)c->aoff_h[ov.end + 1];
-      KScope ks(c, MCQ_K_COMMIT);
-      CK(mcq_launch_copy(c->tab_t + t0, c->tab + t0, t1 - t0, c->stream));
-      CK(mcq_launch_copy(c->atab_t + a0, c->atab + a0, a1 - a0, c->stream));
-      c->launches++;
-    }
-    if (ov.kind == MCQ_PROP_SEL || ov.kind == MCQ_PROP_ESC) {   // per-query consensus values of the range
-      KScope ks(c, MCQ_K_COMMIT);
-      CK(mcq_launch_commit_cons(st, c->ec_t, c->ac_t, c->ec, c->ac, ov.start, ov.end, c->stream));
-    }
-    {
-      KScope ks(c, MCQ_K_COMMIT);
-      CK(mcq_launch_commit_cols(st, c->sel, c->Tn, c->Fn, ov.start, ov.end, sparse ? c->hla : nullptr, ov.hla, c->stream));
+      CK(mcq_launch_commit_all(k, c->stream));
     }
     if (c->opt_lazy) {
-      // the refills of mcmc_moves.c:266-279 are owed, not run: the next evaluation completes what it needs
-      if (set_marks(c, ov.end, ov.end, sparse, ov.hla)) return 1;
+      for_active(c, sparse, ov.hla, [&](int q) { c->fv_h[q] = ov.end; c->bv_h[q] = ov.end; });
     } else {
       // F after the range and B from the range down to 0 do not depend on each other: two streams
       const bool dual = c->timing != 2 && ov.end + 1 < S;

@@ -177,12 +177,19 @@ cudaError_t mcq_launch_emission_both(const EmisArgs &a, cudaStream_t stream);   
 cudaError_t mcq_launch_mu_rescale(const McqStatic &st, const McqModel &m, double mu_new, int nslots,
                                   const double *tab, const double *atab, const double *ec, const double *ac,
                                   double *tab_o, double *atab_o, double *ec_o, double *ac_o, cudaStream_t stream);
-cudaError_t mcq_launch_commit_cols(const McqStatic &st, uint8_t *sel, const int *Tn, int *Fn, int start, int end,
-                                   const uint8_t *active, int active_hla, cudaStream_t stream);
-cudaError_t mcq_launch_copy(const double *src, double *dst, size_t n, cudaStream_t stream);
-cudaError_t mcq_launch_commit_cons(const McqStatic &st, const double *ec_t, const double *ac_t, double *ec,
-                                   double *ac, int start, int end, cudaStream_t stream);
-cudaError_t mcq_launch_commit_params(const McqStatic &st, McqModel m, McqOverride ov, cudaStream_t stream);
+// everything an accepted window / column proposal makes current, in one launch (k_commit_all)
+struct CommitArgs {
+  McqStatic st; McqModel m; McqOverride ov;
+  const double *tab_t, *atab_t, *ec_t, *ac_t;
+  double *tab, *atab, *ec, *ac;
+  size_t t0, t1, a0, a1;          // ranges of the shared table / A values to copy (empty when t0 == t1)
+  int copy_cons;                  // 1: per-query consensus values of start..end
+  uint8_t *sel; const int *Tn; int *Fn;
+  const uint8_t *active; int active_hla;
+  int *fv, *bv; int mark;         // mark >= 0: fv = bv = mark for the active queries
+};
+
+cudaError_t mcq_launch_commit_all(const CommitArgs &a, cudaStream_t stream);
 // host-mapped (pinned) result slot: the reduction kernel writes the total, then the evaluation number
 struct McqHostSlot {
   double value;

@@ -13,6 +13,7 @@
 // without FMA contraction (its Makefile:22 gives -O3 only), and with contraction off the emission
 // rows are bit-identical to the reference's and a cell update differs from it only through the
 // order of the per-site sum over copy states (a warp butterfly here, ascending r there).
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 #include "mcq_internal.cuh"
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE && 
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
   __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wib = MCQ_WPB == 1 ? 0 : (int)(threadIdx.x >> 5);   // (one warp per block: the rings sit at constant addresses)
   if (q >= a.st.Q) return;
   if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) {
     if (lane == 0 && a.llk_out != nullptr) a.llk_out[q] = a.llk_keep[q];
@@ -1099,7 +1100,7 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
   __shared__ __align__(16) uint8_t s_g[MCQ_WPB][MCQ_RING][64 * NJ];
   __shared__ __align__(16) double s_e[MCQ_WPB][MCQ_RING][MCQ_ES];
   const int q = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wib = MCQ_WPB == 1 ? 0 : (int)(threadIdx.x >> 5);   // (one warp per block: the rings sit at constant addresses)
   if (q >= a.st.Q) return;
   if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) return;
   const int S = a.st.S, L = a.st.L, Ls = a.st.Ls;
@@ -1455,99 +1456,71 @@ cudaError_t mcq_launch_set_valid(int *fv, int *bv, int Q, int H, int f, int b, c
 // ------------------------------------------------------------------------------------------
 // K7: accept-commit copies
 // ------------------------------------------------------------------------------------------
-// The proposal's columns start..end become current: their selectors flip (the proposal was written into
-// the buffer that did not hold the current column, so nothing is copied) and the rescale counters follow.
-__global__ void __launch_bounds__(256) k_commit_cols(const McqStatic st, uint8_t *__restrict__ sel,
-                                                     const int *__restrict__ Tn, int *__restrict__ Fn, int start, int W,
-                                                     const uint8_t *__restrict__ active, int active_hla) {
-  const unsigned n = (unsigned)st.Q * (unsigned)W;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned q = i / W;
-    if (active != nullptr && active[(size_t)q * st.H + active_hla] == 0) continue;
-    const size_t o = (size_t)q * st.S + start + (i % W);
-    sel[o] ^= 1;
-    Fn[o] = Tn[o];
-  }
-}
-
-cudaError_t mcq_launch_commit_cols(const McqStatic &st, uint8_t *sel, const int *Tn, int *Fn, int start, int end,
-                                   const uint8_t *active, int active_hla, cudaStream_t stream) {
-  const int W = end - start + 1;
-  const unsigned n = (unsigned)st.Q * (unsigned)W;
-  unsigned blocks = (n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k_commit_cols<<<blocks, 256, 0, stream>>>(st, sel, Tn, Fn, start, W, active, active_hla);
-  return cudaGetLastError();
-}
-
-__global__ void __launch_bounds__(256) k_copy(const double *__restrict__ src, double *__restrict__ dst, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = src[i];
-}
-
-cudaError_t mcq_launch_copy(const double *src, double *dst, size_t n, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  unsigned blocks = (unsigned)((n + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k_copy<<<blocks, 256, 0, stream>>>(src, dst, n);
-  return cudaGetLastError();
-}
-
-// per-query consensus values of sites start..end: tmp -> current
-__global__ void __launch_bounds__(256) k_commit_cons(const McqStatic st, const double *__restrict__ ec_t,
-                                                     const double *__restrict__ ac_t, double *__restrict__ ec,
-                                                     double *__restrict__ ac, int start, int W) {
-  const unsigned n = (unsigned)st.Q * (unsigned)W;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const size_t o = (size_t)(i / W) * st.S + start + (i % W);
-    ec[o] = ec_t[o];
-    ac[o] = ac_t[o];
-  }
-}
-
-cudaError_t mcq_launch_commit_cons(const McqStatic &st, const double *ec_t, const double *ac_t, double *ec,
-                                   double *ac, int start, int end, cudaStream_t stream) {
-  const unsigned n = (unsigned)st.Q * (unsigned)(end - start + 1);
-  unsigned blocks = (n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k_commit_cons<<<blocks, 256, 0, stream>>>(st, ec_t, ac_t, ec, ac, start, end - start + 1);
-  return cudaGetLastError();
-}
-
-// make the proposal's parameter change current (R / omega+rate_out / esc / rev / mu)
-__global__ void k_commit_params(const McqStatic st, McqModel m, McqOverride ov) {
-  const int t = threadIdx.x;
-  switch (ov.kind) {
-    case MCQ_PROP_REC:
-      if (t == 0) m.R[ov.start] = ov.v0;
-      break;
-    case MCQ_PROP_SEL: {
-      const int s = ov.start;
-      if (t == 0) m.omega[s] = ov.v0;
-      // rate_out_of_codons is refreshed for the codons the panel shows at the site (mcmc_moves.c:345-352)
-      for (int k = st.aoff[s] + t - 1; k < st.aoff[s + 1]; k += blockDim.x) {
-        int c;
-        if (k < st.aoff[s]) {               // t == 0 also handles the consensus codon when listed
-          if (!st.cons_in_list[s]) continue;
-          c = st.cons_codon[s];
-        } else c = st.ncodon[k];
-        m.rate_out[(size_t)s * 64 + c] = m.kappa * d_cnt[2][c] + d_cnt[3][c] + ov.v0 * (m.kappa * d_cnt[0][c] + d_cnt[1][c]);
+// One launch makes an accepted window / column proposal current (mcmc_moves.c:263-265,447-449,959-965):
+//   the parameter change itself (R / omega + rate_out_of_codons, mcmc_moves.c:345-352 / esc / rev);
+//   the shared emission rows and the per-query consensus values of the range (tmp -> current);
+//   the columns start..end: their selectors flip (the proposal was written into the buffer that did not hold
+//   the current column, so nothing is copied) and the rescale counters follow;
+//   with lazy refills, the validity marks of the queries touched.
+// The parts touch different arrays: no ordering between them inside the kernel.
+__global__ void __launch_bounds__(256) k_commit_all(const CommitArgs a) {
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const McqStatic &st = a.st;
+  const McqOverride &ov = a.ov;
+  if (blockIdx.x == 0) {
+    const int t = threadIdx.x;
+    switch (ov.kind) {
+      case MCQ_PROP_REC:
+        if (t == 0) a.m.R[ov.start] = ov.v0;
+        break;
+      case MCQ_PROP_SEL: {
+        const int s = ov.start;
+        if (t == 0) a.m.omega[s] = ov.v0;
+        for (int k = st.aoff[s] + t - 1; k < st.aoff[s + 1]; k += blockDim.x) {
+          int c;
+          if (k < st.aoff[s]) {
+            if (!st.cons_in_list[s]) continue;
+            c = st.cons_codon[s];
+          } else c = st.ncodon[k];
+          a.m.rate_out[(size_t)s * 64 + c] = a.m.kappa * d_cnt[2][c] + d_cnt[3][c] + ov.v0 * (a.m.kappa * d_cnt[0][c] + d_cnt[1][c]);
+        }
+        break;
       }
-      break;
+      case MCQ_PROP_ESC:
+        for (int s = ov.start + t; s <= ov.end; s += blockDim.x)
+          a.m.esc[(size_t)ov.hla * st.S + s] = s < ov.split ? ov.v0 : ov.v1;
+        break;
+      case MCQ_PROP_REV:
+        for (int s = ov.start + t; s <= ov.end; s += blockDim.x) a.m.rev[s] = s < ov.split ? ov.v0 : ov.v1;
+        break;
+      default: break;
     }
-    case MCQ_PROP_ESC:
-      for (int s = ov.start + t; s <= ov.end; s += blockDim.x)
-        m.esc[(size_t)ov.hla * st.S + s] = s < ov.split ? ov.v0 : ov.v1;
-      break;
-    case MCQ_PROP_REV:
-      for (int s = ov.start + t; s <= ov.end; s += blockDim.x) m.rev[s] = s < ov.split ? ov.v0 : ov.v1;
-      break;
-    default: break;
   }
+  for (size_t i = a.t0 + tid; i < a.t1; i += nth) a.tab[i] = a.tab_t[i];
+  for (size_t i = a.a0 + tid; i < a.a1; i += nth) a.atab[i] = a.atab_t[i];
+  const unsigned W = (unsigned)(ov.end - ov.start + 1), n = (unsigned)st.Q * W;
+  for (unsigned i = tid; i < n; i += nth) {
+    const unsigned q = i / W;
+    const size_t o = (size_t)q * st.S + ov.start + (i % W);
+    if (a.copy_cons) { a.ec[o] = a.ec_t[o]; a.ac[o] = a.ac_t[o]; }
+    if (a.active != nullptr && a.active[(size_t)q * st.H + a.active_hla] == 0) continue;
+    a.sel[o] ^= 1;
+    a.Fn[o] = a.Tn[o];
+  }
+  if (a.mark >= 0)
+    for (unsigned q = tid; q < (unsigned)st.Q; q += nth) {
+      if (a.active != nullptr && a.active[(size_t)q * st.H + a.active_hla] == 0) continue;
+      a.fv[q] = a.mark; a.bv[q] = a.mark;
+    }
 }
 
-cudaError_t mcq_launch_commit_params(const McqStatic &st, McqModel m, McqOverride ov, cudaStream_t stream) {
-  k_commit_params<<<1, 128, 0, stream>>>(st, m, ov);
+cudaError_t mcq_launch_commit_all(const CommitArgs &a, cudaStream_t stream) {
+  const unsigned n = (unsigned)a.st.Q * (unsigned)(a.ov.end - a.ov.start + 1);
+  size_t most = std::max<size_t>(std::max<size_t>(n, a.t1 - a.t0), (size_t)a.st.Q);
+  unsigned blocks = (unsigned)((most + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks == 0) blocks = 1;
+  k_commit_all<<<blocks, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
