@@ -813,9 +813,10 @@ int main(int argc, char **argv)
   const double T0 = no_anneal ? 1 : 500;
   struct timespec ts0, ts1;
   clock_gettime(CLOCK_MONOTONIC, &ts0);
+  ts1 = ts0;
   time_t t_start = time(NULL);
   int hours_passed = 1, sample_i = 1, chain_i, hours = 0;
-  double prof_s[9] = {0};
+  double prof_s[9] = {0}, state_files_s = 0;
   long prof_n[9] = {0};
   for(chain_i = 0; chain_i < chain_length; chain_i++, sample_i++) {
     int pick = mcq_rand_lim(total);
@@ -869,6 +870,10 @@ int main(int argc, char **argv)
       else if(chain_i == chain_length - 1) chain_length *= 2;
     } else if(chain_i == chain_length - 1) last = true;
     if(last) {
+      /* the chain ends here: the device is drained and the clock stopped before the state (with the closest-L
+       * lists of every query: megabytes of text at large shapes) is written out */
+      if(!c.sample_prior) CHECK(mcq_ctx_synchronize(c.ctx));
+      clock_gettime(CLOCK_MONOTONIC, &ts1);
       mcq_write_state_json(json_file, chain_i, c.llk, c.mu, S, c.omega, c.R, c.hw, H, Qall, closest_n, closest_all);
       break;
     }
@@ -876,8 +881,12 @@ int main(int argc, char **argv)
       snprintf(path, sizeof(path), "%s/%s_interim_final_state.json", out_dir, stamp);
       FILE *f = fopen(path, "w");
       if(f) {
+        struct timespec tj0, tj1;
+        clock_gettime(CLOCK_MONOTONIC, &tj0);
         mcq_write_state_json(f, chain_i, c.llk, c.mu, S, c.omega, c.R, c.hw, H, Qall, closest_n, closest_all);
         fclose(f);
+        clock_gettime(CLOCK_MONOTONIC, &tj1);
+        state_files_s += (tj1.tv_sec - tj0.tv_sec) + 1e-9 * (tj1.tv_nsec - tj0.tv_nsec);
       }
       hours_passed++;
     }
@@ -888,11 +897,12 @@ int main(int argc, char **argv)
          "window_coeff_accept: %i window_coeff_reject: %i\nmut_accept: %i mut_reject: %i\n",
          c.rec_acc, c.rec_rej, c.sel_acc, c.sel_rej, c.merge_acc, c.merge_rej, c.split_acc, c.split_rej,
          c.grow_acc, c.grow_rej, c.coeff_acc, c.coeff_rej, c.mut_acc, c.mut_rej);
-  clock_gettime(CLOCK_MONOTONIC, &ts1);
   {
-    double sec = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
+    /* steps per second of the chain itself: hourly interim state files are not counted, the final one is
+     * written after the clock has stopped */
+    double sec = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec) - state_files_s;
     int done = chain_i < chain_length ? chain_i + 1 : chain_i;
-    printf("MCMC loop: %d steps in %.6f s = %.3f steps/s\n", done, sec, done / sec);
+    printf("MCMC loop: %d steps in %.6f s = %.3f steps/s\n", done, sec, sec > 0 ? done / sec : 0.0);
   }
   if(opt_profile) {
     static const char *names[9] = {"recombination", "selection", "esc merge/split", "rev merge/split", "esc grow",
