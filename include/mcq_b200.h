@@ -220,6 +220,12 @@ enum {
                               costs the length of one warp's dependent chain per site, and there the look-ups of
                               the next site travel under the butterfly of the current one.  Same bits either way.
                               Default: see mcq_ctx.cu (measured cross-over); 0 = never. */
+  MCQ_OPT_CHECKPOINT_STRIDE = 9, /* default 1: F, tmp_F and B are kept whole, as the reference keeps them.  k = 2, 4, 8,
+                              ...: only every k-th column of each is kept; a column in between is recomputed from the
+                              nearest one (at most k-1 sites of the recursion, 1 byte per cell) when a proposal needs
+                              it.  A sweep then moves 1 + 8/k bytes per cell instead of 9 and the matrices take 1/k of
+                              the memory; the values are bit for bit those of k = 1.  Set it before
+                              mcq_ctx_upload_static (the matrices are allocated there). */
   MCQ_OPT_UPLOAD_CHUNK_QUERIES = 5 /* default 1250: mcq_ctx_upload_static transfers and sets up the per-query
                               data in up to 8 chunks of at least this many queries (one chunk = no
                               pipelining; smaller chunks starve the kernels that follow them). */
@@ -227,7 +233,9 @@ enum {
 int mcq_ctx_set_option(mcq_ctx *ctx, int option, int value);
 
 /* ---- inspection (tests, drop-in glue); outputs in the reference's layouts -------------- */
-enum { MCQ_BUF_F = 0, MCQ_BUF_B = 1, MCQ_BUF_TMP_F = 2 };
+/* F, B, tmp_F: the whole matrix of a query, as the reference holds it (with MCQ_OPT_CHECKPOINT_STRIDE > 1 computed
+ * afresh for the call).  F_KEPT / B_KEPT: only the columns the context really keeps, the others 0 (counters -1). */
+enum { MCQ_BUF_F = 0, MCQ_BUF_B = 1, MCQ_BUF_TMP_F = 2, MCQ_BUF_F_KEPT = 3, MCQ_BUF_B_KEPT = 4 };
 int mcq_ctx_get_matrix(mcq_ctx *ctx, int which, int q, double *out /*[L][S]*/, int *rnorm /*[S]*/);
 enum { MCQ_TAB_C2C = 0, MCQ_TAB_A = 1, MCQ_TAB_TMP_C2C = 2, MCQ_TAB_TMP_A = 3 };
 /* rows never written by the reference (codons absent from the site) come back as 0 */

@@ -19,7 +19,7 @@ from ._lib import McqDims, McqParams, McqProposal, check
 
 PROP_REC, PROP_SEL, PROP_ESC, PROP_REV, PROP_MU = 0, 1, 2, 3, 4
 DO_HLA_ESC, DO_HLA_REV, DO_HLA_BOTH, DO_ALL_HLAS = 0, 1, 2, -1   # mcmc_moves.h:6-9
-BUF_F, BUF_B, BUF_TMP_F = 0, 1, 2
+BUF_F, BUF_B, BUF_TMP_F, BUF_F_KEPT, BUF_B_KEPT = 0, 1, 2, 3, 4
 TAB_C2C, TAB_A, TAB_TMP_C2C, TAB_TMP_A = 0, 1, 2, 3
 OPT_SPARSE_ESC = 1
 OPT_LAZY_REFILL = 2
@@ -29,6 +29,7 @@ OPT_UPLOAD_CHUNK_QUERIES = 5
 OPT_EXCHANGE = 6
 OPT_WARPS_PER_QUERY = 7
 OPT_PIPELINE_MAX_QUERIES = 8
+OPT_CHECKPOINT_STRIDE = 9
 K_GATHER, K_EMISSION, K_FORWARD, K_BACKWARD, K_COMMIT, K_SUM = range(6)
 
 

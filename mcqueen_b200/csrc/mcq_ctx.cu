@@ -178,6 +178,11 @@ struct mcq_ctx {
   int opt_exchange = 0;             // MCQ_OPT_EXCHANGE
   int pipe_max = 0;                 // launches that run at most this many queries use the pipelined sweep kernels
   std::vector<int> carriers;        // queries carrying each HLA type (host count)
+  int ck = 1, nc = 0;               // MCQ_OPT_CHECKPOINT_STRIDE: every ck-th column of F / T / B is kept; nc columns per query
+  double *Tcol = nullptr, *Bcol = nullptr;   // ck > 1: the proposal's last column / the backward column at it, per query
+  int *Tncol = nullptr, *Bncol = nullptr;
+  const double *pend_tab = nullptr, *pend_ec = nullptr;   // the rows the pending proposal was evaluated with
+  int pend_rsite = -1; double pend_rvalue = 0.0;
   int wpq = 0;                      // MCQ_OPT_WARPS_PER_QUERY: 0 = the one-warp sweeps, else consumer warps per query
   void *peer_map[16] = {nullptr};   // IPC mappings of the peers' mailboxes
   bool have_peers = false;
@@ -343,7 +348,7 @@ extern "C" void mcq_ctx_destroy(mcq_ctx *c) {
   void *ptrs[] = {c->desc, c->rowdesc, c->nsite, c->G, c->ncodon, c->cons_in_list, c->cons_codon, c->query_codon, c->hla, c->aoff, c->toff,
                   c->pblock,
                   c->F, c->B, c->T, c->Fn, c->Bn, c->Tn, c->tab, c->atab, c->ec, c->ac, c->tab_t, c->atab_t, c->ec_t, c->ac_t,
-                  c->llk_cur, c->llk_prop, c->d_sum, c->d_xchg, c->fv, c->bv, c->sel, c->st_trip, c->st_trip_pad, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
+                  c->llk_cur, c->llk_prop, c->d_sum, c->d_xchg, c->fv, c->bv, c->sel, c->Tcol, c->Bcol, c->Tncol, c->Bncol, c->st_trip, c->st_trip_pad, c->st_cons, c->st_closest, c->st_slot_of, c->st_trip_tab};
   for (void *p : ptrs)
     if (p && !(p == (void *)c->st_trip && c->trip_in_mailbox)) cudaFree(p);
   if (c->h_sum) cudaFreeHost(c->h_sum);
@@ -451,8 +456,16 @@ extern "C" int mcq_ctx_set_option(mcq_ctx *c, int option, int value) {
   if (option == MCQ_OPT_ASYNC_UPLOAD) { c->opt_async_upload = value; return 0; }
   if (option == MCQ_OPT_EXCHANGE) { c->opt_exchange = value; return 0; }
   if (option == MCQ_OPT_PIPELINE_MAX_QUERIES) { c->pipe_max = value; return 0; }
+  if (option == MCQ_OPT_CHECKPOINT_STRIDE) {
+    REQUIRE(value >= 1 && value <= 64 && (value & (value - 1)) == 0, "the checkpoint stride is a power of two, at most 64");
+    REQUIRE(!c->have_static, "set MCQ_OPT_CHECKPOINT_STRIDE before mcq_ctx_upload_static (the matrices are allocated there)");
+    REQUIRE(value == 1 || c->wpq == 0, "checkpointed matrices go with the one-warp sweeps");
+    c->ck = value;
+    return 0;
+  }
   if (option == MCQ_OPT_WARPS_PER_QUERY) {
     REQUIRE(value == 0 || mcq_mw_supported(c->Lg / 64, value), "this number of warps per query is not built for this closest_n");
+    REQUIRE(value == 0 || c->ck == 1, "checkpointed matrices go with the one-warp sweeps");
     // the grouping of the per-site column sum changes with it: F, B and the cached per-query values of one state
     // must all come from one grouping
     REQUIRE(!c->have_state || value == c->wpq, "set MCQ_OPT_WARPS_PER_QUERY before mcq_ctx_init_state");
@@ -538,18 +551,24 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     ALLOC(c->st_closest, (size_t)Q * L);
     ALLOC(c->st_slot_of, (size_t)S * 64);
     ALLOC(c->st_trip_tab, (size_t)(S + 31) / 32 * 32 * 128);
-    const size_t cells = (size_t)Q * S * c->Ls;
+    // the forward / proposal / backward matrices: every ck-th column (all of them with ck = 1)
+    c->nc = (S + c->ck - 1) / c->ck;
+    const size_t ncol = (size_t)Q * c->nc, cells = ncol * c->Ls;
     ALLOC(c->F, cells); ALLOC(c->B, cells); ALLOC(c->T, cells);
-    ALLOC(c->Fn, (size_t)Q * S); ALLOC(c->Bn, (size_t)Q * S); ALLOC(c->Tn, (size_t)Q * S);
-    ALLOC(c->sel, (size_t)Q * S);
-    CK(cudaMemsetAsync(c->sel, 0, (size_t)Q * S, c->stream));
+    ALLOC(c->Fn, ncol); ALLOC(c->Bn, ncol); ALLOC(c->Tn, ncol);
+    ALLOC(c->sel, ncol);
+    CK(cudaMemsetAsync(c->sel, 0, ncol, c->stream));
+    if (c->ck > 1) {
+      ALLOC(c->Tcol, (size_t)Q * c->Ls); ALLOC(c->Bcol, (size_t)Q * c->Ls);
+      ALLOC(c->Tncol, (size_t)Q); ALLOC(c->Bncol, (size_t)Q);
+    }
     ALLOC(c->tab, c->TL); ALLOC(c->tab_t, c->TL); ALLOC(c->atab, (size_t)c->NA); ALLOC(c->atab_t, (size_t)c->NA);
     const size_t qs = (size_t)Q * S;
     ALLOC(c->ec, qs); ALLOC(c->ac, qs); ALLOC(c->ec_t, qs); ALLOC(c->ac_t, qs);
     double *zero[] = {c->tab, c->tab_t, c->atab, c->atab_t, c->ec, c->ac, c->ec_t, c->ac_t};
     const size_t zn[] = {c->TL, c->TL, (size_t)c->NA, (size_t)c->NA, qs, qs, qs, qs};
     for (int i = 0; i < 8; i++) CK(cudaMemsetAsync(zero[i], 0, (zn[i] ? zn[i] : 1) * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->Fn, 0, (size_t)Q * S * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->Fn, 0, ncol * sizeof(int), c->stream));
     std::vector<int> site_of((size_t)c->NA);
     for (int s = 0; s < S; s++)
       for (int k = aoff_h[s]; k < aoff_h[s + 1]; k++) site_of[k] = s;
@@ -797,6 +816,15 @@ static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int star
   a.logBIG = c->logBIG;
   a.pipe = (sparse ? c->carriers[hla] : c->d.num_query) <= c->pipe_max;
   KScope ks(c, MCQ_K_FORWARD);
+  if (c->ck > 1 && mode != FWD_NO_STORE) {
+    // checkpointed matrices: the proposal's last column is handed to k_dot (llk_mode 1 becomes Tcol + 0)
+    a.ck = c->ck; a.nc = c->nc;
+    a.fv = (lazy || mode == FWD_PROPOSAL) && c->opt_lazy ? c->fv : a.fv;
+    if (llk_mode == 1) { a.Tcol = c->Tcol; a.Tncol = c->Tncol; a.llk_mode = 0; }
+    if (tuned_blocks != nullptr) *tuned_blocks = 0;
+    CK(mcq_launch_forward_ck(a, c->stream));
+    return 0;
+  }
   if (c->wpq == 0 && mode == FWD_PROPOSAL && start == end && start > 0 && !lazy && !sparse && llk_mode == 1 &&
       tuned_blocks == nullptr) {
     CK(mcq_launch_column(a, c->stream));       // a one-column proposal, nothing owed: the direct kernel
@@ -813,7 +841,7 @@ static int run_forward(mcq_ctx *c, const double *tab, const double *ec, int star
 // lazy: every query continues from its own bv mark down to column `bottom`; otherwise the reference's
 // update_B(update) down to column 0
 static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream_t stream = nullptr,
-                        bool lazy = false, int bottom = 0, int *tuned_blocks = nullptr) {
+                        bool lazy = false, int bottom = 0, int *tuned_blocks = nullptr, bool deliver = false) {
   if (stream == nullptr) stream = c->stream;
   BwdArgs a{};
   a.st = make_static(c);
@@ -821,6 +849,15 @@ static int run_backward(mcq_ctx *c, int update, bool sparse, int hla, cudaStream
   a.bottom = bottom; a.bv = lazy ? c->bv : nullptr;
   a.active = sparse ? c->hla : nullptr; a.active_hla = hla;
   a.pipe = (sparse ? c->carriers[hla] : c->d.num_query) <= c->pipe_max;
+  if (c->ck > 1) {
+    a.ck = c->ck; a.nc = c->nc;
+    if (deliver) { a.Bcol = c->Bcol; a.Bncol = c->Bncol; }
+    if (tuned_blocks != nullptr) *tuned_blocks = 0;
+    if (stream != c->stream) { c->launches++; c->k_n[MCQ_K_BACKWARD]++; CK(mcq_launch_backward_ck(a, stream)); return 0; }
+    KScope ks(c, MCQ_K_BACKWARD);
+    CK(mcq_launch_backward_ck(a, c->stream));
+    return 0;
+  }
   if (stream != c->stream) {          // beside the main stream: counted, not bracketed
     c->launches++;
     c->k_n[MCQ_K_BACKWARD]++;
@@ -952,7 +989,8 @@ static int set_marks(mcq_ctx *c, int f, int b, bool sparse, int hla) {
 static int flush_lazy(mcq_ctx *c) {
   const int S = c->d.num_sites;
   bool owe_f = false, owe_b = false;
-  for_active(c, false, 0, [&](int q) { owe_f |= c->fv_h[q] < S - 1; owe_b |= c->bv_h[q] > 0; });
+  const int last_cp = (S / c->ck) * c->ck - 1;       // the last forward checkpoint (S - 1 with ck = 1)
+  for_active(c, false, 0, [&](int q) { owe_f |= ((c->fv_h[q] + 1) / c->ck) * c->ck - 1 < last_cp; owe_b |= c->bv_h[q] > 0; });
   if (owe_f) {
     if (run_forward(c, c->tab, c->ec, S, S - 1, FWD_IN_PLACE, 0, nullptr, -1, 0.0, false, 0, true)) return 1;
     for (int &v : c->fv_h) v = S - 1;
@@ -1026,14 +1064,17 @@ static int full_llk_pipelined(mcq_ctx *c, int with_emission, double *llk) {
     a.st = v;
     a.em.tab = c->tab; a.em.ec = c->ec + q0 * S; a.em_pre = a.em; a.R = c->m.R; a.r_site = -1; a.r_value = 0.0;
     a.fv = nullptr; a.mark_fv = c->fv + q0;
-    a.Fin = c->F + q0 * S * Ls; a.Fout = c->T + q0 * S * Ls; a.sel = c->sel + q0 * S;
-    a.Fn_in = c->Fn + q0 * S; a.Fn_out = c->Fn + q0 * S;
+    const size_t nc = (size_t)c->nc;
+    a.Fin = c->F + q0 * nc * Ls; a.Fout = c->T + q0 * nc * Ls; a.sel = c->sel + q0 * nc;
+    a.Fn_in = c->Fn + q0 * nc; a.Fn_out = c->Fn + q0 * nc;
+    a.ck = c->ck; a.nc = c->nc;
     a.in_place = 1; a.no_store = 0; a.start = 0; a.end = S - 1; a.llk_mode = 2;
-    a.B = c->B + q0 * S * Ls; a.Bn = c->Bn + q0 * S; a.llk_out = c->llk_cur + q0; a.llk_keep = c->llk_cur + q0;
+    a.B = c->B + q0 * nc * Ls; a.Bn = c->Bn + q0 * nc; a.llk_out = c->llk_cur + q0; a.llk_keep = c->llk_cur + q0;
     a.active = nullptr; a.active_hla = 0; a.logBIG = c->logBIG;
     a.pipe = 0;
     c->launches++; c->k_n[MCQ_K_FORWARD]++;
-    if (c->wpq > 0) CK(mcq_launch_forward_mw(a, c->wpq, st));
+    if (c->ck > 1) CK(mcq_launch_forward_ck(a, st));
+    else if (c->wpq > 0) CK(mcq_launch_forward_mw(a, c->wpq, st));
     else CK(mcq_launch_forward(a, st));
   }
   for (int &m : c->fv_h) m = S - 1;
@@ -1135,6 +1176,40 @@ extern "C" int mcq_ctx_init_state(mcq_ctx *c, double *llk) {
 // kernel itself, B by a backward launch beside it on the second stream, joined by k_dot.
 static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const McqOverride &ov, int r_site,
                       double r_value, bool sparse) {
+  c->pend_tab = tab; c->pend_ec = ec; c->pend_rsite = r_site; c->pend_rvalue = r_value;
+  if (c->ck > 1) {
+    // Checkpointed matrices: neither F[start-1] nor B[end] need exist.  The forward kernel starts from the last
+    // current checkpoint before the range (completing owed ones on the way) and hands out the proposal's last
+    // column; the backward kernel, beside it on the second stream, does the same from above for B[end]; k_dot
+    // joins the two columns.
+    const int cp_start = (ov.start / c->ck) * c->ck - 1;
+    if (c->opt_lazy)
+      for_active(c, sparse, ov.hla, [&](int q) {
+        if (((c->fv_h[q] + 1) / c->ck) * c->ck - 1 < cp_start) c->fv_h[q] = cp_start;
+        if (c->bv_h[q] > ov.end) c->bv_h[q] = ov.end;
+      });
+    const bool dual = c->timing != 2;
+    if (dual) {
+      CK(cudaEventRecord(c->ev_fork, c->stream));
+      CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    }
+    if (run_backward(c, -1, sparse, ov.hla, dual ? c->stream2 : nullptr, c->opt_lazy != 0, ov.end, nullptr, true)) return 1;
+    if (dual) CK(cudaEventRecord(c->ev_join, c->stream2));
+    if (run_forward(c, tab, ec, ov.start, ov.end, FWD_PROPOSAL, 1, nullptr, r_site, r_value, sparse, ov.hla, false))
+      return 1;
+    if (dual) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    DotArgs d{};
+    d.st = make_static(c);
+    d.cols = 1;
+    d.T = c->Tcol; d.Tn = c->Tncol; d.B = c->Bcol; d.Bn = c->Bncol; d.site = ov.end;
+    d.llk_out = c->llk_prop; d.llk_keep = c->llk_cur;
+    d.active = sparse ? c->hla : nullptr; d.active_hla = ov.hla;
+    d.logBIG = c->logBIG;
+    d.wpq = 0;
+    KScope ks(c, MCQ_K_SUM);
+    CK(mcq_launch_dot(d, c->stream));
+    return 0;
+  }
   bool need_f = false, need_b = false;
   if (c->opt_lazy)
     for_active(c, sparse, ov.hla, [&](int q) { need_f |= c->fv_h[q] < ov.start - 1; need_b |= c->bv_h[q] > ov.end; });
@@ -1157,7 +1232,7 @@ static int eval_range(mcq_ctx *c, const double *tab, const double *ec, const Mcq
   if (run_forward(c, tab, ec, ov.start, ov.end, FWD_PROPOSAL, 0, nullptr, r_site, r_value, sparse, ov.hla, need_f))
     return 1;
   if (dual) CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-  DotArgs d;
+  DotArgs d{};
   d.st = make_static(c);
   d.T = c->T; d.Tn = c->Tn; d.F = c->F; d.sel = c->sel; d.B = c->B; d.Bn = c->Bn; d.site = ov.end;
   d.llk_out = c->llk_prop; d.llk_keep = c->llk_cur;
@@ -1260,6 +1335,8 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
       }
       k.copy_cons = (ov.kind == MCQ_PROP_SEL || ov.kind == MCQ_PROP_ESC) ? 1 : 0;   // per-query consensus values
       k.sel = c->sel; k.Tn = c->Tn; k.Fn = c->Fn;
+      // the checkpoint columns inside the range (every site with ck = 1)
+      k.nc = c->nc; k.c0 = ov.start / c->ck; k.c1 = (ov.end + 1) / c->ck - 1;
       k.active = sparse ? c->hla : nullptr; k.active_hla = ov.hla;
       // with lazy refills the refills of mcmc_moves.c:266-279 are owed, not run: the next evaluation completes
       // what it needs (marks on the device here, mirrored on the host below)
@@ -1293,10 +1370,93 @@ extern "C" int mcq_ctx_accept(mcq_ctx *c) {
 // ------------------------------------------------------------------------------------------
 // inspection
 // ------------------------------------------------------------------------------------------
+// Checkpointed matrices hold every ck-th column only: for inspection the whole matrix of one query is computed
+// afresh, into scratch of the reference's size, by the sweeps of the un-checkpointed layout on a one-query view -
+// the same cell updates, so the same bits the kept columns have.
+static int recompute_matrix(mcq_ctx *c, int which, int q, double *out, int *rnorm) {
+  const int S = c->d.num_sites, L = c->d.closest_n, Ls = c->Ls, H = c->d.num_hla_types;
+  struct Scratch {
+    void *p = nullptr;
+    ~Scratch() { if (p) cudaFree(p); }
+  } f0, f1, n0, n1, z;
+  const size_t cells = (size_t)S * Ls;
+  CK(cudaMalloc(&f0.p, cells * sizeof(double))); CK(cudaMalloc(&f1.p, cells * sizeof(double)));
+  CK(cudaMalloc(&n0.p, (size_t)S * sizeof(int))); CK(cudaMalloc(&n1.p, (size_t)S * sizeof(int)));
+  CK(cudaMalloc(&z.p, (size_t)S));
+  CK(cudaMemsetAsync(z.p, 0, (size_t)S, c->stream));
+  CK(cudaMemsetAsync(f1.p, 0, cells * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(n1.p, 0, (size_t)S * sizeof(int), c->stream));
+  McqStatic v = make_static(c);
+  v.Q = 1;
+  v.G += (size_t)q * S * c->Lg; v.rowdesc += (size_t)q * S; v.query_codon += (size_t)q * S; v.hla += (size_t)q * H;
+  const double *src = (const double *)f0.p;
+  const int *nsrc = (const int *)n0.p;
+  if (which == MCQ_BUF_B) {
+    BwdArgs b{};
+    b.st = v; b.em.tab = c->tab; b.em.ec = c->ec + (size_t)q * S; b.R = c->m.R;
+    b.B = (double *)f0.p; b.Bn = (int *)n0.p; b.update = S - 1; b.bottom = 0;
+    CK(mcq_launch_backward(b, c->stream));
+  } else {
+    FwdArgs a{};
+    a.st = v; a.em.tab = c->tab; a.em.ec = c->ec + (size_t)q * S; a.em_pre = a.em; a.R = c->m.R; a.r_site = -1;
+    a.Fin = (double *)f0.p; a.Fn_in = (int *)n0.p; a.Fout = (double *)f1.p; a.Fn_out = (int *)n0.p;
+    a.sel = (const uint8_t *)z.p; a.in_place = 1; a.start = 0; a.end = S - 1; a.logBIG = c->logBIG;
+    CK(mcq_launch_forward(a, c->stream));
+    if (which == MCQ_BUF_TMP_F && c->has_pending && c->pending.kind != MCQ_PROP_MU) {
+      a.em.tab = c->pend_tab; a.em.ec = c->pend_ec + (size_t)q * S;
+      a.r_site = c->pend_rsite; a.r_value = c->pend_rvalue;
+      a.in_place = 0; a.Fn_out = (int *)n1.p; a.start = c->pending.start; a.end = c->pending.end;
+      CK(mcq_launch_forward(a, c->stream));
+    }
+    if (which == MCQ_BUF_TMP_F) { src = (const double *)f1.p; nsrc = (const int *)n1.p; }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  if (out) {
+    std::vector<double> slab(cells);
+    CK(cudaMemcpy(slab.data(), src, cells * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < L; r++)
+      for (int s2 = 0; s2 < S; s2++) out[(size_t)r * S + s2] = slab[(size_t)s2 * Ls + r];
+  }
+  if (rnorm) CK(cudaMemcpy(rnorm, nsrc, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int mcq_ctx_get_matrix(mcq_ctx *c, int which, int q, double *out, int *rnorm) {
   REQUIRE(c && c->have_static, "context not ready");
   REQUIRE(q >= 0 && q < c->d.num_query, "query index");
   CK(cudaSetDevice(c->d.device));
+  if (which == MCQ_BUF_F_KEPT || which == MCQ_BUF_B_KEPT) {
+    // the columns that are actually kept (all of them with a checkpoint stride of 1), owed refills completed:
+    // the other columns come back as 0 and their counters as -1
+    const int S = c->d.num_sites, L = c->d.closest_n, Ls = c->Ls, ck = c->ck, nc = c->nc;
+    const bool fwd = which == MCQ_BUF_F_KEPT;
+    if (c->have_state && c->have_params && flush_lazy(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<double> k0((size_t)nc * Ls), k1;
+    std::vector<uint8_t> sel(nc, 0);
+    std::vector<int> cnt(nc);
+    CK(cudaMemcpy(k0.data(), (fwd ? c->F : c->B) + (size_t)q * nc * Ls, k0.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnt.data(), (fwd ? c->Fn : c->Bn) + (size_t)q * nc, nc * sizeof(int), cudaMemcpyDeviceToHost));
+    if (fwd) {
+      k1.resize(k0.size());
+      CK(cudaMemcpy(k1.data(), c->T + (size_t)q * nc * Ls, k1.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(sel.data(), c->sel + (size_t)q * nc, nc, cudaMemcpyDeviceToHost));
+    }
+    if (out) memset(out, 0, sizeof(double) * (size_t)L * S);
+    for (int s2 = 0; s2 < S; s2++) {
+      const bool kept = fwd ? (s2 % ck == ck - 1) : (s2 % ck == 0);
+      if (rnorm) rnorm[s2] = kept ? cnt[s2 / ck] : -1;
+      if (!kept || !out) continue;
+      const std::vector<double> &k = sel[s2 / ck] ? k1 : k0;
+      for (int r = 0; r < L; r++) out[(size_t)r * S + s2] = k[(size_t)(s2 / ck) * Ls + r];
+    }
+    return 0;
+  }
+  if (c->ck > 1) {
+    REQUIRE(c->have_params, "mcq_ctx_set_params has not been called");
+    CK(cudaStreamSynchronize(c->stream));
+    return recompute_matrix(c, which, q, out, rnorm);
+  }
   const int S = c->d.num_sites, L = c->d.closest_n, Ls = c->Ls;
   const int *nsrc = which == MCQ_BUF_F ? c->Fn : which == MCQ_BUF_B ? c->Bn : c->Tn;
   if (c->have_state && c->have_params && which != MCQ_BUF_TMP_F && flush_lazy(c)) return 1;

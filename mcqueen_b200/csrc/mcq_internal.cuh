@@ -100,6 +100,11 @@ struct FwdArgs {
   int active_hla;            // column of `active` to test
   double logBIG;
   int pipe;                  // 1: few queries in flight - launch the variant with the shorter per-site chain (same bits)
+  // checkpointed matrices (ck > 1, see k_forward_ck): only the columns of sites s with s % ck == ck-1 exist, as
+  // column s / ck of nc per query (Fin, Fout, sel, Fn_in, Fn_out are indexed that way); Tcol / Tncol ([Q][Ls],
+  // [Q]) receive the column of site `end` and its counter when not null
+  int ck, nc;
+  double *Tcol; int *Tncol;
 };
 
 struct BwdArgs {
@@ -112,6 +117,10 @@ struct BwdArgs {
   int *bv;                   // [Q] first valid column of B per query (S = none); nullptr = use `update`
   const uint8_t *active; int active_hla;
   int pipe;                  // as FwdArgs::pipe
+  // checkpointed matrices (ck > 1, see k_backward_ck): only the columns of sites s with s % ck == 0 exist, as
+  // column s / ck of nc per query; Bcol / Bncol ([Q][Ls], [Q]) receive the column of site `bottom` when not null
+  int ck, nc;
+  double *Bcol; int *Bncol;
 };
 
 struct DotArgs {             // per-query log-likelihood from a proposal column and the backward column
@@ -126,6 +135,7 @@ struct DotArgs {             // per-query log-likelihood from a proposal column 
   const uint8_t *active; int active_hla;
   double logBIG;
   int wpq;                          // consumer warps per query of the sweeps (0: one warp): fixes the summation order
+  int cols;                         // 1: T / B are per-query columns [Q][Ls] with counters Tn / Bn [Q] (checkpointed matrices)
 };
 
 struct EmisArgs {
@@ -153,6 +163,9 @@ cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int8_t *trip, const 
 cudaError_t mcq_launch_rowdesc(const McqStatic &st, uint32_t *out, int q0, int nq, cudaStream_t stream);
 cudaError_t mcq_launch_forward(const FwdArgs &a, cudaStream_t stream);
 cudaError_t mcq_launch_backward(const BwdArgs &a, cudaStream_t stream);
+// the sweeps over checkpointed matrices (FwdArgs::ck / BwdArgs::ck > 1)
+cudaError_t mcq_launch_forward_ck(const FwdArgs &a, cudaStream_t stream);
+cudaError_t mcq_launch_backward_ck(const BwdArgs &a, cudaStream_t stream);
 // a one-column proposal with nothing owed (start == end > 0, all queries): same values as mcq_launch_forward's
 cudaError_t mcq_launch_column(const FwdArgs &a, cudaStream_t stream);
 // time the launch at every residency (blocks per SM) the kernel allows and keep the fastest for launches of
@@ -184,7 +197,8 @@ struct CommitArgs {
   double *tab, *atab, *ec, *ac;
   size_t t0, t1, a0, a1;          // ranges of the shared table / A values to copy (empty when t0 == t1)
   int copy_cons;                  // 1: per-query consensus values of start..end
-  uint8_t *sel; const int *Tn; int *Fn;
+  uint8_t *sel; const int *Tn; int *Fn;  // indexed [Q][nc]: checkpoint columns c0..c1 of every query flip
+  int nc, c0, c1;
   const uint8_t *active; int active_hla;
   int *fv, *bv; int mark;         // mark >= 0: fv = bv = mark for the active queries
 };

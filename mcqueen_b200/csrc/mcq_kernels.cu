@@ -1280,6 +1280,359 @@ cudaError_t mcq_tune_backward(const BwdArgs &a, cudaStream_t stream, int *best_b
 }
 
 // ------------------------------------------------------------------------------------------
+// K4k / K5k: the sweeps over CHECKPOINTED matrices.  Only every ck-th column of F (sites s with s % ck == ck-1)
+// and of B (sites with s % ck == 0) is kept in HBM; a column in between is recomputed from the nearest
+// checkpoint - at most ck-1 sites of the 1 B/cell recursion - by whoever needs it.  A sweep then moves
+// 1 + 8/ck bytes per cell instead of 9, and the matrices take 1/ck of the memory.  Same cell updates in the same
+// order as k_forward / k_backward (the site halves fwd_front / fwd_cells, bwd_front / bwd_cells are theirs), so
+// every column, wherever it is computed, has the bits it has there.
+//   forward : starts at the last current checkpoint at or before start-1 (validity mark fv: checkpoints of sites
+//             <= fv are current), runs the sites up to start-1 with the current rows (completing owed
+//             checkpoints on the way), then start..end with the rows of the launch; checkpoints of start..end go
+//             where the selector says (in place, or into the other buffer for a proposal); the column of site
+//             `end` is handed out in Tcol.
+//   backward: starts at the first current checkpoint at or above `bottom` (bv: checkpoints of sites >= bv are
+//             current; or from the seed column), runs down to `bottom`, completing owed checkpoints, and hands
+//             out the column of `bottom` in Bcol.
+// ------------------------------------------------------------------------------------------
+template <int NJ, bool FULL>
+__global__ void __launch_bounds__(32) k_forward_ck(const FwdArgs a) {
+  __shared__ __align__(16) uint8_t s_g[MCQ_RING][64 * NJ];
+  __shared__ __align__(16) double s_e[MCQ_RING][MCQ_ES];
+  const int q = blockIdx.x, lane = threadIdx.x;
+  if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) {
+    if (lane == 0 && a.llk_out != nullptr) a.llk_out[q] = a.llk_keep[q];
+    return;
+  }
+  const int S = a.st.S, Ls = a.st.Ls, ck = a.ck, km = ck - 1, NC = a.nc;
+  const size_t qoff = (size_t)q * NC * Ls;
+  const uint8_t *__restrict__ Gl = a.st.G + (size_t)q * S * (64 * NJ) + lane * 16;
+  const uint32_t *__restrict__ rdq = a.st.rowdesc + (size_t)q * S;
+  const double *ecq = a.em.ec ? a.em.ec + (size_t)q * S : nullptr;
+  const double *ecq_pre = a.em_pre.ec ? a.em_pre.ec + (size_t)q * S : nullptr;
+  const double *tabl = a.em.tab + lane, *tabl_pre = a.em_pre.tab + lane;
+  // the last current checkpoint at or before start - 1 (-1: none, the sweep starts with the seed column)
+  const int cp_start = (a.start / ck) * ck - 1;
+  int p = cp_start, known = S - 1;
+  if (a.fv != nullptr) {
+    known = a.fv[q];
+    p = min(p, ((known + 1) / ck) * ck - 1);
+  }
+  const int s0 = p + 1;
+  double *X0 = const_cast<double *>(a.Fin) + qoff + 2 * lane;
+  const ptrdiff_t delta = a.Fout - a.Fin;
+  const uint8_t *selq = a.sel + (size_t)q * NC;
+  int *Fno = a.Fn_out + (size_t)q * NC;
+  int *Fnc = const_cast<int *>(a.Fn_in) + (size_t)q * NC;
+  uint8_t *gring = &s_g[0][0];
+  double *ering = &s_e[0][0];
+  if (lane < MCQ_RING) ering[lane * MCQ_ES + MCQ_NOSLOT] = 0.0;
+  const unsigned g_sh = (unsigned)__cvta_generic_to_shared(gring) + lane * 16;
+  const unsigned e_sh = (unsigned)__cvta_generic_to_shared(ering) + lane * 8;
+  const uint8_t *gl = gring + lane * (2 * NJ);
+  bool inrow[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) inrow[j] = FULL || (64 * j + 2 * lane < Ls);
+
+  const int sA = (s0 == 0) ? 1 : s0;
+  FwdWarp<NJ> w;
+  {
+    const bool pre = 0 < a.start;
+    const double *eq = pre ? ecq_pre : ecq;
+    stage_k<NJ, 3>(g_sh, e_sh, s0 == 0, s0 == 0 ? rdq[0] : 0u, pre ? tabl_pre : tabl, eq, eq != nullptr, a.R, Gl, lane);
+  }
+#define MCQ_FWD_PROLOGUE(K)                                                                                  \
+  {                                                                                                          \
+    const int tt = sA + K;                                                                                   \
+    const bool pre = tt < a.start;                                                                           \
+    const double *eq = pre ? ecq_pre : ecq;                                                                  \
+    stage_k<NJ, K>(g_sh, e_sh, tt <= a.end, tt <= a.end ? rdq[tt] : 0u, pre ? tabl_pre : tabl, eq + tt,      \
+                   eq != nullptr, a.R + tt, Gl + (size_t)tt * (64 * NJ), lane);                              \
+  }
+  MCQ_FWD_PROLOGUE(0) MCQ_FWD_PROLOGUE(1) MCQ_FWD_PROLOGUE(2)
+#undef MCQ_FWD_PROLOGUE
+  w.t = sA + MCQ_PF;
+#pragma unroll
+  for (int k = 0; k < MCQ_RING; k++) {
+    const int tt = w.t + k;
+    w.rd[(k + MCQ_PF) & 3] = (tt <= a.end) ? rdq[tt] : 0u;
+  }
+  w.gsrc = Gl + (size_t)w.t * (64 * NJ);
+  w.rdp = rdq + w.t + MCQ_RING;
+  w.rdsafe = rdq + a.end;
+  w.Rp = a.R + w.t;
+  const double invN = 1.0 / (double)a.st.N;
+
+  if (s0 == 0) {
+    // column 0 is the bare emission and is never rescaled (forward_backward.c:27-39,102-111); with ck > 1 site 0
+    // is not a checkpoint
+    cp_async_wait<MCQ_PF>();
+    __syncwarp();
+    unsigned g[(2 * NJ + 3) / 4];
+    load_slots<NJ, 3>(gl, g);
+    const double *es = ering + 3 * MCQ_ES;
+    double loc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      w.p0[j] = emis_at(es, g[j >> 1], (j & 1) * 2); w.p1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+      loc += w.p0[j]; loc += w.p1[j];
+    }
+    w.cnt = 0;
+    w.tot = warp_sum(loc);
+  } else {
+    const int c = p / ck;
+    const double *__restrict__ Fi = X0 + (size_t)c * Ls + (selq[c] ? delta : 0);
+    double loc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      w.p0[j] = 0.0; w.p1[j] = 0.0;
+      if (inrow[j]) {
+        const double2 v = *reinterpret_cast<const double2 *>(Fi + 64 * j);
+        w.p0[j] = v.x; w.p1[j] = v.y;
+      }
+      loc += w.p0[j]; loc += w.p1[j];
+    }
+    w.cnt = Fnc[c];
+    w.tot = warp_sum(loc);
+  }
+
+#define MCQ_FWD_SITE(K, SITE)                                                                                       \
+  {                                                                                                                 \
+    const int s_ = (SITE);                                                                                          \
+    fwd_front<NJ, true, K>(a, w, s_, gl, ering, g_sh, e_sh, tabl, tabl_pre, ecq, ecq_pre, lane);                    \
+    w.tot = warp_sum(fwd_cells<NJ>(w, invN));                                                                       \
+    if (w.tot < MCQ_BIGI) {                       /* forward_backward.c:163-167 */                                  \
+      ++w.cnt;                                                                                                      \
+      _Pragma("unroll") for (int j = 0; j < NJ; j++) { w.p0[j] *= MCQ_BIG; w.p1[j] *= MCQ_BIG; }                    \
+      w.tot *= MCQ_BIG;                                                                                             \
+    }                                                                                                               \
+    if ((s_ & km) == km && !a.no_store) {           /* a checkpoint */                                              \
+      const int c = s_ / ck;                                                                                        \
+      const bool pre = s_ < a.start;                                                                                \
+      const bool into1 = (selq[c] != 0) != (!a.in_place && !pre);                                                   \
+      double *__restrict__ Fs = X0 + (size_t)c * Ls + (into1 ? delta : 0);                                          \
+      _Pragma("unroll") for (int j = 0; j < NJ; j++)                                                                \
+        if (FULL || inrow[j]) __stcs(reinterpret_cast<double2 *>(Fs + 64 * j), make_double2(w.p0[j], w.p1[j]));     \
+      if (lane == 0) (pre ? Fnc : Fno)[c] = w.cnt;                                                                  \
+    }                                                                                                               \
+  }
+  for (int s = sA; s <= a.end; s += 4) {
+    MCQ_FWD_SITE(0, s);
+    if (s + 1 > a.end) break;
+    MCQ_FWD_SITE(1, s + 1);
+    if (s + 2 > a.end) break;
+    MCQ_FWD_SITE(2, s + 2);
+    if (s + 3 > a.end) break;
+    MCQ_FWD_SITE(3, s + 3);
+  }
+#undef MCQ_FWD_SITE
+  cp_async_wait<0>();
+  if (lane == 0) {
+    // the checkpoints up to start - 1 are current now; a full in-place sweep makes all of them current
+    if (a.fv != nullptr && !a.no_store && known < cp_start) a.fv[q] = cp_start;
+    if (a.mark_fv != nullptr) a.mark_fv[q] = a.end;
+  }
+  if (a.Tcol != nullptr) {
+    double *__restrict__ Tc = a.Tcol + (size_t)q * Ls + 2 * lane;
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      if (FULL || inrow[j]) *reinterpret_cast<double2 *>(Tc + 64 * j) = make_double2(w.p0[j], w.p1[j]);
+    if (lane == 0) a.Tncol[q] = w.cnt;
+  }
+  if (a.llk_mode == 2 && lane == 0) a.llk_out[q] = log(w.tot) - w.cnt * a.logBIG;   // dmodel.c:899-901
+}
+
+template <int NJ, bool FULL>
+__global__ void __launch_bounds__(32) k_backward_ck(const BwdArgs a) {
+  __shared__ __align__(16) uint8_t s_g[MCQ_RING][64 * NJ];
+  __shared__ __align__(16) double s_e[MCQ_RING][MCQ_ES];
+  const int q = blockIdx.x, lane = threadIdx.x;
+  if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) return;
+  const int S = a.st.S, L = a.st.L, Ls = a.st.Ls, ck = a.ck, km = ck - 1, NC = a.nc;
+  const int bottom = a.bottom;
+  // checkpoints of sites >= vb are current
+  const int vb = a.bv != nullptr ? a.bv[q] : a.update + 1;
+  const bool deliver = a.Bcol != nullptr;
+  if (!deliver && vb <= bottom) return;
+  const size_t qoff = (size_t)q * NC * Ls;
+  const uint8_t *__restrict__ Gl = a.st.G + (size_t)q * S * (64 * NJ) + lane * 16;
+  const uint32_t *__restrict__ rdq = a.st.rowdesc + (size_t)q * S;
+  const double *ecq = a.em.ec ? a.em.ec + (size_t)q * S : nullptr;
+  const double *tabl = a.em.tab + lane;
+  double *__restrict__ Bq = a.B + qoff + 2 * lane;
+  int *__restrict__ Bnq = a.Bn + (size_t)q * NC;
+  double *__restrict__ Bc = deliver ? a.Bcol + (size_t)q * Ls + 2 * lane : nullptr;
+  uint8_t *gring = &s_g[0][0];
+  double *ering = &s_e[0][0];
+  if (lane < MCQ_RING) ering[lane * MCQ_ES + MCQ_NOSLOT] = 0.0;
+  const unsigned g_sh = (unsigned)__cvta_generic_to_shared(gring) + lane * 16;
+  const unsigned e_sh = (unsigned)__cvta_generic_to_shared(ering) + lane * 8;
+  const uint8_t *gl = gring + lane * (2 * NJ);
+  bool inrow[NJ];
+  double m0[NJ], m1[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int r = 64 * j + 2 * lane;
+    inrow[j] = FULL || (r < Ls);
+    m0[j] = (r < L) ? 1.0 : 0.0;
+    m1[j] = (r + 1 < L) ? 1.0 : 0.0;
+  }
+  BwdWarp<NJ> w;
+  // the first current checkpoint at or above `bottom`, or the seed column (forward_backward.c:197-203)
+  const int lo = max(vb, bottom);
+  const int p = ((lo + km) / ck) * ck;
+  int s;                                        // the first column to compute
+  if (p <= S - 1) {
+    const int c = p / ck;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      w.b0[j] = 0.0; w.b1[j] = 0.0;
+      if (inrow[j]) {
+        const double2 v = *reinterpret_cast<const double2 *>(Bq + (size_t)c * Ls + 64 * j);
+        w.b0[j] = v.x; w.b1[j] = v.y;
+      }
+    }
+    w.cnt = Bnq[c];
+    s = p - 1;
+  } else {
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { w.b0[j] = m0[j]; w.b1[j] = m1[j]; }
+    w.cnt = 0;
+    if (((S - 1) & km) == 0) {
+      const int c = (S - 1) / ck;
+#pragma unroll
+      for (int j = 0; j < NJ; j++)
+        if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bq + (size_t)c * Ls + 64 * j), make_double2(w.b0[j], w.b1[j]));
+      if (lane == 0) Bnq[c] = 0;
+    }
+    s = S - 2;
+  }
+  auto hand_out = [&]() {
+    if (!deliver) return;
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      if (FULL || inrow[j]) *reinterpret_cast<double2 *>(Bc + 64 * j) = make_double2(w.b0[j], w.b1[j]);
+    if (lane == 0) a.Bncol[q] = w.cnt;
+  };
+  if (s < bottom) {                             // the column asked for is the one just loaded / seeded
+    hand_out();
+    if (a.bv != nullptr && lane == 0 && bottom < vb) a.bv[q] = bottom;
+    return;
+  }
+  const int tA = s + 1;
+#define MCQ_BWD_PROLOGUE(K)                                                                                  \
+  {                                                                                                          \
+    const int tt = tA - K;                                                                                   \
+    stage_k<NJ, K>(g_sh, e_sh, tt >= bottom, tt >= bottom ? rdq[tt] : 0u, tabl, ecq + tt, ecq != nullptr,    \
+                   a.R + tt, Gl + (ptrdiff_t)tt * (64 * NJ), lane);                                          \
+  }
+  MCQ_BWD_PROLOGUE(0) MCQ_BWD_PROLOGUE(1) MCQ_BWD_PROLOGUE(2)
+#undef MCQ_BWD_PROLOGUE
+  w.t = tA - MCQ_PF;
+#pragma unroll
+  for (int k = 0; k < MCQ_RING; k++) {
+    const int tt = w.t - k;
+    w.rd[(k + MCQ_PF) & 3] = (tt >= bottom) ? rdq[tt] : 0u;
+  }
+  w.gsrc = Gl + (ptrdiff_t)w.t * (64 * NJ);
+  w.rdp = rdq + (w.t - MCQ_RING);
+  w.rdsafe = rdq + bottom;
+  w.ecp = ecq + w.t;
+  w.Rp = a.R + w.t;
+  const double invN = 1.0 / (double)a.st.N;
+  {
+    cp_async_wait<MCQ_PF - 1>();
+    __syncwarp();
+    bwd_stage<NJ, 0>(a, w, g_sh, e_sh, tabl, bottom, lane);
+    unsigned g[(2 * NJ + 3) / 4];
+    load_slots<NJ, 0>(gl, g);
+    const double *es = ering;
+    double loc = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      w.e0[j] = emis_at(es, g[j >> 1], (j & 1) * 2); w.e1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
+      loc += w.b0[j] * w.e0[j]; loc += w.b1[j] * w.e1[j];
+    }
+    w.sx = warp_sum(loc);
+    w.Rnext = es[MCQ_RSLOT];
+  }
+#define MCQ_BWD_SITE(K, COL)                                                                                        \
+  {                                                                                                                 \
+    const int s_ = (COL);                                                                                           \
+    bwd_front<NJ, K>(a, w, gl, ering, g_sh, e_sh, tabl, bottom, lane);                                              \
+    double locv, locy;                                                                                              \
+    bwd_cells<NJ>(w, m0, m1, invN, locv, locy);                                                                     \
+    _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) {                                                            \
+      locv += __shfl_xor_sync(0xffffffffu, locv, o);                                                                \
+      locy += __shfl_xor_sync(0xffffffffu, locy, o);                                                                \
+    }                                                                                                               \
+    w.sx = locy;                                                                                                    \
+    if (locv < MCQ_BIGI) {                        /* forward_backward.c:236-242 */                                  \
+      ++w.cnt;                                                                                                      \
+      _Pragma("unroll") for (int j = 0; j < NJ; j++) { w.b0[j] *= MCQ_BIG; w.b1[j] *= MCQ_BIG; }                    \
+      w.sx *= MCQ_BIG;                                                                                              \
+    }                                                                                                               \
+    if ((s_ & km) == 0) {                           /* a checkpoint */                                              \
+      const int c = s_ / ck;                                                                                        \
+      _Pragma("unroll") for (int j = 0; j < NJ; j++)                                                                \
+        if (FULL || inrow[j])                                                                                       \
+          __stcs(reinterpret_cast<double2 *>(Bq + (size_t)c * Ls + 64 * j), make_double2(w.b0[j], w.b1[j]));        \
+      if (lane == 0) Bnq[c] = w.cnt;                                                                                \
+    }                                                                                                               \
+  }
+  for (; s >= bottom; s -= 4) {
+    MCQ_BWD_SITE(1, s);
+    if (s - 1 < bottom) break;
+    MCQ_BWD_SITE(2, s - 1);
+    if (s - 2 < bottom) break;
+    MCQ_BWD_SITE(3, s - 2);
+    if (s - 3 < bottom) break;
+    MCQ_BWD_SITE(0, s - 3);
+  }
+#undef MCQ_BWD_SITE
+  cp_async_wait<0>();
+  hand_out();
+  if (a.bv != nullptr && lane == 0 && bottom < vb) a.bv[q] = bottom;
+}
+
+template <int NJ>
+static cudaError_t launch_forward_ck_nj(const FwdArgs &a, cudaStream_t stream) {
+  if (a.st.Ls == 64 * NJ) k_forward_ck<NJ, true><<<(unsigned)a.st.Q, 32, 0, stream>>>(a);
+  else k_forward_ck<NJ, false><<<(unsigned)a.st.Q, 32, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+template <int NJ>
+static cudaError_t launch_backward_ck_nj(const BwdArgs &a, cudaStream_t stream) {
+  if (a.st.Ls == 64 * NJ) k_backward_ck<NJ, true><<<(unsigned)a.st.Q, 32, 0, stream>>>(a);
+  else k_backward_ck<NJ, false><<<(unsigned)a.st.Q, 32, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t mcq_launch_forward_ck(const FwdArgs &a, cudaStream_t stream) {
+  if (a.ck < 2 || (a.ck & (a.ck - 1)) != 0 || a.sel == nullptr || a.em_pre.tab == nullptr) return cudaErrorInvalidValue;
+  switch (a.st.Lg / 64) {
+    case 1: return launch_forward_ck_nj<1>(a, stream);
+    case 2: return launch_forward_ck_nj<2>(a, stream);
+    case 4: return launch_forward_ck_nj<4>(a, stream);
+    case 8: return launch_forward_ck_nj<8>(a, stream);
+    case 16: return launch_forward_ck_nj<16>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t mcq_launch_backward_ck(const BwdArgs &a, cudaStream_t stream) {
+  if (a.ck < 2 || (a.ck & (a.ck - 1)) != 0) return cudaErrorInvalidValue;
+  switch (a.st.Lg / 64) {
+    case 1: return launch_backward_ck_nj<1>(a, stream);
+    case 2: return launch_backward_ck_nj<2>(a, stream);
+    case 4: return launch_backward_ck_nj<4>(a, stream);
+    case 8: return launch_backward_ck_nj<8>(a, stream);
+    case 16: return launch_backward_ck_nj<16>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K6: per-query log-likelihood of a proposal from its last forward column and the backward column at
 // the same site (mcmc_moves.c:220-223): one warp per query.
 // ------------------------------------------------------------------------------------------
@@ -1292,9 +1645,10 @@ __global__ void __launch_bounds__(128) k_dot(const DotArgs a) {
     return;
   }
   const int S = a.st.S, Ls = a.st.Ls;
-  const size_t col = ((size_t)q * S + a.site) * Ls;
+  const size_t col = a.cols ? (size_t)q * Ls : ((size_t)q * S + a.site) * Ls;
+  const size_t cnt_at = a.cols ? (size_t)q : (size_t)q * S + a.site;
   // the proposal's column is in the buffer that does NOT hold the current one
-  const double *Tq = (a.sel != nullptr && a.sel[(size_t)q * S + a.site] != 0) ? a.F : a.T;
+  const double *Tq = (!a.cols && a.sel != nullptr && a.sel[(size_t)q * S + a.site] != 0) ? a.F : a.T;
   const double2 *__restrict__ t = reinterpret_cast<const double2 *>(Tq + col);
   const double2 *__restrict__ b = reinterpret_cast<const double2 *>(a.B + col);
   double dot;
@@ -1323,7 +1677,7 @@ __global__ void __launch_bounds__(128) k_dot(const DotArgs a) {
     }
   }
   if (lane == 0)
-    a.llk_out[q] = log(dot) - (a.Tn[(size_t)q * S + a.site] + a.Bn[(size_t)q * S + a.site]) * a.logBIG;
+    a.llk_out[q] = log(dot) - (a.Tn[cnt_at] + a.Bn[cnt_at]) * a.logBIG;
 }
 
 cudaError_t mcq_launch_dot(const DotArgs &a, cudaStream_t stream) {
@@ -1498,14 +1852,22 @@ __global__ void __launch_bounds__(256) k_commit_all(const CommitArgs a) {
   }
   for (size_t i = a.t0 + tid; i < a.t1; i += nth) a.tab[i] = a.tab_t[i];
   for (size_t i = a.a0 + tid; i < a.a1; i += nth) a.atab[i] = a.atab_t[i];
-  const unsigned W = (unsigned)(ov.end - ov.start + 1), n = (unsigned)st.Q * W;
-  for (unsigned i = tid; i < n; i += nth) {
-    const unsigned q = i / W;
-    const size_t o = (size_t)q * st.S + ov.start + (i % W);
-    if (a.copy_cons) { a.ec[o] = a.ec_t[o]; a.ac[o] = a.ac_t[o]; }
-    if (a.active != nullptr && a.active[(size_t)q * st.H + a.active_hla] == 0) continue;
-    a.sel[o] ^= 1;
-    a.Fn[o] = a.Tn[o];
+  if (a.copy_cons) {
+    const unsigned W = (unsigned)(ov.end - ov.start + 1), n = (unsigned)st.Q * W;
+    for (unsigned i = tid; i < n; i += nth) {
+      const size_t o = (size_t)(i / W) * st.S + ov.start + (i % W);
+      a.ec[o] = a.ec_t[o]; a.ac[o] = a.ac_t[o];
+    }
+  }
+  if (a.c1 >= a.c0) {
+    const unsigned W = (unsigned)(a.c1 - a.c0 + 1), n = (unsigned)st.Q * W;
+    for (unsigned i = tid; i < n; i += nth) {
+      const unsigned q = i / W;
+      if (a.active != nullptr && a.active[(size_t)q * st.H + a.active_hla] == 0) continue;
+      const size_t o = (size_t)q * a.nc + a.c0 + (i % W);
+      a.sel[o] ^= 1;
+      a.Fn[o] = a.Tn[o];
+    }
   }
   if (a.mark >= 0)
     for (unsigned q = tid; q < (unsigned)st.Q; q += nth) {
