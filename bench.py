@@ -297,9 +297,11 @@ def mcmc_steps_per_s(workload, steps, ref_steps=12,
         dist.broadcast_object_list(box, src=0)
     tmp, tag = box
     out = {"workload": workload, "steps": steps, "n_gpus": world,
-           "variants": "gpu = driver defaults (escape-window proposals re-evaluate carriers only when the shard is "
-                       "large enough to be bound by bytes); dense_esc = every query, as the reference; eager_refill = "
-                       "dense_esc with the reference's refill after every accept"}
+           "variants": "gpu = driver defaults (every fourth column of F / B kept, refills when next read, escape-window "
+                       "proposals re-evaluate carriers only when the shard is large enough to be bound by bytes); "
+                       "dense_esc = every query, as the reference; whole_matrices = --checkpoint 1; reference_schedule = "
+                       "whole matrices, every query, refill after every accept (what the reference does, on the GPU)",
+           "timing": "the chain's own clock (MCMC loop line of the driver): the final state file is written after it stops"}
     try:
         paths = L = None
         if rank == 0:
@@ -632,6 +634,32 @@ def main():
         extras["window_accept_ms"] = ctx.last_timing()[0]
         extras["closest_L"] = p.closest_stats
         ctx.enable_timing(0)
+        # the same evaluation on checkpointed matrices (MCQ_OPT_CHECKPOINT_STRIDE = 4: every fourth column of F kept,
+        # what the MCMC driver runs on by default): reported beside the headline, which keeps whole matrices
+        ck = api.Context(p.S, p.L, p.N, p.Q, p.H, device=dev)
+        ck.set_option(api.OPT_CHECKPOINT_STRIDE, 4)
+        ck.upload_static(p.ref_triplets, p.closest_refs, p.cons_query_nucls, p.query_codons, p.hla, p.consensus_codons,
+                         p.n_site_codons, p.site_codons)
+        ck.set_params(mu=p.mu, kappa=p.kappa, phi=p.phi, prior=p.prior, R=p.R, omega=p.omega,
+                      rate_out=p.rate_out_of_codons(), esc=p.esc, rev=p.rev[0])
+        llk_ck = ck.init_state()
+        ck.enable_timing(1)
+
+        def timed_ck(fn, reps=3):
+            best = 1e30
+            for _ in range(reps):
+                fn()
+                best = min(best, ck.last_timing()[0])
+            return best
+
+        t = timed_ck(lambda: ck.full_llk(True))
+        tw = timed_ck(lambda: ck.propose(api.PROP_REV, w0, w1, value0=1.1))
+        extras["checkpoint_stride_4"] = {
+            "full_llk_ms": t, "full_llk_cells_per_s": cells / t * 1e3, "llk_equals_whole_matrices": bool(llk_ck == llk0),
+            "algorithmic_bytes_per_cell": 1.0 + 8.0 / 4 + 520.0 / L, "window_proposal_ms": tw,
+            "window_proposal_cells_per_s": p.Q * (w1 - w0 + 1) * L / tw * 1e3,
+            "device_gib": ck.device_bytes() / 2**30, "device_gib_whole_matrices": ctx.device_bytes() / 2**30}
+        ck.close()
 
     # ---- gather over ranks (max time)
     stats = np.array([ms_dev, t_wall, ms_e2e_dev, t_e2e, fwd_ms / max(fwd_n, 1),
@@ -712,13 +740,16 @@ def main():
         ctx.close()
         mc = mcmc_steps_per_s("C2", args.mcmc_steps, ref_steps=12 if world == 1 else 0, rank=rank, world=world,
                               dist=dist if world > 1 else None,
-                              variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]), ("gpu_sparse_esc", ["--sparse_esc"]))
-                              if world == 1 else (("gpu", []),))
+                              variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]), ("gpu_sparse_esc", ["--sparse_esc"]),
+                                        ("gpu_whole_matrices", ["--checkpoint", "1"]))
+                              if world == 1 else (("gpu", []), ("gpu_whole_matrices", ["--checkpoint", "1"])))
         mc4 = mcmc_steps_per_s(args.workload, 600, ref_steps=0, rank=rank, world=world, dist=dist if world > 1 else None,
                                variants=(("gpu", []), ("gpu_dense_esc", ["--dense_esc"]),
                                          ("gpu_sparse_esc", ["--sparse_esc"]),
-                                         ("gpu_eager_refill", ["--dense_esc", "--eager_refill"])) if world == 1 else
-                               (("gpu", []), ("gpu_dense_esc", ["--dense_esc"])))
+                                         ("gpu_whole_matrices", ["--checkpoint", "1"]),
+                                         ("gpu_reference_schedule", ["--checkpoint", "1", "--dense_esc", "--eager_refill"]))
+                               if world == 1 else
+                               (("gpu", []), ("gpu_dense_esc", ["--dense_esc"]), ("gpu_whole_matrices", ["--checkpoint", "1"])))
         if rank == 0:
             line["mcmc"], line["mcmc_c4"] = mc, mc4
     if rank == 0:

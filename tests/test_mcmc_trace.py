@@ -39,6 +39,7 @@ def log_rows(path):
 
 
 @pytest.mark.parametrize("extra,gaps,model", [([], False, "simple"), (["--sparse_esc"], False, "simple"),
+                                              (["--checkpoint", "1"], True, "dsim"),
                                               ([], True, "simple"), ([], False, "dsim")])
 def test_trace_matches_reference_dmodel(tmp_path, extra, gaps, model):
     if not os.path.exists(DRIVER):

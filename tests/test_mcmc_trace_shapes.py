@@ -4,7 +4,8 @@ config-5-shaped slice (3000 codons, L=200: NJ=4, self-reference mode).  The C dr
 every accept/reject decision (mcmc_moves.c:249-251, 437, 941, 1153) and every rand() draw of the UNMODIFIED
 reference dmodel; the reference's traces were recorded in the build container by
 tests/golden/make_trace_golden.py (the reference runs live instead when oracle/_ref/dmodel_ref is present and
-the fixture is not)."""
+the fixture is not).  The driver keeps every fourth column of F and B by default (--checkpoint); whole matrices and
+other strides are run as well."""
 import os
 import re
 import subprocess
@@ -53,7 +54,9 @@ def reference_chain(name, tmp_path, paths, L):
     return read_trace(t), float(re.search(INIT_RE, out).group(1)), log_rows(str(tmp_path / "ref"))
 
 
-@pytest.mark.parametrize("extra", [[], ["--sparse_esc"], ["--eager_refill"]], ids=["default", "sparse_esc", "eager"])
+@pytest.mark.parametrize("extra", [[], ["--sparse_esc"], ["--eager_refill"], ["--checkpoint", "1"], ["--checkpoint", "1", "--sparse_esc"],
+                          ["--checkpoint", "8", "--sparse_esc"], ["--checkpoint", "2", "--eager_refill"]],
+                         ids=["default", "sparse_esc", "eager", "whole", "whole_sparse", "checkpoint8_sparse", "checkpoint2_eager"])
 @pytest.mark.parametrize("name", list(SHAPES))
 def test_trace_matches_reference_at_benchmark_shapes(tmp_path, name, extra):
     if not os.path.exists(DRIVER):
