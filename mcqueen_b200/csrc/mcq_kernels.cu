@@ -516,7 +516,7 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
     ++w.cnt;
 #pragma unroll
     for (int j = 0; j < NJ; j++) { w.p0[j] *= MCQ_BIG; w.p1[j] *= MCQ_BIG; }
-    w.tot *= MCQ_BIG;
+    w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));   // of the column as stored (mcq_sweep_common.cuh)
   }
   if (STORE) {
     // the column goes into the buffer that holds the current one (a catch-up site, an in-place refill)
@@ -598,7 +598,7 @@ __device__ __forceinline__ void fwd_finish(const FwdArgs &a, FwdWarp<NJ> &w, int
     ++w.cnt;
 #pragma unroll
     for (int j = 0; j < NJ; j++) { w.p0[j] *= MCQ_BIG; w.p1[j] *= MCQ_BIG; }
-    w.tot *= MCQ_BIG;
+    w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));   // of the column as stored (mcq_sweep_common.cuh)
   }
   if (STORE) {
     const bool pre = PRE && s < a.start;
@@ -710,12 +710,10 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE && 
     // column 0 belongs to the catch-up when start > 0
     const bool into1 = ((has_sel ? selq[0] : 0) != 0) != (!a.in_place && !(PRE && 0 < a.start));
     double *F0 = into1 ? X0 + delta : X0;
-    double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       w.p0[j] = emis_at(es, g[j >> 1], (j & 1) * 2); w.p1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
       if (STORE && inrow[j]) __stcs(reinterpret_cast<double2 *>(F0 + 64 * j), make_double2(w.p0[j], w.p1[j]));
-      loc += w.p0[j]; loc += w.p1[j];
     }
     w.cnt = 0;
     if (STORE && lane == 0) {
@@ -723,10 +721,9 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE && 
       Fno[0] = 0;
       if (a.Fn_in != nullptr) Fnc[0] = 0;
     }
-    w.tot = warp_sum(loc);
+    w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));
   } else {
     const double *__restrict__ Fi = X0 + (size_t)(s0 - 1) * Ls + ((has_sel && selq[s0 - 1]) ? (a.Fout - a.Fin) : 0);
-    double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       w.p0[j] = 0.0; w.p1[j] = 0.0;
@@ -734,10 +731,9 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) __maxnreg__((NJ <= 8 && !PRE && 
         const double2 v = *reinterpret_cast<const double2 *>(Fi + 64 * j);
         w.p0[j] = v.x; w.p1[j] = v.y;
       }
-      loc += w.p0[j]; loc += w.p1[j];
     }
     w.cnt = Fnc[s0 - 1];
-    w.tot = warp_sum(loc);
+    w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));
   }
 
   if constexpr (!PIPE) {
@@ -1017,7 +1013,7 @@ __device__ __forceinline__ void bwd_site(const BwdArgs &a, BwdWarp<NJ> &w, const
     ++w.cnt;
 #pragma unroll
     for (int j = 0; j < NJ; j++) { w.b0[j] *= MCQ_BIG; w.b1[j] *= MCQ_BIG; }
-    w.sx *= MCQ_BIG;
+    w.sx = warp_sum(lane_dot<NJ>(w.b0, w.b1, w.e0, w.e1));   // of the column as stored (mcq_sweep_common.cuh)
   }
   // (the sites run K = 1, 2, 3, 0, 1, ...: the output pointers address the site of K = 1)
   constexpr int J = (K + 3) & 3;
@@ -1083,7 +1079,7 @@ __device__ __forceinline__ void bwd_finish(const BwdArgs &a, BwdWarp<NJ> &w, dou
     ++w.cnt;
 #pragma unroll
     for (int j = 0; j < NJ; j++) { w.b0[j] *= MCQ_BIG; w.b1[j] *= MCQ_BIG; }
-    w.sx *= MCQ_BIG;
+    w.sx = warp_sum(lane_dot<NJ>(w.b0, w.b1, w.e0, w.e1));   // of the column as stored (mcq_sweep_common.cuh)
   }
   constexpr int J = (K + 3) & 3;
   const size_t row = FULL ? (size_t)(64 * NJ) : (size_t)a.st.Ls;
@@ -1194,13 +1190,11 @@ __global__ void __launch_bounds__(32 * MCQ_WPB) k_backward(const BwdArgs a) {
     unsigned g[(2 * NJ + 3) / 4];
     load_slots<NJ, 0>(gl, g);
     const double *es = ering;
-    double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       w.e0[j] = emis_at(es, g[j >> 1], (j & 1) * 2); w.e1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
-      loc += w.b0[j] * w.e0[j]; loc += w.b1[j] * w.e1[j];
     }
-    w.sx = warp_sum(loc);
+    w.sx = warp_sum(lane_dot<NJ>(w.b0, w.b1, w.e0, w.e1));
     w.Rnext = es[MCQ_RSLOT];                    // R[s+1]
   }
 
@@ -1371,18 +1365,15 @@ __global__ void __launch_bounds__(32) k_forward_ck(const FwdArgs a) {
     unsigned g[(2 * NJ + 3) / 4];
     load_slots<NJ, 3>(gl, g);
     const double *es = ering + 3 * MCQ_ES;
-    double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       w.p0[j] = emis_at(es, g[j >> 1], (j & 1) * 2); w.p1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
-      loc += w.p0[j]; loc += w.p1[j];
     }
     w.cnt = 0;
-    w.tot = warp_sum(loc);
+    w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));
   } else {
     const int c = p / ck;
     const double *__restrict__ Fi = X0 + (size_t)c * Ls + (selq[c] ? delta : 0);
-    double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       w.p0[j] = 0.0; w.p1[j] = 0.0;
@@ -1390,10 +1381,9 @@ __global__ void __launch_bounds__(32) k_forward_ck(const FwdArgs a) {
         const double2 v = *reinterpret_cast<const double2 *>(Fi + 64 * j);
         w.p0[j] = v.x; w.p1[j] = v.y;
       }
-      loc += w.p0[j]; loc += w.p1[j];
     }
     w.cnt = Fnc[c];
-    w.tot = warp_sum(loc);
+    w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));
   }
 
 #define MCQ_FWD_SITE(K, SITE)                                                                                       \
@@ -1404,7 +1394,7 @@ __global__ void __launch_bounds__(32) k_forward_ck(const FwdArgs a) {
     if (w.tot < MCQ_BIGI) {                       /* forward_backward.c:163-167 */                                  \
       ++w.cnt;                                                                                                      \
       _Pragma("unroll") for (int j = 0; j < NJ; j++) { w.p0[j] *= MCQ_BIG; w.p1[j] *= MCQ_BIG; }                    \
-      w.tot *= MCQ_BIG;                                                                                             \
+      w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));                                                                   \
     }                                                                                                               \
     if ((s_ & km) == km && !a.no_store) {           /* a checkpoint */                                              \
       const int c = s_ / ck;                                                                                        \
@@ -1547,13 +1537,11 @@ __global__ void __launch_bounds__(32) k_backward_ck(const BwdArgs a) {
     unsigned g[(2 * NJ + 3) / 4];
     load_slots<NJ, 0>(gl, g);
     const double *es = ering;
-    double loc = 0.0;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       w.e0[j] = emis_at(es, g[j >> 1], (j & 1) * 2); w.e1[j] = emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
-      loc += w.b0[j] * w.e0[j]; loc += w.b1[j] * w.e1[j];
     }
-    w.sx = warp_sum(loc);
+    w.sx = warp_sum(lane_dot<NJ>(w.b0, w.b1, w.e0, w.e1));
     w.Rnext = es[MCQ_RSLOT];
   }
 #define MCQ_BWD_SITE(K, COL)                                                                                        \
@@ -1570,7 +1558,7 @@ __global__ void __launch_bounds__(32) k_backward_ck(const BwdArgs a) {
     if (locv < MCQ_BIGI) {                        /* forward_backward.c:236-242 */                                  \
       ++w.cnt;                                                                                                      \
       _Pragma("unroll") for (int j = 0; j < NJ; j++) { w.b0[j] *= MCQ_BIG; w.b1[j] *= MCQ_BIG; }                    \
-      w.sx *= MCQ_BIG;                                                                                              \
+      w.sx = warp_sum(lane_dot<NJ>(w.b0, w.b1, w.e0, w.e1));                                                        \
     }                                                                                                               \
     if ((s_ & km) == 0) {                           /* a checkpoint */                                              \
       const int c = s_ / ck;                                                                                        \
@@ -1735,10 +1723,7 @@ __global__ void __launch_bounds__(128) k_column(const FwdArgs a) {
     }
   }
   __syncwarp();
-  double loc = 0.0;
-#pragma unroll
-  for (int j = 0; j < NJ; j++) { loc += p0[j]; loc += p1[j]; }
-  double tot = warp_sum(loc);
+  double tot = warp_sum(lane_sum<NJ>(p0, p1));
   const double jump = tot * (Rs * (1.0 / (double)a.st.N));
   const double stay = 1 - Rs;
   double la = 0.0, lb = 0.0;

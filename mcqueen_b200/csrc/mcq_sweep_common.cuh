@@ -13,6 +13,31 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------
+// The sum a sweep carries from one column to the next (the `ref_sum` of forward_backward.c:135-138, :218-227) is
+// DEFINED on the column as it is stored - the reference re-forms it from F[.][s-1] / B[.][s+1] at every site - and
+// formed in ONE order: each lane adds its even-state and its odd-state cells in two chains (fused multiply-adds for
+// the backward products), adds the two, and the warp butterfly adds the lanes.  A sweep that continues from the
+// registers, one that restarts from a stored column or a checkpoint, and the site after a rescaling (which re-forms
+// the sum from the rescaled cells instead of scaling the sum) therefore carry the same bits: every refill schedule
+// (eager, lazy, checkpointed at any stride) produces identical columns and totals.
+// ------------------------------------------------------------------------------------------
+template <int NJ>
+__device__ __forceinline__ double lane_sum(const double (&p0)[NJ], const double (&p1)[NJ]) {
+  double la = 0.0, lb = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) { la += p0[j]; lb += p1[j]; }
+  return la + lb;
+}
+template <int NJ>
+__device__ __forceinline__ double lane_dot(const double (&b0)[NJ], const double (&b1)[NJ], const double (&e0)[NJ],
+                                           const double (&e1)[NJ]) {
+  double ya = 0.0, yb = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) { ya = __fma_rn(b0[j], e0[j], ya); yb = __fma_rn(b1[j], e1[j], yb); }
+  return ya + yb;
+}
+
+// ------------------------------------------------------------------------------------------
 // asynchronous global->shared copies (LDGSTS): a warp stages the codon-slot row G[q][s][.] and the
 // emission row of the sites ahead of the one it is computing
 // ------------------------------------------------------------------------------------------

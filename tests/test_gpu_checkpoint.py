@@ -4,11 +4,10 @@ whole matrices give: every proposal total and per-query value, the kept columns 
 whole matrices, the state after accepts against the CPU chain - for ragged and full rows, lazy and eager refills,
 carriers-only escape proposals, strides 2 to 16.
 
-Tolerance.  The cell updates are the same operations in the same order; what differs is WHERE a sweep restarts from
-a kept column.  A restart re-forms the column sum from the stored values (after the x BIG rescale, in another
-order of additions) instead of carrying it, which moves the last bit of what follows: 1e-16 relative per restart,
-the same effect the lazy and the eager refill schedules have on each other for closest_n > 128.  Asserted here:
-1e-13 on totals and per-query values, 1e-13 on kept columns (the contract is 1e-9)."""
+Tolerance: none.  The cell updates are the same operations in the same order, and the column sum a sweep carries is
+defined on the stored column and formed in one order (mcq_sweep_common.cuh, lane_sum / lane_dot), so a sweep that
+restarts from a kept column continues with the bits the whole-matrix sweep had in its registers: totals, per-query
+values and kept columns are asserted equal (RTOL_CK = 0)."""
 import numpy as np
 import pytest
 
@@ -17,7 +16,7 @@ from cpu_chain import CpuState, REC, SEL, ESC, REV, MU
 from problems import make_problem
 from test_gpu_parity import RTOL_LLK, _moves, assert_state_matches, checker, rel
 
-RTOL_CK = 1e-13
+RTOL_CK = 0.0
 
 pytestmark = pytest.mark.gpu
 

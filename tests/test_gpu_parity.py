@@ -151,12 +151,16 @@ def test_proposal_columns_and_selector_flip(api):
     ctx.close()
 
 
+@pytest.mark.parametrize("over", [dict(), dict(L=100, N=150), dict(L=500, N=600, S=60, Q=9), dict(L=1000, N=1100, S=40, Q=6)],
+                         ids=["L20", "L100", "L500", "L1000"])
 @pytest.mark.parametrize("sparse", [0, 1])
-def test_lazy_refills_are_bit_identical_to_eager(api, sparse):
+def test_lazy_refills_are_bit_identical_to_eager(api, sparse, over):
     """Owed refills (MCQ_OPT_LAZY_REFILL) compute the columns the reference would have computed at the
     accept, with the same kernels' arithmetic: every proposal total, every per-query value and the final
-    F/B matrices are bit-identical to the eager schedule over a random chain with many accepts."""
-    p = make_problem("toy", gaps=True)
+    F/B matrices are bit-identical to the eager schedule over a random chain with many accepts - at every number
+    of states per lane (a sweep that restarts from a stored column carries the same column sum as one that
+    continues from its registers: mcq_sweep_common.cuh, lane_sum / lane_dot)."""
+    p = make_problem("toy", gaps=True, **over)
     ctxs = []
     for lazy in (0, 1):
         c = api.Context.from_problem(p)
