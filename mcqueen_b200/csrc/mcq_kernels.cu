@@ -485,12 +485,15 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
     // one bump per group
     const int t = w.t + K;
     const unsigned cur = w.rd[KT];
-    // consumed four sites from now.  The load is unconditional (beyond the range: the word of the last site, ignored
-    // by stage_k): a select on the loaded VALUE would park the warp on the load's latency right here
-    w.rd[KT] = *((t + MCQ_RING <= a.end) ? w.rdp + K : w.rdsafe);
+    // consumed four sites from now.  The likelihood-only sweep loads unconditionally (beyond the range: the word of the
+    // last site, ignored by stage_k): a select on the loaded VALUE parks the warp on the load's latency right here.
+    // The stored sweep keeps the select: measured on one box at 1 250 queries, 0.533 ms against 0.556 ms with the
+    // unconditional load (its stores leave the load/store unit little room; 10 000 queries: no difference)
+    if constexpr (STORE) w.rd[KT] = (t + MCQ_RING <= a.end) ? w.rdp[K] : 0u;
+    else w.rd[KT] = *((t + MCQ_RING <= a.end) ? w.rdp + K : w.rdsafe);
     const bool pre = PRE && t < a.start;
     const double *eq = pre ? ecq_pre : ecq;
-    stage_k<NJ, KT>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.Rp + K,
+    stage_k<NJ, KT, STORE>(g_sh, e_sh, t <= a.end, cur, pre ? tabl_pre : tabl, eq + t, eq != nullptr, w.Rp + K,
                     w.gsrc + K * (64 * NJ), lane);
     if (K == 3) { w.t += 4; w.rdp += 4; w.Rp += 4; w.gsrc += 4 * (64 * NJ); }
   }
@@ -509,7 +512,7 @@ __device__ __forceinline__ void fwd_site(const FwdArgs &a, FwdWarp<NJ> &w, int s
     const double v0 = __fma_rn(stay, w.p0[j], jump) * emis_at(es, g[j >> 1], (j & 1) * 2);
     const double v1 = __fma_rn(stay, w.p1[j], jump) * emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
     w.p0[j] = v0; w.p1[j] = v1;
-    la += v0; lb += v1;
+    if (j == 0) { la = v0; lb = v1; } else { la += v0; lb += v1; }   // (0 + v = v: no add for the first)
   }
   w.tot = warp_sum(la + lb);
   if (w.tot < MCQ_BIGI) {                       // forward_backward.c:163-167
@@ -584,7 +587,7 @@ __device__ __forceinline__ double fwd_cells(FwdWarp<NJ> &w, double invN) {
     const double v0 = __fma_rn(stay, w.p0[j], jump) * w.e0[j];
     const double v1 = __fma_rn(stay, w.p1[j], jump) * w.e1[j];
     w.p0[j] = v0; w.p1[j] = v1;
-    la += v0; lb += v1;
+    if (j == 0) { la = v0; lb = v1; } else { la += v0; lb += v1; }   // (0 + v = v: no add for the first)
   }
   return la + lb;
 }
@@ -960,7 +963,7 @@ struct BwdWarp {
 };
 
 // stage site w.t into ring slot (K + MCQ_PF) & 3 and fetch the descriptor word needed four sites on
-template <int NJ, int K>
+template <int NJ, int K, bool WHOLE = false>
 __device__ __forceinline__ void bwd_stage(const BwdArgs &a, BwdWarp<NJ> &w, unsigned g_sh, unsigned e_sh,
                                           const double *tabl, int bottom, int lane) {
   // (the staging calls run K = 0, 1, 2, 3, 0, ...: the running pointers address the site of K = 0, constant
@@ -968,8 +971,11 @@ __device__ __forceinline__ void bwd_stage(const BwdArgs &a, BwdWarp<NJ> &w, unsi
   constexpr int KT = (K + MCQ_PF) & 3;
   const int t = w.t - K;
   const unsigned cur = w.rd[KT];
-  w.rd[KT] = *((t - MCQ_RING >= bottom) ? w.rdp - K : w.rdsafe);   // (unconditional load: see fwd_site)
-  stage_k<NJ, KT>(g_sh, e_sh, t >= bottom, cur, tabl, w.ecp - K, a.em.ec != nullptr, w.Rp - K,
+  // (see fwd_site: the sweep that stores whole columns keeps the select on the value - 0.510 ms against 0.586 ms at
+  // 1 250 queries -, the checkpointed and pipelined ones load unconditionally)
+  if constexpr (WHOLE) w.rd[KT] = (t - MCQ_RING >= bottom) ? *(w.rdp - K) : 0u;
+  else w.rd[KT] = *((t - MCQ_RING >= bottom) ? w.rdp - K : w.rdsafe);
+  stage_k<NJ, KT, WHOLE>(g_sh, e_sh, t >= bottom, cur, tabl, w.ecp - K, a.em.ec != nullptr, w.Rp - K,
                   w.gsrc - K * (64 * NJ), lane);
   if (K == 3) { w.t -= 4; w.rdp -= 4; w.ecp -= 4; w.Rp -= 4; w.gsrc -= 4 * (64 * NJ); }
 }
@@ -982,7 +988,7 @@ __device__ __forceinline__ void bwd_site(const BwdArgs &a, BwdWarp<NJ> &w, const
                                          const double (&m1)[NJ], double invN) {
   cp_async_wait<MCQ_PF - 1>();   // rows of site s
   __syncwarp();
-  bwd_stage<NJ, K>(a, w, g_sh, e_sh, tabl, bottom, lane);
+  bwd_stage<NJ, K, true>(a, w, g_sh, e_sh, tabl, bottom, lane);
   unsigned g[(2 * NJ + 3) / 4];
   load_slots<NJ, K>(gl, g);
   const double *es = ering + K * MCQ_ES;
@@ -998,7 +1004,7 @@ __device__ __forceinline__ void bwd_site(const BwdArgs &a, BwdWarp<NJ> &w, const
     const double v0 = __fma_rn(stay * w.b0[j], w.e0[j], jump) * m0[j];
     const double v1 = __fma_rn(stay * w.b1[j], w.e1[j], jump) * m1[j];
     w.b0[j] = v0; w.b1[j] = v1;
-    locv += v0; locv2 += v1;
+    if (j == 0) { locv = v0; locv2 = v1; } else { locv += v0; locv2 += v1; }
     locy = __fma_rn(v0, n0, locy); locy2 = __fma_rn(v1, n1, locy2);
     w.e0[j] = n0; w.e1[j] = n1;
   }
@@ -1059,7 +1065,7 @@ __device__ __forceinline__ void bwd_cells(BwdWarp<NJ> &w, const double (&m0)[NJ]
     const double v0 = __fma_rn(stay * w.b0[j], w.e0[j], jump) * m0[j];
     const double v1 = __fma_rn(stay * w.b1[j], w.e1[j], jump) * m1[j];
     w.b0[j] = v0; w.b1[j] = v1;
-    v_a += v0; v_b += v1;
+    if (j == 0) { v_a = v0; v_b = v1; } else { v_a += v0; v_b += v1; }
     y_a = __fma_rn(v0, w.n0[j], y_a); y_b = __fma_rn(v1, w.n1[j], y_b);
     w.e0[j] = w.n0[j]; w.e1[j] = w.n1[j];
   }
@@ -1732,7 +1738,7 @@ __global__ void __launch_bounds__(128) k_column(const FwdArgs a) {
     const double v0 = __fma_rn(stay, p0[j], jump) * emis_at(es, g[j >> 1], (j & 1) * 2);
     const double v1 = __fma_rn(stay, p1[j], jump) * emis_at(es, g[j >> 1], (j & 1) * 2 + 1);
     p0[j] = v0; p1[j] = v1;
-    la += v0; lb += v1;
+    if (j == 0) { la = v0; lb = v1; } else { la += v0; lb += v1; }   // (0 + v = v: no add for the first)
   }
   tot = warp_sum(la + lb);
   if (tot < MCQ_BIGI) {                         // forward_backward.c:163-167

@@ -23,9 +23,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ------------------------------------------------------------------------------------------
 template <int NJ>
 __device__ __forceinline__ double lane_sum(const double (&p0)[NJ], const double (&p1)[NJ]) {
-  double la = 0.0, lb = 0.0;
+  double la = p0[0], lb = p1[0];
 #pragma unroll
-  for (int j = 0; j < NJ; j++) { la += p0[j]; lb += p1[j]; }
+  for (int j = 1; j < NJ; j++) { la += p0[j]; lb += p1[j]; }
   return la + lb;
 }
 template <int NJ>
@@ -74,14 +74,14 @@ __device__ __forceinline__ void cp_async8_if(unsigned sa, const void *gmem, bool
 // of the rings, already offset by this lane's 16 / 8 bytes; gsrc = the site's G row, tabl = the emission
 // table, both offset by this lane's share; ecp = the query's consensus-row value of the site (lane 0 copies
 // it), Rp = the site's recombination probability (lane 1).
-template <int NJ, int KS>
+template <int NJ, int KS, bool RDZ = false>     // RDZ: the caller passes rd = 0 for a site that is not valid
 __device__ __forceinline__ void stage_k(unsigned g_sh, unsigned e_sh, bool valid, unsigned rd,
                                         const double *__restrict__ tabl, const double *__restrict__ ecp, bool has_ec,
                                         const double *__restrict__ Rp, const uint8_t *__restrict__ gsrc, int lane) {
 #pragma unroll
   for (int i = 0; i < (NJ + 7) / 8; i++)
     cp_async16_if(g_sh + KS * (64 * NJ) + 512 * i, gsrc + 512 * i, valid && (lane + 32 * i) * 16 < 64 * NJ);
-  const int kr = valid ? (int)(rd >> MCQ_RD_SHIFT) : 0;   // at most 64 entries: two predicated copies, no loop
+  const int kr = (RDZ || valid) ? (int)(rd >> MCQ_RD_SHIFT) : 0;   // at most 64 entries: two predicated copies, no loop
   const double *row = tabl + (rd & MCQ_RD_MASK);
   const unsigned ed = e_sh + (KS * MCQ_ES + 1) * 8;
   cp_async8_if(ed, row, lane < kr);
