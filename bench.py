@@ -85,6 +85,12 @@ def build_shard(name, q0, q1, device_index, dist=None, world=1):
     ctypes.CDLL("libc.so.6").srandom(SEED & 0x7fffffff)
     closest_all = np.concatenate([api.closest_replay(b, L, skip_first=skip) for b in blocks])
     t2 = time.time()
+    ham_ovl, sel_ovl = api.closest_last_timing()
+    # the kernel times proper: the same call once more with the chunks one after the other (in the pass above they
+    # alternate between two streams, so a chunk's events also span its wait for the other stream's kernels)
+    os.environ["MCQ_CLOSEST_SERIAL"] = "1"
+    api.closest_groups(refs, qs, L, skip_first=skip, device=device_index)
+    del os.environ["MCQ_CLOSEST_SERIAL"]
     ham_ms, sel_ms = api.closest_last_timing()
     closest = np.ascontiguousarray(closest_all[q0:q1])
     cons_q = api.consensus_batch(refs, closest, device=device_index)
@@ -100,8 +106,9 @@ def build_shard(name, q0, q1, device_index, dist=None, world=1):
     p.closest_stats = {
         "shape": f"{refs.shape[0]} refs x {nq} queries on this GPU (of {qs_all.shape[0]}) x {nb} nt, L={L} (BASELINE config 3 when the workload is C4)",
         "hamming_kernel_ms": ham_ms, "select_kernel_ms": sel_ms,
-        "kernel_times": "CUDA events per chunk of queries, summed; chunks alternate between two streams, so the two sums "
-                        "overlap in time (one after the other: profiles/)",
+        "kernel_times": "CUDA events per chunk of queries, summed, from a pass that runs the chunks one after the other; "
+                        "the wall time is of the pass that alternates chunks between two streams",
+        "event_sums_of_the_two_stream_pass_ms": {"hamming": ham_ovl, "select": sel_ovl},
         "wall_seconds_incl_transfers_exchange_and_tie_shuffles": t2 - t1,
         "nt_compares_per_s": refs.shape[0] * nq * nb / (ham_ms * 1e-3) if ham_ms > 0 else None,
         # one 64-bit POPC word per 64 nt per pair: B200 issues 16 POPC.32 lanes/clk/SM
@@ -630,9 +637,12 @@ def main():
             (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
              if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0)
         ctx.enable_timing(1)
-        ctx.propose(api.PROP_REV, w0, w1, value0=1.1)
-        ctx.accept()
-        extras["window_accept_ms"] = ctx.last_timing()[0]
+        best = 1e30
+        for v in (1.1, 1.2, 1.3):        # (the first accept of a process also loads the kernel: best of three)
+            ctx.propose(api.PROP_REV, w0, w1, value0=v)
+            ctx.accept()
+            best = min(best, ctx.last_timing()[0])
+        extras["window_accept_ms"] = best
         extras["closest_L"] = p.closest_stats
         ctx.enable_timing(0)
         # the same evaluation on checkpointed matrices (MCQ_OPT_CHECKPOINT_STRIDE = 4: every fourth column of F kept,

@@ -1304,7 +1304,7 @@ __global__ void __launch_bounds__(32) k_forward_ck(const FwdArgs a) {
     if (lane == 0 && a.llk_out != nullptr) a.llk_out[q] = a.llk_keep[q];
     return;
   }
-  const int S = a.st.S, Ls = a.st.Ls, ck = a.ck, km = ck - 1, NC = a.nc;
+  const int S = a.st.S, Ls = a.st.Ls, ck = a.ck, km = ck - 1, NC = a.nc, cksh = __ffs(ck) - 1;
   const size_t qoff = (size_t)q * NC * Ls;
   const uint8_t *__restrict__ Gl = a.st.G + (size_t)q * S * (64 * NJ) + lane * 16;
   const uint32_t *__restrict__ rdq = a.st.rowdesc + (size_t)q * S;
@@ -1312,11 +1312,11 @@ __global__ void __launch_bounds__(32) k_forward_ck(const FwdArgs a) {
   const double *ecq_pre = a.em_pre.ec ? a.em_pre.ec + (size_t)q * S : nullptr;
   const double *tabl = a.em.tab + lane, *tabl_pre = a.em_pre.tab + lane;
   // the last current checkpoint at or before start - 1 (-1: none, the sweep starts with the seed column)
-  const int cp_start = (a.start / ck) * ck - 1;
+  const int cp_start = (a.start & ~km) - 1;
   int p = cp_start, known = S - 1;
   if (a.fv != nullptr) {
     known = a.fv[q];
-    p = min(p, ((known + 1) / ck) * ck - 1);
+    p = min(p, ((known + 1) & ~km) - 1);
   }
   const int s0 = p + 1;
   double *X0 = const_cast<double *>(a.Fin) + qoff + 2 * lane;
@@ -1378,7 +1378,7 @@ __global__ void __launch_bounds__(32) k_forward_ck(const FwdArgs a) {
     w.cnt = 0;
     w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));
   } else {
-    const int c = p / ck;
+    const int c = p >> cksh;
     const double *__restrict__ Fi = X0 + (size_t)c * Ls + (selq[c] ? delta : 0);
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
@@ -1403,7 +1403,7 @@ __global__ void __launch_bounds__(32) k_forward_ck(const FwdArgs a) {
       w.tot = warp_sum(lane_sum<NJ>(w.p0, w.p1));                                                                   \
     }                                                                                                               \
     if ((s_ & km) == km && !a.no_store) {           /* a checkpoint */                                              \
-      const int c = s_ / ck;                                                                                        \
+      const int c = s_ >> cksh;                     /* ck is a power of two: no division inside the sweep */         \
       const bool pre = s_ < a.start;                                                                                \
       const bool into1 = (selq[c] != 0) != (!a.in_place && !pre);                                                   \
       double *__restrict__ Fs = X0 + (size_t)c * Ls + (into1 ? delta : 0);                                          \
@@ -1444,7 +1444,7 @@ __global__ void __launch_bounds__(32) k_backward_ck(const BwdArgs a) {
   __shared__ __align__(16) double s_e[MCQ_RING][MCQ_ES];
   const int q = blockIdx.x, lane = threadIdx.x;
   if (a.active != nullptr && a.active[(size_t)q * a.st.H + a.active_hla] == 0) return;
-  const int S = a.st.S, L = a.st.L, Ls = a.st.Ls, ck = a.ck, km = ck - 1, NC = a.nc;
+  const int S = a.st.S, L = a.st.L, Ls = a.st.Ls, ck = a.ck, km = ck - 1, NC = a.nc, cksh = __ffs(ck) - 1;
   const int bottom = a.bottom;
   // checkpoints of sites >= vb are current
   const int vb = a.bv != nullptr ? a.bv[q] : a.update + 1;
@@ -1476,10 +1476,10 @@ __global__ void __launch_bounds__(32) k_backward_ck(const BwdArgs a) {
   BwdWarp<NJ> w;
   // the first current checkpoint at or above `bottom`, or the seed column (forward_backward.c:197-203)
   const int lo = max(vb, bottom);
-  const int p = ((lo + km) / ck) * ck;
+  const int p = (lo + km) & ~km;
   int s;                                        // the first column to compute
   if (p <= S - 1) {
-    const int c = p / ck;
+    const int c = p >> cksh;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       w.b0[j] = 0.0; w.b1[j] = 0.0;
@@ -1495,7 +1495,7 @@ __global__ void __launch_bounds__(32) k_backward_ck(const BwdArgs a) {
     for (int j = 0; j < NJ; j++) { w.b0[j] = m0[j]; w.b1[j] = m1[j]; }
     w.cnt = 0;
     if (((S - 1) & km) == 0) {
-      const int c = (S - 1) / ck;
+      const int c = (S - 1) >> cksh;
 #pragma unroll
       for (int j = 0; j < NJ; j++)
         if (inrow[j]) __stcs(reinterpret_cast<double2 *>(Bq + (size_t)c * Ls + 64 * j), make_double2(w.b0[j], w.b1[j]));
@@ -1567,7 +1567,7 @@ __global__ void __launch_bounds__(32) k_backward_ck(const BwdArgs a) {
       w.sx = warp_sum(lane_dot<NJ>(w.b0, w.b1, w.e0, w.e1));                                                        \
     }                                                                                                               \
     if ((s_ & km) == 0) {                           /* a checkpoint */                                              \
-      const int c = s_ / ck;                                                                                        \
+      const int c = s_ >> cksh;                     /* ck is a power of two: no division inside the sweep */         \
       _Pragma("unroll") for (int j = 0; j < NJ; j++)                                                                \
         if (FULL || inrow[j])                                                                                       \
           __stcs(reinterpret_cast<double2 *>(Bq + (size_t)c * Ls + 64 * j), make_double2(w.b0[j], w.b1[j]));        \

@@ -46,7 +46,7 @@ if hasattr(api, "OPT_CHECKPOINT_STRIDE"):
                      p.n_site_codons, p.site_codons)
     ck.set_params(mu=p.mu, kappa=p.kappa, phi=p.phi, prior=p.prior, R=p.R, omega=p.omega,
                   rate_out=p.rate_out_of_codons(), esc=p.esc, rev=p.rev[0])
-    ck.init_state()
+    print(f"{ROOT[-8:]} Q={nq} checkpoint 4: init_state llk {ck.init_state()!r}  full_llk {ck.full_llk(True)!r}  llk_only {ck.llk_only(True)!r}")
     for rep in range(2):
         t0 = time.perf_counter()
         for _ in range(30):
