@@ -309,8 +309,8 @@ __global__ void __launch_bounds__(512) k_select_row(const uint16_t *__restrict__
   // here): the element of rank n among the head is an upper bound U of the row's element of rank n, and only
   // the few per cent of the remaining entries that are <= U are counted at all.
   const int nhead = min(nvec, max(16 * n, 4096) >> 3);
-  __shared__ unsigned s_cand, s_kept;
-  if (threadIdx.x == 0) { s_cand = 0; s_kept = 0; }
+  __shared__ unsigned s_cand;
+  if (threadIdx.x == 0) s_cand = 0;
   for (int v0 = wid * 32; v0 < nhead; v0 += blockDim.x) {
     const int v = v0 + lane;
     uint4 x = make_uint4(0, 0, 0, 0);
