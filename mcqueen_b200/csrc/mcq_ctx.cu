@@ -546,7 +546,7 @@ extern "C" int mcq_ctx_upload_static(mcq_ctx *c, const char *ref_triplets, const
     ALLOC(c->hla, (size_t)Q * H);
     ALLOC(c->G, (size_t)Q * S * c->Lg);
     if (!c->st_trip) ALLOC(c->st_trip, (size_t)N * S);
-    ALLOC(c->st_trip_pad, (size_t)N * ((S + 31) / 32 * 32));
+    ALLOC(c->st_trip_pad, (size_t)N * mcq_gather_pitch(S));
     ALLOC(c->st_cons, (size_t)Q * 3 * S);
     ALLOC(c->st_closest, (size_t)Q * L);
     ALLOC(c->st_slot_of, (size_t)S * 64);

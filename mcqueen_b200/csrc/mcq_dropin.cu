@@ -73,7 +73,7 @@ struct Scratch {
     Lg = 64;
     while (Lg < Ls) Lg *= 2;
     DK(cudaMalloc((void **)&trip, (size_t)L * S));
-    DK(cudaMalloc((void **)&trip_pad, (size_t)L * ((S + 31) / 32 * 32)));
+    DK(cudaMalloc((void **)&trip_pad, (size_t)L * mcq_gather_pitch(S)));
     DK(cudaMalloc((void **)&cons, (size_t)3 * S));
     DK(cudaMalloc((void **)&closest, (size_t)L * sizeof(int)));
     DK(cudaMalloc((void **)&aoff, (size_t)(S + 1) * sizeof(int)));

@@ -150,6 +150,9 @@ struct EmisArgs {
 
 // launchers (mcq_kernels.cu); all asynchronous on `stream`, return cudaGetLastError()
 cudaError_t mcq_launch_tables_init();
+// pitch of the re-pitched reference slot rows (trip_pad, N rows): whole 128-byte lines, so that a gather tile (64
+// sites) never reads past a row
+static inline size_t mcq_gather_pitch(int S) { return ((size_t)S + 127) / 128 * 128; }
 // the query-independent tables of the gather: trip_tab [ceil32(S)][128] (triplet -> slot per site) and trip_pad
 // [N][ceil32(S)], the SLOT of every reference codon (both scratch)
 cudaError_t mcq_launch_gather_prepare(const int8_t *ref_triplets, int8_t *trip_pad, const uint8_t *slot_of /*[S][64]*/,

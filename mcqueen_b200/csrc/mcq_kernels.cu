@@ -113,85 +113,128 @@ __global__ void __launch_bounds__(256) k_slot_rows(const int8_t *__restrict__ sr
   }
 }
 
-// One block per (query, 32 sites).  A PAIR of lanes owns eight consecutive physical positions of the G rows (=
-// eight copy states): the even lane takes the block's first 16 sites, the odd lane the other 16, so the two
-// 16-byte loads of a pair fall into one aligned 32-byte sector of the reference's slot row and a warp
-// instruction touches 16 sectors, not 32.  What is left is a byte transpose in registers: per site a lane packs
-// the eight slots of its references and stores its 8 bytes, the even (odd) lanes of a warp together 128
-// contiguous bytes of one G row.
-__global__ void __launch_bounds__(256, 4) k_gather(const int8_t *__restrict__ slot_rows, int Sp,
-                                                   const int8_t *__restrict__ trip,
-                                                   const int *__restrict__ closest,
-                                                   const int8_t *__restrict__ cons_nucls,
-                                                   const uint8_t *__restrict__ slot_of,
-                                                   uint8_t *__restrict__ G, int S, int L, int Lg, int N,
-                                                   int *__restrict__ err) {
-  const int q = blockIdx.y;
-  const int lg2 = 31 - __clz(Lg >> 5);              // log2(2 * NJ)
-  const int pos = 8 * (threadIdx.x >> 1), sb = 16 * (threadIdx.x & 1);   // first position, first site
-  if (pos >= Lg) return;
-  // the eight references; padding states (r >= L) read row 0 and are overwritten with MCQ_NOSLOT below
-  unsigned pad0 = 0, pad1 = 0;                      // byte k = 0xFF when position pos + k (+4) is padding
-  int refs[8];
+// One block per query (and share of its 64-site tiles).  The slot rows of the query's references are brought
+// into shared memory first, 64 bytes of each per tile (cp.async, 16 bytes per lane: a warp instruction covers
+// 64-byte runs of 8 references), the next tile travelling while the current one is turned.  Then a lane owns
+// SIXTEEN consecutive physical positions of the G rows (= sixteen copy states) and sixteen sites: a 16 x 16 byte
+// transpose in registers, after which the lane stores 16 bytes per site and the LG/16 lanes of a row together one
+// whole G row per store instruction (512 contiguous bytes at closest_n = 500).  Shared layout: the row of position
+// pos sits at slot (pos % 16) * (LG/16) + pos / 16, its four 16-byte chunks XOR-swizzled with bits 1-2 of pos / 16:
+// the 16-byte reads of a quarter warp then fall into eight different bank groups.
+#define MCQ_GT 64
+template <int LG>                  // LG = padded states per G row (64 ... 1024): every offset below is an immediate
+__global__ void __launch_bounds__(LG / 4 < 32 ? 32 : LG / 4) k_gather(const int8_t *__restrict__ slot_rows, int Sp,
+                                                const int8_t *__restrict__ trip,
+                                                const int *__restrict__ closest,
+                                                const int8_t *__restrict__ cons_nucls,
+                                                const uint8_t *__restrict__ slot_of,
+                                                uint8_t *__restrict__ G, int S, int L, int N,
+                                                int *__restrict__ err) {
+  constexpr int GT = MCQ_GT, CPR = GT / 16;                         // sites per tile, 16-byte chunks per reference
+  constexpr int LPR = LG / 16;                                      // lanes per G row
+  constexpr int NT = LG / 4 < 32 ? 32 : LG / 4;                     // threads per block
+  constexpr int LG2 = LG == 64 ? 1 : LG == 128 ? 2 : LG == 256 ? 3 : LG == 512 ? 4 : 5;   // log2(2 * NJ)
+  extern __shared__ __align__(16) uint8_t g_rows[];                 // two buffers [LG][GT] of slot bytes, then int refs[LG]
+  int *s_ref = reinterpret_cast<int *>(g_rows + 2 * (size_t)LG * GT);
+  const int q = blockIdx.y, ntiles = (S + GT - 1) / GT;
+  // the references of the LG positions; padding states (r >= L) read row 0 and are overwritten below
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int r = g_state_of(pos + k, lg2);
+  for (int p = threadIdx.x; p < LG; p += NT) {
+    const int r = g_state_of(p, LG2);
     int ref = 0;
     if (r < L) {
       ref = closest[(size_t)q * L + r];
       if ((unsigned)ref >= (unsigned)N) { ref = 0; *err = 2; }   // reported by mcq_ctx_upload_static
-    } else if (k < 4) pad0 |= 0xFFu << (8 * k);
-    else pad1 |= 0xFFu << (8 * (k - 4));
-    refs[k] = ref;
+    }
+    s_ref[p] = ref;
   }
-  const unsigned fill0 = pad0 & (MCQ_NOSLOT * 0x01010101u), fill1 = pad1 & (MCQ_NOSLOT * 0x01010101u);
-  // the block's share of the 32-site blocks (the reference list is fetched once for all of them)
-  for (int s0 = blockIdx.x * 32; s0 < S; s0 += gridDim.x * 32) {
-  unsigned w[8][4];
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const uint4 a = *reinterpret_cast<const uint4 *>(slot_rows + (size_t)refs[k] * Sp + s0 + sb);
-    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
-  }
-  uint8_t *dst = G + ((size_t)q * S + s0 + sb) * Lg + pos;
-  const int nrow = min(16, S - s0 - sb);            // rows of this half inside the genome (may be <= 0)
-  unsigned worst = 0;
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    // byte (i & 3) of word (i >> 2) of each of the eight rows -> two words
-    const unsigned sel2 = 0x0040u + (i & 3) * 0x0011u;            // {b of x, b of y, 0, 0}
-    const unsigned p01 = __byte_perm(w[0][i >> 2], w[1][i >> 2], sel2), p23 = __byte_perm(w[2][i >> 2], w[3][i >> 2], sel2);
-    const unsigned p45 = __byte_perm(w[4][i >> 2], w[5][i >> 2], sel2), p67 = __byte_perm(w[6][i >> 2], w[7][i >> 2], sel2);
-    unsigned lo = __byte_perm(p01, p23, 0x5410), hi = __byte_perm(p45, p67, 0x5410);
-    lo = (lo & ~pad0) | fill0;
-    hi = (hi & ~pad1) | fill1;
-    worst |= lo | hi;
-    if (i < nrow) *reinterpret_cast<uint2 *>(dst + (size_t)i * Lg) = make_uint2(lo, hi);
-  }
-  // every real slot value is below 0x80, MCQ_NEEDS_CONS is not: bit 7 of the OR says whether any occurred
-  if (worst & 0x80808080u) {
-    // triplet_to_codon (amino_acids.c:50-66): unknown bases take the query's local consensus
-#pragma unroll 1
-    for (int i = 0; i < nrow; i++) {
-      const int s = s0 + sb + i;
-#pragma unroll 1
-      for (int k = 0; k < 8; k++) {
-        if (((k < 4 ? pad0 >> (8 * k) : pad1 >> (8 * (k - 4))) & 1) != 0) continue;
-        int ref = 0;                                  // (refs[] indexed by a loop variable would go to local memory)
-#pragma unroll
-        for (int kk = 0; kk < 8; kk++) if (kk == k) ref = refs[kk];
-        const unsigned tt = (uint8_t)trip[(size_t)ref * S + s];
-        int d0 = tt / 25, d1 = (tt / 5) % 5, d2 = tt % 5;
-        if (tt >= 125 || (d0 != 4 && d1 != 4 && d2 != 4)) continue;
-        const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
-        if (d0 == 4) d0 = cn[0];
-        if (d1 == 4) d1 = cn[1];
-        if (d2 == 4) d2 = cn[2];
-        dst[(size_t)i * Lg + k] = slot_of[(size_t)s * 64 + (d0 * 16 + d1 * 4 + d2)];
+  __syncthreads();
+  // chunk c = threadIdx.x + i * NT: NT is a multiple of CPR, so a thread keeps its 16-byte part of the row
+  // segment and walks the positions in steps of NT / CPR
+  const int part = threadIdx.x % CPR, p0 = threadIdx.x / CPR;
+  const unsigned sm0 = (unsigned)__cvta_generic_to_shared(g_rows);
+  auto fetch = [&](int tile, int buf) {             // one commit group per call (empty past the last tile)
+    if (tile < ntiles) {
+      const int8_t *src = slot_rows + tile * GT + part * 16;
+      const unsigned sm = sm0 + buf * (LG * GT);
+#pragma unroll 8
+      for (int i = 0; i < LG * CPR / NT; i++) {
+        const int p = p0 + i * (NT / CPR);
+        const unsigned slot = (unsigned)(p & 15) * LPR + (unsigned)(p >> 4);
+        cp_async16_if(sm + slot * GT + (((unsigned)part ^ ((unsigned)(p >> 5) & 3u)) << 4),
+                      src + (size_t)s_ref[p] * (size_t)Sp, true);
       }
     }
+    cp_async_commit();
+  };
+  const int l = threadIdx.x % LPR, sg = threadIdx.x / LPR;   // position group (16 l ...), group of 16 sites in the tile
+  const int pos = 16 * l;
+  const bool mine = sg < CPR;
+  unsigned pad[4] = {0, 0, 0, 0};                   // byte k = 0xFF when position pos + 4 m + k is padding
+#pragma unroll
+  for (int k = 0; k < 16; k++)
+    if (g_state_of(pos + k, LG2) >= L) pad[k >> 2] |= 0xFFu << (8 * (k & 3));
+  const bool any_pad = (pad[0] | pad[1] | pad[2] | pad[3]) != 0;
+  const unsigned chunk = (((unsigned)sg ^ ((unsigned)(l >> 1) & 3u)) & (CPR - 1)) << 4;
+  // the block's tiles, the rows of the next one travelling while this one is turned
+  fetch(blockIdx.x, 0);
+  int it = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    fetch(tile + gridDim.x, (it + 1) & 1);
+    cp_async_wait<1>();
+    __syncthreads();
+    const int s0 = tile * GT + 16 * sg;               // this lane's sixteen sites
+    const int nrow = min(16, S - s0);                 // ... inside the genome (may be <= 0)
+    if (mine && nrow > 0) {
+      const uint8_t *rows = g_rows + (it & 1) * (LG * GT) + l * GT + chunk;
+      unsigned w[16][4];
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(rows + k * (LPR * GT));
+        w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+      }
+      uint8_t *dst = G + ((size_t)q * S + s0) * LG + pos;
+      unsigned worst = 0;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        // byte (i & 3) of word (i >> 2) of each of the sixteen rows -> four words
+        const unsigned sel2 = 0x0040u + (i & 3) * 0x0011u;            // {b of x, b of y, 0, 0}
+        unsigned o[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const unsigned p01 = __byte_perm(w[4 * m][i >> 2], w[4 * m + 1][i >> 2], sel2);
+          const unsigned p23 = __byte_perm(w[4 * m + 2][i >> 2], w[4 * m + 3][i >> 2], sel2);
+          o[m] = __byte_perm(p01, p23, 0x5410);
+          if (any_pad) o[m] = (o[m] & ~pad[m]) | (pad[m] & (MCQ_NOSLOT * 0x01010101u));
+          worst |= o[m];
+        }
+        if (i < nrow) __stcs(reinterpret_cast<uint4 *>(dst + i * LG), make_uint4(o[0], o[1], o[2], o[3]));   // streaming
+      }
+      // every real slot value is below 0x80, MCQ_NEEDS_CONS is not: bit 7 of the OR says whether any occurred
+      if (worst & 0x80808080u) {
+        // triplet_to_codon (amino_acids.c:50-66): unknown bases take the query's local consensus
+#pragma unroll 1
+        for (int i = 0; i < nrow; i++) {
+          const int s = s0 + i;
+#pragma unroll 1
+          for (int k = 0; k < 16; k++) {
+            if (g_state_of(pos + k, LG2) >= L) continue;
+            const unsigned tt = (uint8_t)trip[(size_t)s_ref[pos + k] * S + s];
+            int d0 = tt / 25, d1 = (tt / 5) % 5, d2 = tt % 5;
+            if (tt >= 125 || (d0 != 4 && d1 != 4 && d2 != 4)) continue;
+            const int8_t *cn = cons_nucls + (size_t)q * 3 * S + 3 * s;
+            if (d0 == 4) d0 = cn[0];
+            if (d1 == 4) d1 = cn[1];
+            if (d2 == 4) d2 = cn[2];
+            dst[(size_t)i * LG + k] = slot_of[(size_t)s * 64 + (d0 * 16 + d1 * 4 + d2)];
+          }
+        }
+      }
+    }
+    __syncthreads();                                  // the buffer is refilled two tiles on
   }
-  }   // site blocks
+  cp_async_wait<0>();
 }
 
 // '0'/'1' characters (load_data.c:125-157) -> 0/1, in place
@@ -200,10 +243,11 @@ __global__ void __launch_bounds__(256) k_hla_bits(uint8_t *hla, size_t n) {
   if (i < n) hla[i] = (hla[i] == '1');
 }
 
-// query-independent part: the per-site triplet -> slot table and the re-pitched reference rows
+// query-independent part: the per-site triplet -> slot table and the re-pitched reference rows (pitch
+// mcq_gather_pitch(S): whole 128-byte lines)
 cudaError_t mcq_launch_gather_prepare(const int8_t *ref_triplets, int8_t *trip_pad, const uint8_t *slot_of,
                                       uint8_t *trip_tab, int S, int N, cudaStream_t stream) {
-  const int sblocks = (S + 31) / 32, Sp = sblocks * 32;
+  const int sblocks = (S + 31) / 32, Sp = (int)mcq_gather_pitch(S);
   k_trip_table<<<sblocks * 32, 128, 0, stream>>>(slot_of, trip_tab, S);
   const size_t words = (size_t)N * (Sp / 4);
   unsigned blocks = (unsigned)((words + 255) / 256);
@@ -212,23 +256,46 @@ cudaError_t mcq_launch_gather_prepare(const int8_t *ref_triplets, int8_t *trip_p
   return cudaGetLastError();
 }
 
+template <int LG>
+static cudaError_t launch_gather_lg(const int8_t *trip_pad, int Sp, const int8_t *trip, const int *closest,
+                                    const int8_t *cons_nucls, const uint8_t *slot_of, uint8_t *G, int Q, int S, int L,
+                                    int N, int *err, cudaStream_t stream) {
+  constexpr int threads = LG / 4 < 32 ? 32 : LG / 4;
+  constexpr size_t smem = 2 * (size_t)LG * MCQ_GT + (size_t)LG * sizeof(int);
+  // (per device; the largest case, closest_n = 1024, takes 128 KB + 4 KB)
+  cudaError_t e = cudaFuncSetAttribute(k_gather<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int ntiles = (S + MCQ_GT - 1) / MCQ_GT;
+  for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
+    int nq = Q - q0 < 65535 ? Q - q0 : 65535;
+    // about eight tiles per block, fetched one ahead; more blocks per query when there are few queries
+    int bx = (ntiles + 7) / 8;
+    while (bx < ntiles && (long long)bx * nq < 148 * 6) bx *= 2;
+    dim3 grid(bx < ntiles ? bx : ntiles, nq);
+    k_gather<LG><<<grid, threads, smem, stream>>>(trip_pad, Sp, trip, closest + (size_t)q0 * L,
+                                                  cons_nucls + (size_t)q0 * 3 * S, slot_of,
+                                                  G + (size_t)q0 * S * LG, S, L, N, err);
+  }
+  return cudaGetLastError();
+}
+
 // G rows (and the 0/1 HLA flags) of Q queries; the pointers address the first of them
 cudaError_t mcq_launch_gather(const int8_t *trip_pad, const int8_t *trip, const int *closest, const int8_t *cons_nucls,
                               const uint8_t *slot_of, uint8_t *G, uint8_t *hla_chars, int Q,
                               int S, int L, int Lg, int N, int H, int *err, cudaStream_t stream) {
-  const int sblocks = (S + 31) / 32, Sp = sblocks * 32;
+  const int Sp = (int)mcq_gather_pitch(S);
   if (hla_chars != nullptr) {
     const size_t n = (size_t)Q * H;
     k_hla_bits<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(hla_chars, n);
   }
-  const int threads = Lg / 4 < 32 ? 32 : Lg / 4;
-  for (int q0 = 0; q0 < Q; q0 += 65535) {   // gridDim.y is limited to 65535
-    int nq = Q - q0 < 65535 ? Q - q0 : 65535;
-    dim3 grid((sblocks + 3) / 4, nq);            // four 32-site blocks per thread block
-    k_gather<<<grid, threads, 0, stream>>>(trip_pad, Sp, trip, closest + (size_t)q0 * L, cons_nucls + (size_t)q0 * 3 * S,
-                                           slot_of, G + (size_t)q0 * S * Lg, S, L, Lg, N, err);
+  switch (Lg) {
+    case 64: return launch_gather_lg<64>(trip_pad, Sp, trip, closest, cons_nucls, slot_of, G, Q, S, L, N, err, stream);
+    case 128: return launch_gather_lg<128>(trip_pad, Sp, trip, closest, cons_nucls, slot_of, G, Q, S, L, N, err, stream);
+    case 256: return launch_gather_lg<256>(trip_pad, Sp, trip, closest, cons_nucls, slot_of, G, Q, S, L, N, err, stream);
+    case 512: return launch_gather_lg<512>(trip_pad, Sp, trip, closest, cons_nucls, slot_of, G, Q, S, L, N, err, stream);
+    case 1024: return launch_gather_lg<1024>(trip_pad, Sp, trip, closest, cons_nucls, slot_of, G, Q, S, L, N, err, stream);
+    default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
