@@ -154,7 +154,7 @@ cudaError_t mcq_launch_tables_init();
 // sites) never reads past a row
 static inline size_t mcq_gather_pitch(int S) { return ((size_t)S + 127) / 128 * 128; }
 // the query-independent tables of the gather: trip_tab [ceil32(S)][128] (triplet -> slot per site) and trip_pad
-// [N][ceil32(S)], the SLOT of every reference codon (both scratch)
+// [N][mcq_gather_pitch(S)], the SLOT of every reference codon (both scratch)
 cudaError_t mcq_launch_gather_prepare(const int8_t *ref_triplets, int8_t *trip_pad, const uint8_t *slot_of /*[S][64]*/,
                                       uint8_t *trip_tab, int S, int N, cudaStream_t stream);
 // G rows of Q queries (pointers address the first of them); trip = ref_triplets on the device (for the triplets with
